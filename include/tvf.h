@@ -1,0 +1,151 @@
+/* tvf.h -- C ABI of libtvf.so: batched linear three-view pose estimation on
+ * NVIDIA B200 (sm_100a), a drop-in for the linear hot path of
+ * LauraFJulia/TFT_vs_Fund.  Every entry point below replaces one MATLAB
+ * function of the reference (file:line cited per function); B = 1 reproduces
+ * the reference signature exactly, B > 1 is the batched superset.
+ *
+ * Conventions
+ *   - all data FP64, MATLAB column-major, caller-owned buffers;
+ *   - a batch is the trailing dimension: `Corresp` is 6 x n x B (48 contiguous
+ *     bytes per point), `CalM` 9 x 3 (shared) or 9 x 3 x B, poses 3 x 4 x B,
+ *     tensors 3 x 3 x 3 x B, `Reconst` 3 x n x B;
+ *   - plain pointers and sizes only; no exceptions cross the boundary;
+ *   - return value: < 0 argument/runtime error (tvf_last_error() has the text),
+ *     0 success, > 0 number of problems whose status word is non-zero;
+ *   - `status` (int32 per problem, may be NULL) is a bit set, see TVF_ST_*;
+ *   - one handle per host thread and per GPU; calls on a handle are serialised
+ *     by the caller (MATLAB calls MEX on its interpreter thread only);
+ *   - there is no CPU fallback: without a CUDA device tvf_create() fails.
+ *
+ * Results agree with the reference up to the sign/scale freedom the reference
+ * itself leaves open: T and F up to sign (unit Frobenius norm / arbitrary
+ * scale), triangulated homogeneous points up to sign.
+ */
+#ifndef TVF_H_
+#define TVF_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tvf_context* tvf_handle_t;
+
+/* return codes */
+#define TVF_OK 0
+#define TVF_ERR_ARG (-1)            /* bad pointer / size / unsupported shape            */
+#define TVF_ERR_CUDA (-2)           /* CUDA runtime error                                */
+#define TVF_ERR_TOO_FEW_POINTS (-3) /* linearF.m:35-37: N < 8 (or N mismatch)            */
+#define TVF_ERR_NOMEM (-4)
+
+/* per-problem status bits */
+#define TVF_ST_EIG_NOCONV 1    /* inverse iteration hit its cap: the design matrix has no usable spectral gap */
+#define TVF_ST_EPIPOLE_ZERO 2  /* sign(V(end)) == 0 at R_t_from_TFT.m:50,55                                   */
+#define TVF_ST_NO_POSE_2 4     /* all 4 cheirality votes < 0 or NaN: MATLAB leaves R_f undefined (:91-104)    */
+#define TVF_ST_NO_POSE_3 8
+#define TVF_ST_NONFINITE 16    /* non-finite value in R_t / reprojection error                                */
+
+/* the message linearF.m:36 raises; gateways re-raise it verbatim */
+#define TVF_LINEARF_ERRMSG \
+    "At least 8 correspondences are necessary to compute the fundamental matrix linearly\\n"
+
+/* ---- lifetime ------------------------------------------------------------------------- */
+int tvf_version(void);
+int tvf_device_count(void);
+int tvf_create(tvf_handle_t* out, int device);
+void tvf_destroy(tvf_handle_t h);
+const char* tvf_last_error(tvf_handle_t h); /* h may be NULL: error of the last failed tvf_create */
+int tvf_device(tvf_handle_t h);
+/* problems per internal chunk (work-space size / pipelining granularity); 0 restores the default */
+int tvf_set_chunk(tvf_handle_t h, int64_t problems);
+/* stream used by the *_dev entry points: a cudaStream_t (NULL = the legacy default stream).
+ * Until this is called -- and again after tvf_use_own_stream() -- the handle's own stream is used. */
+int tvf_set_stream(tvf_handle_t h, void* cuda_stream);
+int tvf_use_own_stream(tvf_handle_t h);
+int tvf_synchronize(tvf_handle_t h);
+/* pinned host memory, so the host-pointer entry points overlap copies with compute */
+void* tvf_host_alloc(size_t bytes);
+void tvf_host_free(void* p);
+
+/* ---- method entry points (host pointers; copies are inside the call) ------------------- */
+
+/* [R_t_2,R_t_3,Reconst,T,iter] = LinearTFTPoseEstimation(Corresp,CalM)
+ * TFT_methods/LinearTFTPoseEstimation.m:1,45-62 (iter is the constant 0 and is not returned here).
+ * corresp 6 x n x B; calm 9 x 3 (calm_batched = 0) or 9 x 3 x B (1).
+ * Outputs (any may be NULL): Rt2, Rt3 3x4xB; reconst 3 x n x B; T 3x3x3xB (pixel coordinates,
+ * unit Frobenius norm); repr_err B = ReprError({K1[I|0],K2*R_t_2,K3*R_t_3},Corresp,Reconst)
+ * (auxiliar_functions/ReprError.m:39-65, what experiments.m:112-114 evaluates next). */
+int tvf_linear_tft_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,
+                        int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
+                        int32_t* status);
+
+/* [R_t_2,R_t_3,Reconst,T,iter] = LinearFPoseEstimation(Corresp,CalM)
+ * F_methods/LinearFPoseEstimation.m:1,42-78.  Same arguments; T = TFT_from_P(...) (:78).
+ * F21, F31 (3x3xB each, may be NULL) expose the fundamental matrices of :55-56.
+ * n < 8 returns TVF_ERR_TOO_FEW_POINTS (linearF.m:35-37). */
+int tvf_linear_f_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,
+                      int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
+                      double* F21, double* F31, int32_t* status);
+
+/* [T,P1,P2,P3] = linearTFT(p1,p2,p3)   TFT_methods/linearTFT.m:1,36-91.
+ * p1,p2,p3: rows x n x B with rows = 2, or 3 for homogeneous points (:39-43).
+ * T 3x3x3xB; P2,P3 3x4xB (may be NULL); P1 is eye(3,4) (:88) and is left to the caller. */
+int tvf_linear_tft(tvf_handle_t h, const double* p1, const double* p2, const double* p3, int rows, int n,
+                   int64_t B, double* T, double* P2, double* P3, int32_t* status);
+
+/* F = linearF(p1,p2)   F_methods/linearF.m:1,32-62.  n < 8 -> TVF_ERR_TOO_FEW_POINTS. */
+int tvf_linear_f(tvf_handle_t h, const double* p1, const double* p2, int rows, int n, int64_t B, double* F,
+                 int32_t* status);
+
+/* ---- the smaller reference functions, batched ------------------------------------------- */
+
+/* [new_points,N_matrix] = Normalize2Ddata(points)   auxiliar_functions/Normalize2Ddata.m:1,33-39.
+ * points 2 x n x B -> new_points 2 x n x B, N_matrix 3 x 3 x B (either may be NULL). */
+int tvf_normalize2d(tvf_handle_t h, const double* points, int n, int64_t B, double* new_points, double* N_matrix);
+
+/* T_new = transform_TFT(T_old,M1,M2,M3,inverse)   TFT_methods/transform_TFT.m:1,32-49.
+ * M1..M3 3x3 shared (mats_batched = 0) or 3x3xB. */
+int tvf_transform_tft(tvf_handle_t h, const double* T_old, const double* M1, const double* M2, const double* M3,
+                      int mats_batched, int inverse, int64_t B, double* T_new);
+
+/* [R_t_2,R_t_3] = R_t_from_TFT(T,CalM,Corresp)   TFT_methods/R_t_from_TFT.m:1,40-106. */
+int tvf_rt_from_tft(tvf_handle_t h, const double* T, const double* calm, int calm_batched, const double* corresp,
+                    int n, int64_t B, double* Rt2, double* Rt3, int32_t* status);
+
+/* T = TFT_from_P(P1,P2,P3)   TFT_methods/TFT_from_P.m:1,25-33.  P* 3x4xB. */
+int tvf_tft_from_p(tvf_handle_t h, const double* P1, const double* P2, const double* P3, int64_t B, double* T);
+
+/* space_points = triangulation3D(Pcam,image_points)   auxiliar_functions/triangulation3D.m:1,32-64.
+ * P: 3 x 4 x M (cams_batched = 0) or 3 x 4 x M x B; image_points (rows*M) x n x B with rows = 2 or 3;
+ * X 4 x n x B unit null vectors (sign arbitrary, as in the reference).  M = 2 or 3 (the only cases
+ * on the path); other M return TVF_ERR_ARG. */
+int tvf_triangulate(tvf_handle_t h, const double* P, int M, int cams_batched, const double* image_points, int rows,
+                    int n, int64_t B, double* X);
+
+/* error = ReprError(ProjM,Corresp,Points3D)   auxiliar_functions/ReprError.m:1,39-65.
+ * points3d NULL -> triangulate first (:43-44); else pts_rows = 3 or 4 (:45-48). */
+int tvf_repr_error(tvf_handle_t h, const double* P, int M, int cams_batched, const double* corresp, int rows, int n,
+                   int64_t B, const double* points3d, int pts_rows, double* err);
+
+/* [rot_err,t_err] = AngError(R_t_true,R_t_est)   auxiliar_functions/AngError.m:1,21-28 (degrees).
+ * Rt_true 3x4 (true_batched = 0) or 3x4xB. */
+int tvf_ang_error(tvf_handle_t h, const double* Rt_true, int true_batched, const double* Rt_est, int64_t B,
+                  double* rot_err, double* t_err);
+
+/* ---- device-pointer forms (inputs/outputs already in HBM; asynchronous on the handle's stream,
+ *      return 0 without synchronising -- read `status` after tvf_synchronize) ----------------- */
+int tvf_linear_tft_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,
+                            int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
+                            int32_t* status);
+int tvf_linear_f_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,
+                          int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
+                          double* F21, double* F31, int32_t* status);
+
+/* number of kernel launches issued through this handle since creation (bench bookkeeping) */
+int64_t tvf_launch_count(tvf_handle_t h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVF_H_ */

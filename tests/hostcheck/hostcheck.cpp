@@ -1,0 +1,81 @@
+// TEST-ONLY: compiles the host/device headers of tft_vs_fund_b200/csrc with g++
+// so the thread-level math that the CUDA kernels inline can be checked against
+// the oracle on a machine without a GPU.  Not linked into the product library,
+// never on the product path.
+#include "tvf_pose.cuh"
+
+using namespace tvf;
+
+extern "C" {
+
+void hc_null3(const double* M, double* v) { null3(M, v); }
+
+void hc_svd3(const double* M, double* U, double* s, double* V) { svd3_full(M, U, s, V); }
+
+void hc_inv3(const double* M, double* Mi) { inv3(M, Mi); }
+
+void hc_transform_tft(const double* T, const double* M1, const double* M2, const double* M3, int inverse, double* Tn) {
+    transform_tft(T, M1, M2, M3, inverse, Tn);
+}
+
+void hc_tft_from_p(const double* P1, const double* P2, const double* P3, double* T) { tft_from_p(P1, P2, P3, T); }
+
+void hc_epipoles(const double* T, double* e21, double* e31) { tft_epipoles(T, e21, e31); }
+
+void hc_onb3(const double* e, double* u1, double* u2) { onb3(e, u1, u2); }
+
+void hc_ang_error(const double* a, const double* b, double* r, double* t) { ang_error(a, b, r, t); }
+
+// rows: M x 4 row-major
+int hc_dlt(const double* rows, int M, double* x) {
+    int it = 0;
+    if (M == 4) {
+        double a[4][4];
+        for (int i = 0; i < 16; ++i) a[i / 4][i % 4] = rows[i];
+        dlt_null<4>(a, x, &it);
+    } else {
+        double a[6][4];
+        for (int i = 0; i < 24; ++i) a[i / 4][i % 4] = rows[i];
+        dlt_null<6>(a, x, &it);
+    }
+    return it;
+}
+
+// Whole pose tail on one problem, stage by stage exactly as the kernels chain them.
+// mode 0: `model` is T (27, pixel coordinates); mode 1: `model` is [F21(9) F31(9)].
+int hc_pose_tail(int mode, const double* model, const double* CalM, const double* corresp, int n,
+                 double* Rt2, double* Rt3, double* reconst, double* repr, int* votes8) {
+    double cand[CAND_SIZE];
+    int st = (mode == 0) ? candidates_from_tft(model, CalM, cand) : candidates_from_f(model, model + 9, CalM, cand);
+    double P1[12];
+    load_K1_as_P1(CalM, P1);
+    int vote[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int nan2 = 0, nan3 = 0;
+    for (int i = 0; i < n; ++i) {
+        const double* p = corresp + 6 * i;
+        cheirality_point(P1, cand, p[0], p[1], p[2], p[3], vote, &nan2);
+        cheirality_point(P1, cand + CAND_PAIR, p[0], p[1], p[4], p[5], vote + 4, &nan3);
+    }
+    for (int k = 0; k < 8; ++k) votes8[k] = vote[k];
+    const int k2 = select_candidate(vote, nan2), k3 = select_candidate(vote + 4, nan3);
+    if (k2 < 0) st |= ST_NO_POSE_2;
+    if (k3 < 0) st |= ST_NO_POSE_3;
+    if (k2 < 0 || k3 < 0) return st;
+    double P2[12], P3[12];
+    selected_pose(cand, k2, Rt2, P2);
+    selected_pose(cand + CAND_PAIR, k3, Rt3, P3);
+    double num = 0.0, den = 0.0;
+    for (int i = 0; i < n; ++i) {
+        double a, b;
+        scale_point(P1, P2, P3, P3 + 9, corresp + 6 * i, &a, &b);
+        num += a; den += b;
+    }
+    const double lam = -num / den;
+    for (int i = 0; i < 3; ++i) { Rt3[9 + i] *= lam; P3[9 + i] *= lam; }
+    double sq = 0.0;
+    for (int i = 0; i < n; ++i) sq += final_point(P1, P2, P3, corresp + 6 * i, reconst + 3 * i);
+    *repr = sqrt(sq / (3.0 * n));
+    return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,84 @@
+"""The thread-level device math of csrc/tvf_math.cuh + tvf_pose.cuh, compiled for the host
+(TEST-ONLY build, tests/hostcheck) and compared with the oracle.  Same source the kernels inline."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle as o
+from conftest import rel_frob_up_to_sign, assert_pose_close
+
+dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+cm = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).T).ravel()   # 2-D column-major
+
+
+def test_null3_and_svd3(hostcheck):
+    rs = np.random.RandomState(0)
+    for trial in range(50):
+        M = rs.standard_normal((3, 3))
+        if trial % 3 == 0:                                   # exactly rank 2
+            M = np.outer(rs.standard_normal(3), rs.standard_normal(3)) + np.outer(rs.standard_normal(3), rs.standard_normal(3))
+        v = np.zeros(3); hostcheck.hc_null3(dp(cm(M)), dp(v))
+        vr = o.matlab_svd(M)[2][:, -1]
+        assert rel_frob_up_to_sign(v, vr) < 1e-11
+        U = np.zeros(9); s = np.zeros(3); V = np.zeros(9)
+        if trial % 3 == 0:
+            hostcheck.hc_svd3(dp(cm(M)), dp(U), dp(s), dp(V))
+            U = U.reshape(3, 3).T; V = V.reshape(3, 3).T
+            assert np.allclose(U @ np.diag(s) @ V.T, M, atol=1e-13)
+            assert np.allclose(U.T @ U, np.eye(3), atol=1e-12) and abs(np.linalg.det(U) * np.linalg.det(V) - 1) < 2.1
+
+
+def test_transform_tft_and_tft_from_p(hostcheck):
+    rs = np.random.RandomState(1)
+    for inverse in (0, 1):
+        T = rs.standard_normal((3, 3, 3))
+        Ms = [rs.standard_normal((3, 3)) + 2 * np.eye(3) for _ in range(3)]
+        out = np.zeros(27)
+        hostcheck.hc_transform_tft(dp(T.ravel(order="F").copy()), dp(cm(Ms[0])), dp(cm(Ms[1])), dp(cm(Ms[2])), inverse, dp(out))
+        ref = o.transform_TFT(T, *Ms, inverse)
+        assert np.abs(out.reshape(3, 3, 3, order="F") - ref).max() < 1e-13
+    Ps = [rs.standard_normal((3, 4)) for _ in range(3)]
+    out = np.zeros(27)
+    hostcheck.hc_tft_from_p(dp(cm(Ps[0])), dp(cm(Ps[1])), dp(cm(Ps[2])), dp(out))
+    assert np.abs(out.reshape(3, 3, 3, order="F") - o.TFT_from_P(*Ps)).max() < 1e-13
+
+
+def test_onb_and_angerror(hostcheck):
+    rs = np.random.RandomState(2)
+    for _ in range(20):
+        e = rs.standard_normal(3); e /= np.linalg.norm(e)
+        u1 = np.zeros(3); u2 = np.zeros(3)
+        hostcheck.hc_onb3(dp(e), dp(u1), dp(u2))
+        Q = np.column_stack([e, u1, u2])
+        assert np.abs(Q.T @ Q - np.eye(3)).max() < 1e-14
+    A = np.column_stack([np.eye(3), [1.0, 2, 3]])
+    c, s = np.cos(0.7), np.sin(0.7)
+    B = np.column_stack([np.array([[1, 0, 0], [0, c, -s], [0, s, c]]), [0.5, -1, 2.0]])
+    r = np.zeros(1); t = np.zeros(1)
+    hostcheck.hc_ang_error(dp(cm(A)), dp(cm(B)), dp(r), dp(t))
+    rr, tt = o.AngError(A, B)
+    assert abs(r[0] - rr) < 1e-11 and abs(t[0] - tt) < 1e-11
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("n,noise", [(8, 1.0), (20, 0.0), (20, 1.0), (20, 3.0), (60, 2.0)])
+def test_pose_tail_matches_oracle(hostcheck, mode, n, noise):
+    for seed in (1, 2, 3):
+        CalM, R_t0, Cr, _ = o.experiments_subsample(n, noise, seed)
+        K = CalM[:3]
+        if mode == 0:
+            R2, R3, Rec, T, _ = o.LinearTFTPoseEstimation(Cr, CalM)
+            model = T.ravel(order="F").copy()
+        else:
+            R2, R3, Rec, T, _, F21, F31 = o.LinearFPoseEstimation(Cr, CalM, return_F=True)
+            model = np.concatenate([cm(F21), cm(F31)])
+        rep = o.ReprError([K @ np.eye(3, 4), K @ R2, K @ R3], Cr, Rec)
+        Rt2 = np.zeros(12); Rt3 = np.zeros(12); rec = np.zeros(3 * n); rp = np.zeros(1); v = np.zeros(8, dtype=np.int32)
+        st = hostcheck.hc_pose_tail(mode, dp(model), dp(cm(CalM)), dp(cm(Cr)), n, dp(Rt2), dp(Rt3), dp(rec), dp(rp),
+                                    v.ctypes.data_as(C.POINTER(C.c_int)))
+        assert st == 0
+        got = (Rt2.reshape(3, 4, order="F"), Rt3.reshape(3, 4, order="F"), rec.reshape(n, 3).T, T, rp[0])
+        assert_pose_close((R2, R3, Rec, T, rep), got, "n=%d noise=%g seed=%d" % (n, noise, seed))
+        # votes: one candidate sees every point in front of both cameras
+        assert sorted(v[:4])[-1] == 2 * n and sorted(v[4:])[-1] == 2 * n

@@ -1,0 +1,585 @@
+// tvf_api.cu -- the C ABI of include/tvf.h: handle, work-space arenas, chunked
+// host-pointer entry points (H2D / kernels / D2H pipelined over three streams)
+// and asynchronous device-pointer entry points.  No CPU fallback lives here:
+// every entry point either runs the CUDA kernels or returns an error.
+#include "../../include/tvf.h"
+
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "tvf_kernels.h"
+#include "tvf_pose.cuh"
+
+using namespace tvf;
+
+namespace {
+
+constexpr int NSLOT = 3;
+constexpr int NSCRATCH = 12;
+constexpr int64_t DEFAULT_CHUNK = 65536;
+constexpr size_t ARENA_BUDGET = 384u << 20;   // bytes of per-slot work space the automatic chunk aims for
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    char* arena = nullptr;
+    size_t cap = 0;
+};
+
+std::string g_create_error;
+
+}  // namespace
+
+struct tvf_context {
+    int device = 0;
+    int sm_count = 148;
+    Slot slot[NSLOT];
+    cudaStream_t user_stream = nullptr;
+    bool use_user_stream = false;
+    int64_t chunk_user = 0;
+    void* scratch[NSCRATCH] = {};
+    size_t scratch_cap[NSCRATCH] = {};
+    std::string err;
+    int64_t launches = 0;
+};
+
+namespace {
+
+int fail(tvf_handle_t h, int code, const std::string& msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+#define TVF_CK(call)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(h, TVF_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));     \
+    } while (0)
+
+int ensure_arena(tvf_handle_t h, Slot& s, size_t bytes) {
+    if (s.cap >= bytes) return TVF_OK;
+    if (s.arena) { TVF_CK(cudaStreamSynchronize(s.stream)); TVF_CK(cudaFree(s.arena)); s.arena = nullptr; s.cap = 0; }
+    const size_t want = bytes + (bytes >> 3);
+    cudaError_t e = cudaMalloc(&s.arena, want);
+    if (e != cudaSuccess) return fail(h, TVF_ERR_NOMEM, std::string("cudaMalloc(arena): ") + cudaGetErrorString(e));
+    s.cap = want;
+    return TVF_OK;
+}
+
+int ensure_scratch(tvf_handle_t h, int id, size_t bytes, void** out) {
+    if (h->scratch_cap[id] < bytes) {
+        if (h->scratch[id]) { TVF_CK(cudaDeviceSynchronize()); TVF_CK(cudaFree(h->scratch[id])); h->scratch[id] = nullptr; h->scratch_cap[id] = 0; }
+        cudaError_t e = cudaMalloc(&h->scratch[id], bytes ? bytes : 8);
+        if (e != cudaSuccess) return fail(h, TVF_ERR_NOMEM, std::string("cudaMalloc(scratch): ") + cudaGetErrorString(e));
+        h->scratch_cap[id] = bytes ? bytes : 8;
+    }
+    *out = h->scratch[id];
+    return TVF_OK;
+}
+
+// bump allocator over a slot arena (256-byte aligned pieces)
+struct Carver {
+    char* base; size_t off = 0;
+    explicit Carver(char* b) : base(b) {}
+    template <typename T> T* take(size_t count) {
+        T* p = reinterpret_cast<T*>(base + off);
+        off += (count * sizeof(T) + 255) & ~size_t(255);
+        return p;
+    }
+};
+
+struct ChunkBufs {
+    double* in; double* calm; double* T; double* F; double* cand; int* votes; double* scale;
+    double* Rt2; double* Rt3; double* reconst; double* repr; int* status;
+};
+
+size_t carve(char* base, int n, int64_t C, bool host_io, bool calm_batched, ChunkBufs* out) {
+    Carver c(base);
+    ChunkBufs b{};
+    b.T = c.take<double>(27 * C);
+    b.F = c.take<double>(18 * C);
+    b.cand = c.take<double>((size_t)CAND_SIZE * C);
+    b.votes = c.take<int>(10 * C);
+    b.scale = c.take<double>(2 * C);
+    b.status = c.take<int>(C);
+    if (host_io) {
+        b.in = c.take<double>((size_t)6 * n * C);
+        b.calm = calm_batched ? c.take<double>(27 * C) : nullptr;
+        b.Rt2 = c.take<double>(12 * C);
+        b.Rt3 = c.take<double>(12 * C);
+        b.reconst = c.take<double>((size_t)3 * n * C);
+        b.repr = c.take<double>(C);
+    }
+    if (out) *out = b;
+    return c.off;
+}
+
+int64_t pick_chunk(tvf_handle_t h, int n, int64_t B, bool host_io) {
+    int64_t c = h->chunk_user > 0 ? h->chunk_user : DEFAULT_CHUNK;
+    if (h->chunk_user <= 0) {   // automatic: keep one slot's work space near ARENA_BUDGET
+        size_t payload = (27 + 18 + CAND_SIZE + 2) * 8 + 11 * 4;
+        if (host_io) payload += (size_t)(6 * n + 27 + 24 + 3 * n + 1) * 8;
+        const int64_t fit = (int64_t)(ARENA_BUDGET / payload);
+        if (c > fit) c = fit;
+    }
+    if (c < 1) c = 1;
+    if (c > B) c = B;
+    return c;
+}
+
+enum Method { METHOD_TFT = 0, METHOD_F = 1 };
+
+// kernels of one chunk; all pointers are device pointers
+int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double* d_corresp, const double* d_calm,
+                   int calm_batched, int n, int64_t Bc, double* d_T, double* d_F, double* d_cand, int* d_votes,
+                   double* d_scale, double* d_Rt2, double* d_Rt3, double* d_reconst, double* d_repr, int* d_status) {
+    CoreInput in{};
+    in.p1 = d_corresp; in.p2 = nullptr; in.p3 = nullptr; in.packed = 1; in.rows = 2; in.n = n; in.B = Bc; in.normalize = 1;
+    PoseTailArgs a{};
+    a.corresp = d_corresp; a.calm = d_calm; a.calm_batched = calm_batched; a.n = n; a.B = Bc;
+    a.cand = d_cand; a.votes = d_votes; a.scale = d_scale;
+    a.Rt2 = d_Rt2; a.Rt3 = d_Rt3; a.reconst = d_reconst; a.repr_err = d_repr; a.status = d_status;
+    if (method == METHOD_TFT) {
+        launch_tft_core(in, d_T, nullptr, nullptr, d_status, h->sm_count, st);
+        launch_candidates(0, d_T, a, st);
+        launch_pose_tail(a, h->sm_count, st);
+        h->launches += 5;
+    } else {
+        launch_f_core(in, d_F, d_status, h->sm_count, st);
+        launch_candidates(1, d_F, a, st);
+        launch_pose_tail(a, h->sm_count, st);
+        if (d_T != nullptr) { launch_tft_from_pose(d_calm, calm_batched, d_Rt2, d_Rt3, Bc, d_T, st); h->launches += 1; }
+        h->launches += 5;
+    }
+    TVF_CK(cudaGetLastError());
+    return TVF_OK;
+}
+
+int check_pose_args(tvf_handle_t h, const void* corresp, const void* calm, int n, int64_t B, Method m) {
+    if (!h) return TVF_ERR_ARG;
+    if (!corresp || !calm) return fail(h, TVF_ERR_ARG, "corresp/calm must not be NULL");
+    if (B < 0 || n < 1) return fail(h, TVF_ERR_ARG, "need n >= 1 and B >= 0");
+    if (m == METHOD_F && n < 8) return fail(h, TVF_ERR_TOO_FEW_POINTS, TVF_LINEARF_ERRMSG);
+    return TVF_OK;
+}
+
+int count_flagged(const int32_t* st, int64_t B) {
+    int64_t c = 0;
+    for (int64_t i = 0; i < B; ++i) c += (st[i] != 0);
+    return (int)(c > 0x7fffffff ? 0x7fffffff : c);
+}
+
+int pose_host(tvf_handle_t h, Method method, const double* corresp, const double* calm, int calm_batched, int n,
+              int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21,
+              double* F31, int32_t* status) {
+    int rc = check_pose_args(h, corresp, calm, n, B, method);
+    if (rc != TVF_OK) return rc;
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    const int64_t C = pick_chunk(h, n, B, true);
+    const size_t need = carve(nullptr, n, C, true, calm_batched != 0, nullptr);
+    double* d_calm_shared = nullptr;
+    if (!calm_batched) {
+        void* p; rc = ensure_scratch(h, 0, 27 * sizeof(double), &p); if (rc) return rc;
+        d_calm_shared = (double*)p;
+        TVF_CK(cudaMemcpy(d_calm_shared, calm, 27 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    std::vector<int32_t> st_tmp;
+    int32_t* st_host = status;
+    if (!st_host) { st_tmp.resize((size_t)B); st_host = st_tmp.data(); }
+
+    int64_t done = 0; int ci = 0;
+    while (done < B) {
+        const int64_t Bc = (B - done < C) ? (B - done) : C;
+        Slot& s = h->slot[ci % NSLOT];
+        TVF_CK(cudaStreamSynchronize(s.stream));        // slot reuse: its previous chunk (incl. D2H) is finished
+        rc = ensure_arena(h, s, need); if (rc) return rc;
+        ChunkBufs b; carve(s.arena, n, C, true, calm_batched != 0, &b);
+        TVF_CK(cudaMemcpyAsync(b.in, corresp + done * 6 * n, (size_t)Bc * 6 * n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        const double* d_calm = d_calm_shared;
+        if (calm_batched) {
+            TVF_CK(cudaMemcpyAsync(b.calm, calm + done * 27, (size_t)Bc * 27 * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+            d_calm = b.calm;
+        }
+        rc = run_pose_chunk(h, s.stream, method, b.in, d_calm, calm_batched, n, Bc,
+                            (method == METHOD_TFT || T) ? b.T : nullptr, b.F, b.cand, b.votes, b.scale, b.Rt2, b.Rt3,
+                            b.reconst, b.repr, b.status);
+        if (rc) return rc;
+        if (Rt2) TVF_CK(cudaMemcpyAsync(Rt2 + done * 12, b.Rt2, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (Rt3) TVF_CK(cudaMemcpyAsync(Rt3 + done * 12, b.Rt3, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (reconst) TVF_CK(cudaMemcpyAsync(reconst + done * 3 * n, b.reconst, (size_t)Bc * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (T) TVF_CK(cudaMemcpyAsync(T + done * 27, b.T, (size_t)Bc * 27 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (repr_err) TVF_CK(cudaMemcpyAsync(repr_err + done, b.repr, (size_t)Bc * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (method == METHOD_F && F21)
+            TVF_CK(cudaMemcpy2DAsync(F21 + done * 9, 72, b.F, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
+        if (method == METHOD_F && F31)
+            TVF_CK(cudaMemcpy2DAsync(F31 + done * 9, 72, b.F + 9, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
+        TVF_CK(cudaMemcpyAsync(st_host + done, b.status, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        done += Bc; ++ci;
+    }
+    for (int i = 0; i < NSLOT; ++i) TVF_CK(cudaStreamSynchronize(h->slot[i].stream));
+    return count_flagged(st_host, B);
+}
+
+int pose_dev(tvf_handle_t h, Method method, const double* corresp, const double* calm, int calm_batched, int n,
+             int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21,
+             double* F31, int32_t* status) {
+    int rc = check_pose_args(h, corresp, calm, n, B, method);
+    if (rc != TVF_OK) return rc;
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Slot& s = h->slot[0];
+    cudaStream_t st = h->use_user_stream ? h->user_stream : s.stream;
+    const int64_t C = pick_chunk(h, n, B, false);
+    // internal buffers only; Rt2/Rt3 are needed internally by the F method's TFT_from_P, so stage them if absent
+    const size_t need = carve(nullptr, n, C, false, false, nullptr) + (size_t)(24 * C) * sizeof(double) + 512;
+    rc = ensure_arena(h, s, need); if (rc) return rc;
+    ChunkBufs b; const size_t used = carve(s.arena, n, C, false, false, &b);
+    double* tmpRt2 = reinterpret_cast<double*>(s.arena + used);
+    double* tmpRt3 = tmpRt2 + 12 * C;
+    for (int64_t done = 0; done < B; done += C) {
+        const int64_t Bc = (B - done < C) ? (B - done) : C;
+        double* dT = T ? T + done * 27 : (method == METHOD_TFT ? b.T : nullptr);
+        double* dRt2 = Rt2 ? Rt2 + done * 12 : tmpRt2;
+        double* dRt3 = Rt3 ? Rt3 + done * 12 : tmpRt3;
+        rc = run_pose_chunk(h, st, method, corresp + done * 6 * n, calm + (calm_batched ? done * 27 : 0), calm_batched, n,
+                            Bc, dT, b.F, b.cand, b.votes, b.scale, dRt2, dRt3, reconst ? reconst + done * 3 * n : nullptr,
+                            repr_err ? repr_err + done : nullptr, status ? status + done : b.status);
+        if (rc) return rc;
+        if (method == METHOD_F && F21)
+            TVF_CK(cudaMemcpy2DAsync(F21 + done * 9, 72, b.F, 144, 72, (size_t)Bc, cudaMemcpyDeviceToDevice, st));
+        if (method == METHOD_F && F31)
+            TVF_CK(cudaMemcpy2DAsync(F31 + done * 9, 72, b.F + 9, 144, 72, (size_t)Bc, cudaMemcpyDeviceToDevice, st));
+    }
+    return TVF_OK;
+}
+
+// small helper for the stand-alone functions: upload, run, download on slot 0
+struct Up {
+    tvf_handle_t h; cudaStream_t st; int rc = TVF_OK; int next = 1;
+    explicit Up(tvf_handle_t hh) : h(hh), st(hh->slot[0].stream) {}
+    template <typename T> T* in(const T* host, size_t count) {
+        if (rc) return nullptr;
+        void* p; rc = ensure_scratch(h, next++, count * sizeof(T), &p);
+        if (rc) return nullptr;
+        if (host && count) {
+            cudaError_t e = cudaMemcpyAsync(p, host, count * sizeof(T), cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) { rc = fail(h, TVF_ERR_CUDA, cudaGetErrorString(e)); return nullptr; }
+        }
+        return (T*)p;
+    }
+    template <typename T> T* out(size_t count) { return in<T>(nullptr, count); }
+    template <typename T> void back(T* host, const T* dev, size_t count) {
+        if (rc || !host) return;
+        cudaError_t e = cudaMemcpyAsync(host, dev, count * sizeof(T), cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = fail(h, TVF_ERR_CUDA, cudaGetErrorString(e));
+    }
+    int finish() {
+        if (rc) return rc;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) return fail(h, TVF_ERR_CUDA, cudaGetErrorString(e));
+        return TVF_OK;
+    }
+};
+
+}  // namespace
+
+// =========================================================================== C ABI
+extern "C" {
+
+int tvf_version(void) { return 100; }
+
+int tvf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int tvf_create(tvf_handle_t* out, int device) {
+    tvf_handle_t h = nullptr;
+    if (!out) return fail(nullptr, TVF_ERR_ARG, "out must not be NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, TVF_ERR_CUDA, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                                               " (libtvf has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, TVF_ERR_ARG, "device index out of range");
+    TVF_CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    TVF_CK(cudaGetDeviceProperties(&prop, device));
+    h = new tvf_context();
+    h->device = device;
+    h->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < NSLOT; ++i) {
+        e = cudaStreamCreateWithFlags(&h->slot[i].stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) { std::string m = cudaGetErrorString(e); tvf_destroy(h); return fail(nullptr, TVF_ERR_CUDA, m); }
+    }
+    *out = h;
+    return TVF_OK;
+}
+
+void tvf_destroy(tvf_handle_t h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < NSLOT; ++i) {
+        if (h->slot[i].stream) { cudaStreamSynchronize(h->slot[i].stream); cudaStreamDestroy(h->slot[i].stream); }
+        if (h->slot[i].arena) cudaFree(h->slot[i].arena);
+    }
+    for (int i = 0; i < NSCRATCH; ++i)
+        if (h->scratch[i]) cudaFree(h->scratch[i]);
+    delete h;
+}
+
+const char* tvf_last_error(tvf_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int tvf_device(tvf_handle_t h) { return h ? h->device : -1; }
+
+int tvf_set_chunk(tvf_handle_t h, int64_t problems) {
+    if (!h || problems < 0) return TVF_ERR_ARG;
+    h->chunk_user = problems;
+    return TVF_OK;
+}
+
+int tvf_set_stream(tvf_handle_t h, void* cuda_stream) {
+    if (!h) return TVF_ERR_ARG;
+    h->user_stream = (cudaStream_t)cuda_stream;   // NULL is the legacy default stream
+    h->use_user_stream = true;
+    return TVF_OK;
+}
+
+int tvf_use_own_stream(tvf_handle_t h) {
+    if (!h) return TVF_ERR_ARG;
+    h->use_user_stream = false;
+    return TVF_OK;
+}
+
+int tvf_synchronize(tvf_handle_t h) {
+    if (!h) return TVF_ERR_ARG;
+    TVF_CK(cudaSetDevice(h->device));
+    for (int i = 0; i < NSLOT; ++i) TVF_CK(cudaStreamSynchronize(h->slot[i].stream));
+    if (h->use_user_stream) TVF_CK(cudaStreamSynchronize(h->user_stream));
+    return TVF_OK;
+}
+
+void* tvf_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+
+void tvf_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int64_t tvf_launch_count(tvf_handle_t h) { return h ? h->launches : 0; }
+
+int tvf_linear_tft_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
+                        double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, int32_t* status) {
+    return pose_host(h, METHOD_TFT, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, nullptr, nullptr, status);
+}
+
+int tvf_linear_f_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
+                      double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21, double* F31,
+                      int32_t* status) {
+    return pose_host(h, METHOD_F, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, F21, F31, status);
+}
+
+int tvf_linear_tft_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
+                            double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, int32_t* status) {
+    return pose_dev(h, METHOD_TFT, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, nullptr, nullptr, status);
+}
+
+int tvf_linear_f_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
+                          double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21, double* F31,
+                          int32_t* status) {
+    return pose_dev(h, METHOD_F, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, F21, F31, status);
+}
+
+int tvf_linear_tft(tvf_handle_t h, const double* p1, const double* p2, const double* p3, int rows, int n, int64_t B,
+                   double* T, double* P2, double* P3, int32_t* status) {
+    if (!h) return TVF_ERR_ARG;
+    if (!p1 || !p2 || !p3 || !T) return fail(h, TVF_ERR_ARG, "p1,p2,p3,T must not be NULL");
+    if ((rows != 2 && rows != 3) || n < 1 || B < 0) return fail(h, TVF_ERR_ARG, "rows must be 2 or 3, n >= 1, B >= 0");
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    const size_t np = (size_t)rows * n * B;
+    CoreInput in{};
+    in.p1 = u.in(p1, np); in.p2 = u.in(p2, np); in.p3 = u.in(p3, np);
+    in.packed = 0; in.rows = rows; in.n = n; in.B = B; in.normalize = 0;
+    double* dT = u.out<double>(27 * (size_t)B);
+    double* dP2 = u.out<double>(12 * (size_t)B);
+    double* dP3 = u.out<double>(12 * (size_t)B);
+    int* dst = u.out<int>((size_t)B);
+    if (u.rc) return u.rc;
+    launch_tft_core(in, dT, dP2, dP3, dst, h->sm_count, u.st);
+    h->launches += 1;
+    std::vector<int32_t> tmp; int32_t* sth = status;
+    if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }
+    u.back(T, dT, 27 * (size_t)B); u.back(P2, dP2, 12 * (size_t)B); u.back(P3, dP3, 12 * (size_t)B);
+    u.back(sth, (const int32_t*)dst, (size_t)B);
+    int rc = u.finish();
+    return rc ? rc : count_flagged(sth, B);
+}
+
+int tvf_linear_f(tvf_handle_t h, const double* p1, const double* p2, int rows, int n, int64_t B, double* F,
+                 int32_t* status) {
+    if (!h) return TVF_ERR_ARG;
+    if (!p1 || !p2 || !F) return fail(h, TVF_ERR_ARG, "p1,p2,F must not be NULL");
+    if ((rows != 2 && rows != 3) || B < 0) return fail(h, TVF_ERR_ARG, "rows must be 2 or 3, B >= 0");
+    if (n < 8) return fail(h, TVF_ERR_TOO_FEW_POINTS, TVF_LINEARF_ERRMSG);
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    const size_t np = (size_t)rows * n * B;
+    CoreInput in{};
+    in.p1 = u.in(p1, np); in.p2 = u.in(p2, np); in.p3 = nullptr;
+    in.packed = 0; in.rows = rows; in.n = n; in.B = B; in.normalize = 0;
+    double* dF = u.out<double>(9 * (size_t)B);
+    int* dst = u.out<int>((size_t)B);
+    if (u.rc) return u.rc;
+    launch_f_core(in, dF, dst, h->sm_count, u.st);
+    h->launches += 1;
+    std::vector<int32_t> tmp; int32_t* sth = status;
+    if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }
+    u.back(F, dF, 9 * (size_t)B);
+    u.back(sth, (const int32_t*)dst, (size_t)B);
+    int rc = u.finish();
+    return rc ? rc : count_flagged(sth, B);
+}
+
+int tvf_normalize2d(tvf_handle_t h, const double* points, int n, int64_t B, double* new_points, double* N_matrix) {
+    if (!h) return TVF_ERR_ARG;
+    if (!points || n < 1 || B < 0) return fail(h, TVF_ERR_ARG, "points must not be NULL, n >= 1");
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    const double* d = u.in(points, (size_t)2 * n * B);
+    double* o = u.out<double>((size_t)2 * n * B);
+    double* N = u.out<double>(9 * (size_t)B);
+    if (u.rc) return u.rc;
+    launch_normalize2d(d, n, B, o, N, u.st); h->launches += 1;
+    u.back(new_points, o, (size_t)2 * n * B); u.back(N_matrix, N, 9 * (size_t)B);
+    return u.finish();
+}
+
+int tvf_transform_tft(tvf_handle_t h, const double* T_old, const double* M1, const double* M2, const double* M3,
+                      int mats_batched, int inverse, int64_t B, double* T_new) {
+    if (!h) return TVF_ERR_ARG;
+    if (!T_old || !M1 || !M2 || !M3 || !T_new || B < 0) return fail(h, TVF_ERR_ARG, "NULL argument");
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    const size_t nm = mats_batched ? 9 * (size_t)B : 9;
+    const double* t = u.in(T_old, 27 * (size_t)B);
+    const double* m1 = u.in(M1, nm); const double* m2 = u.in(M2, nm); const double* m3 = u.in(M3, nm);
+    double* o = u.out<double>(27 * (size_t)B);
+    if (u.rc) return u.rc;
+    launch_transform_tft(t, m1, m2, m3, mats_batched, inverse, B, o, u.st); h->launches += 1;
+    u.back(T_new, o, 27 * (size_t)B);
+    return u.finish();
+}
+
+int tvf_rt_from_tft(tvf_handle_t h, const double* T, const double* calm, int calm_batched, const double* corresp, int n,
+                    int64_t B, double* Rt2, double* Rt3, int32_t* status) {
+    if (!h) return TVF_ERR_ARG;
+    if (!T || !calm || !corresp || n < 1 || B < 0) return fail(h, TVF_ERR_ARG, "NULL argument or bad size");
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    PoseTailArgs a{};
+    const double* dT = u.in(T, 27 * (size_t)B);
+    a.corresp = u.in(corresp, (size_t)6 * n * B);
+    a.calm = u.in(calm, calm_batched ? 27 * (size_t)B : 27);
+    a.calm_batched = calm_batched; a.n = n; a.B = B;
+    a.cand = u.out<double>((size_t)CAND_SIZE * B);
+    a.votes = u.out<int>(10 * (size_t)B);
+    a.scale = u.out<double>(2 * (size_t)B);
+    a.Rt2 = u.out<double>(12 * (size_t)B); a.Rt3 = u.out<double>(12 * (size_t)B);
+    a.status = u.out<int>((size_t)B);
+    if (u.rc) return u.rc;
+    TVF_CK(cudaMemsetAsync(a.status, 0, (size_t)B * sizeof(int), u.st));
+    launch_candidates(0, dT, a, u.st);
+    launch_pose_tail(a, h->sm_count, u.st);
+    h->launches += 4;
+    std::vector<int32_t> tmp; int32_t* sth = status;
+    if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }
+    u.back(Rt2, a.Rt2, 12 * (size_t)B); u.back(Rt3, a.Rt3, 12 * (size_t)B);
+    u.back(sth, (const int32_t*)a.status, (size_t)B);
+    int rc = u.finish();
+    return rc ? rc : count_flagged(sth, B);
+}
+
+int tvf_tft_from_p(tvf_handle_t h, const double* P1, const double* P2, const double* P3, int64_t B, double* T) {
+    if (!h) return TVF_ERR_ARG;
+    if (!P1 || !P2 || !P3 || !T || B < 0) return fail(h, TVF_ERR_ARG, "NULL argument");
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    const double* a = u.in(P1, 12 * (size_t)B); const double* b = u.in(P2, 12 * (size_t)B); const double* c = u.in(P3, 12 * (size_t)B);
+    double* o = u.out<double>(27 * (size_t)B);
+    if (u.rc) return u.rc;
+    launch_tft_from_p(a, b, c, B, o, u.st); h->launches += 1;
+    u.back(T, o, 27 * (size_t)B);
+    return u.finish();
+}
+
+int tvf_triangulate(tvf_handle_t h, const double* P, int M, int cams_batched, const double* image_points, int rows, int n,
+                    int64_t B, double* X) {
+    if (!h) return TVF_ERR_ARG;
+    if (!P || !image_points || !X || n < 1 || B < 0) return fail(h, TVF_ERR_ARG, "NULL argument or bad size");
+    if (M != 2 && M != 3) return fail(h, TVF_ERR_ARG, "triangulation3D: only M = 2 or 3 views are supported");
+    if (rows != 2 && rows != 3) return fail(h, TVF_ERR_ARG, "rows must be 2 or 3");   // triangulation3D.m:46-47
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    const double* dP = u.in(P, (size_t)12 * M * (cams_batched ? B : 1));
+    const double* dp = u.in(image_points, (size_t)rows * M * n * B);
+    double* o = u.out<double>((size_t)4 * n * B);
+    if (u.rc) return u.rc;
+    launch_triangulate(dP, M, cams_batched, dp, rows, n, B, o, u.st); h->launches += 1;
+    u.back(X, o, (size_t)4 * n * B);
+    return u.finish();
+}
+
+int tvf_repr_error(tvf_handle_t h, const double* P, int M, int cams_batched, const double* corresp, int rows, int n,
+                   int64_t B, const double* points3d, int pts_rows, double* err) {
+    if (!h) return TVF_ERR_ARG;
+    if (!P || !corresp || !err || n < 1 || B < 0) return fail(h, TVF_ERR_ARG, "NULL argument or bad size");
+    if (M != 2 && M != 3) return fail(h, TVF_ERR_ARG, "ReprError: only M = 2 or 3 views are supported");
+    if (rows != 2 && rows != 3) return fail(h, TVF_ERR_ARG, "rows must be 2 or 3");
+    if (points3d && pts_rows != 3 && pts_rows != 4) return fail(h, TVF_ERR_ARG, "pts_rows must be 3 or 4");
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    const double* dP = u.in(P, (size_t)12 * M * (cams_batched ? B : 1));
+    const double* dc = u.in(corresp, (size_t)rows * M * n * B);
+    const double* dx = points3d ? u.in(points3d, (size_t)pts_rows * n * B) : nullptr;
+    double* o = u.out<double>((size_t)B);
+    if (u.rc) return u.rc;
+    launch_repr_error(dP, M, cams_batched, dc, rows, n, B, dx, pts_rows, o, u.st); h->launches += 1;
+    u.back(err, o, (size_t)B);
+    return u.finish();
+}
+
+int tvf_ang_error(tvf_handle_t h, const double* Rt_true, int true_batched, const double* Rt_est, int64_t B,
+                  double* rot_err, double* t_err) {
+    if (!h) return TVF_ERR_ARG;
+    if (!Rt_true || !Rt_est || !rot_err || !t_err || B < 0) return fail(h, TVF_ERR_ARG, "NULL argument");
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    const double* a = u.in(Rt_true, (size_t)12 * (true_batched ? B : 1));
+    const double* e = u.in(Rt_est, 12 * (size_t)B);
+    double* r = u.out<double>((size_t)B); double* t = u.out<double>((size_t)B);
+    if (u.rc) return u.rc;
+    launch_ang_error(a, true_batched, e, B, r, t, u.st); h->launches += 1;
+    u.back(rot_err, r, (size_t)B); u.back(t_err, t, (size_t)B);
+    return u.finish();
+}
+
+}  // extern "C"

@@ -1,0 +1,64 @@
+// tvf_kernels.h -- internal interface between the C-ABI layer (tvf_api.cu) and
+// the kernel translation units.  Not installed; the public contract is include/tvf.h.
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tvf {
+
+// Where a warp/thread finds the correspondences of problem b, point i.
+//   packed != 0 : p1 is `Corresp` 6 x n x B (column-major; 48 contiguous bytes per point)
+//   packed == 0 : p1,p2,p3 are rows x n x B each (rows = 2, or 3 for homogeneous input)
+struct CoreInput {
+    const double* p1;
+    const double* p2;
+    const double* p3;
+    int packed;
+    int rows;
+    int n;
+    long long B;
+    int normalize;   // 1: *PoseEstimation path (Normalize2Ddata + undo); 0: estimator called directly
+};
+
+void launch_tft_core(const CoreInput& in, double* T, double* P2, double* P3, int* status, int sm_count,
+                     cudaStream_t stream);
+void launch_f_core(const CoreInput& in, double* F, int* status, int sm_count, cudaStream_t stream);
+
+// ---- pose tail -----------------------------------------------------------------------------
+struct PoseTailArgs {
+    const double* corresp;     // 6 x n x B
+    const double* calm;        // 9 x 3 (shared) or 9 x 3 x B
+    int calm_batched;
+    int n;
+    long long B;
+    // workspace (device)
+    double* cand;              // CAND_SIZE x B
+    int* votes;                // 10 x B : 8 votes, nanmask pair 2, nanmask pair 3
+    double* scale;             // 2 x B : num, den
+    // outputs (device; any may be null)
+    double* Rt2;               // 12 x B
+    double* Rt3;               // 12 x B
+    double* reconst;           // 3 x n x B
+    double* repr_err;          // B
+    int* status;               // B (or-ed into)
+};
+
+// mode 0: model = T (27 x B, pixel coordinates); mode 1: model = [F21 F31] (18 x B)
+void launch_candidates(int mode, const double* model, const PoseTailArgs& a, cudaStream_t stream);
+void launch_pose_tail(const PoseTailArgs& a, int sm_count, cudaStream_t stream);
+// LinearFPoseEstimation.m:78  T = TFT_from_P(K1*eye(3,4), K2*R_t_2, K3*R_t_3)
+void launch_tft_from_pose(const double* calm, int calm_batched, const double* Rt2, const double* Rt3,
+                          long long B, double* T, cudaStream_t stream);
+
+// ---- stand-alone reference functions (batched) ---------------------------------------------
+void launch_normalize2d(const double* pts, int n, long long B, double* out, double* Nmat, cudaStream_t s);
+void launch_transform_tft(const double* T, const double* M1, const double* M2, const double* M3, int mats_batched,
+                          int inverse, long long B, double* Tout, cudaStream_t s);
+void launch_tft_from_p(const double* P1, const double* P2, const double* P3, long long B, double* T, cudaStream_t s);
+void launch_triangulate(const double* P, int M, int cams_batched, const double* pts, int rows, int n, long long B,
+                        double* X, cudaStream_t s);
+void launch_repr_error(const double* P, int M, int cams_batched, const double* corresp, int rows, int n, long long B,
+                       const double* pts3d, int pts_rows, double* err, cudaStream_t s);
+void launch_ang_error(const double* Rt_true, int true_batched, const double* Rt_est, long long B, double* rot,
+                      double* tr, cudaStream_t s);
+
+}  // namespace tvf

@@ -1,0 +1,448 @@
+// tvf_pose_kernels.cu -- the pose tail shared by both methods
+// (R_t_from_TFT.m:40-106, LinearFPoseEstimation.m:59-78, triangulation3D.m,
+// ReprError.m) plus the stand-alone batched forms of the small reference
+// functions.  Thread mappings:
+//   candidates : one thread per problem (3x3 algebra, 18 tiny SVDs)
+//   votes / scale / final : one thread per (problem, point); a CTA covers
+//       floor(256/n) whole problems (or strides over the points of one problem
+//       when n > 256) so every per-problem reduction stays inside the CTA and
+//       runs in a fixed order (integer atomics for the votes, a fixed-shape
+//       shared-memory tree for the FP64 sums) -> bit-reproducible results.
+#include "tvf_kernels.h"
+#include "tvf_pose.cuh"
+
+namespace tvf {
+
+constexpr int PT_THREADS = 256;
+
+struct PointMap {
+    int ppb;    // problems per CTA iteration
+    int tpp;    // threads per problem
+    int lp;     // local problem of this thread
+    int lpt;    // thread's rank inside its problem
+    __device__ __forceinline__ PointMap(int n) {
+        tpp = (n <= PT_THREADS) ? n : PT_THREADS;
+        ppb = PT_THREADS / tpp;
+        lp = threadIdx.x / tpp;
+        lpt = threadIdx.x - lp * tpp;
+    }
+};
+
+// fixed-shape tree over the tpp partials of each problem; result lands at lpt==0
+__device__ __forceinline__ void seg_reduce(double* red, const PointMap& m) {
+    int s = 1;
+    while (s < m.tpp) s <<= 1;
+    for (s >>= 1; s >= 1; s >>= 1) {
+        __syncthreads();
+        if (m.lp < m.ppb && m.lpt < s && m.lpt + s < m.tpp) red[threadIdx.x] += red[threadIdx.x + s];
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ const double* calm_of(const PoseTailArgs& a, long long b) {
+    return a.calm + (a.calm_batched ? b * 27 : 0);
+}
+
+// ------------------------------------------------------------------ candidates
+__global__ void __launch_bounds__(128)
+candidates_kernel(int mode, const double* __restrict__ model, PoseTailArgs a) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= a.B) return;
+    double calm[27];
+    const double* cm = calm_of(a, b);
+#pragma unroll
+    for (int i = 0; i < 27; ++i) calm[i] = __ldg(cm + i);
+    double cand[CAND_SIZE];
+    int st;
+    if (mode == 0) {
+        double T[27];
+#pragma unroll
+        for (int i = 0; i < 27; ++i) T[i] = model[b * 27 + i];
+        st = candidates_from_tft(T, calm, cand);
+    } else {
+        double F[18];
+#pragma unroll
+        for (int i = 0; i < 18; ++i) F[i] = model[b * 18 + i];
+        st = candidates_from_f(F, F + 9, calm, cand);
+    }
+#pragma unroll
+    for (int i = 0; i < CAND_SIZE; ++i) a.cand[b * CAND_SIZE + i] = cand[i];
+    if (a.status != nullptr && st != 0) a.status[b] |= st;
+}
+
+// ------------------------------------------------------------------------ votes
+__global__ void __launch_bounds__(PT_THREADS)
+votes_kernel(PoseTailArgs a) {
+    __shared__ int sv[PT_THREADS * 10];
+    const PointMap m(a.n);
+    for (long long b0 = (long long)blockIdx.x * m.ppb; b0 < a.B; b0 += (long long)gridDim.x * m.ppb) {
+        for (int e = threadIdx.x; e < m.ppb * 10; e += PT_THREADS) sv[e] = 0;
+        __syncthreads();
+        const long long b = b0 + m.lp;
+        if (m.lp < m.ppb && b < a.B) {
+            double P1[12];
+            load_K1_as_P1(calm_of(a, b), P1);
+            const double* cand = a.cand + b * CAND_SIZE;
+            int vote[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            int nan2 = 0, nan3 = 0;
+            for (int pt = m.lpt; pt < a.n; pt += m.tpp) {
+                const double2* q = reinterpret_cast<const double2*>(a.corresp + (b * a.n + pt) * 6);
+                const double2 p1 = __ldg(q), p2 = __ldg(q + 1), p3 = __ldg(q + 2);
+                cheirality_point(P1, cand, p1.x, p1.y, p2.x, p2.y, vote, &nan2);
+                cheirality_point(P1, cand + CAND_PAIR, p1.x, p1.y, p3.x, p3.y, vote + 4, &nan3);
+            }
+            int* dst = sv + m.lp * 10;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                if (vote[k] != 0) atomicAdd(dst + k, vote[k]);
+            if (nan2) atomicOr(dst + 8, nan2);
+            if (nan3) atomicOr(dst + 9, nan3);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < m.ppb * 10; e += PT_THREADS) {
+            const long long bb = b0 + e / 10;
+            if (bb < a.B) a.votes[bb * 10 + (e % 10)] = sv[e];
+        }
+        __syncthreads();
+    }
+}
+
+struct Selected {
+    int k2, k3;
+    double P1[12], P2[12], Rt2[12], Rt3[12], KR3u3[12];   // KR3u3 = [K3*R3 | K3*t3] (t3 not yet scaled)
+};
+
+__device__ __forceinline__ void load_selected(const PoseTailArgs& a, long long b, Selected& s) {
+    const int* v = a.votes + b * 10;
+    int vote[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vote[k] = v[k];
+    s.k2 = select_candidate(vote, v[8]);
+    s.k3 = select_candidate(vote + 4, v[9]);
+    load_K1_as_P1(calm_of(a, b), s.P1);
+    const double* cand = a.cand + b * CAND_SIZE;
+    selected_pose(cand, s.k2 < 0 ? 0 : s.k2, s.Rt2, s.P2);
+    selected_pose(cand + CAND_PAIR, s.k3 < 0 ? 0 : s.k3, s.Rt3, s.KR3u3);
+}
+
+// ------------------------------------------------------------------------ scale
+__global__ void __launch_bounds__(PT_THREADS)
+scale_kernel(PoseTailArgs a) {
+    __shared__ double rnum[PT_THREADS], rden[PT_THREADS];
+    const PointMap m(a.n);
+    for (long long b0 = (long long)blockIdx.x * m.ppb; b0 < a.B; b0 += (long long)gridDim.x * m.ppb) {
+        const long long b = b0 + m.lp;
+        double num = 0.0, den = 0.0;
+        if (m.lp < m.ppb && b < a.B) {
+            Selected s;
+            load_selected(a, b, s);
+            for (int pt = m.lpt; pt < a.n; pt += m.tpp) {
+                const double2* q = reinterpret_cast<const double2*>(a.corresp + (b * a.n + pt) * 6);
+                const double2 p1 = __ldg(q), p2 = __ldg(q + 1), p3 = __ldg(q + 2);
+                const double p6[6] = {p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+                double cn, cd;
+                scale_point(s.P1, s.P2, s.KR3u3, s.KR3u3 + 9, p6, &cn, &cd);
+                num += cn; den += cd;
+            }
+        }
+        rnum[threadIdx.x] = num; rden[threadIdx.x] = den;
+        seg_reduce(rnum, m);
+        seg_reduce(rden, m);
+        if (m.lp < m.ppb && b < a.B && m.lpt == 0) {
+            a.scale[2 * b] = rnum[threadIdx.x];
+            a.scale[2 * b + 1] = rden[threadIdx.x];
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------ final
+__global__ void __launch_bounds__(PT_THREADS)
+final_kernel(PoseTailArgs a) {
+    __shared__ double rsq[PT_THREADS];
+    const PointMap m(a.n);
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (long long b0 = (long long)blockIdx.x * m.ppb; b0 < a.B; b0 += (long long)gridDim.x * m.ppb) {
+        const long long b = b0 + m.lp;
+        const bool live = (m.lp < m.ppb && b < a.B);
+        double sq = 0.0;
+        bool ok = false;
+        Selected s;
+        if (live) {
+            load_selected(a, b, s);
+            ok = (s.k2 >= 0 && s.k3 >= 0);
+            const double lam = -a.scale[2 * b] / a.scale[2 * b + 1];          // R_t_from_TFT.m:72-74
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { s.Rt3[9 + i] *= lam; s.KR3u3[9 + i] *= lam; }
+            for (int pt = m.lpt; pt < a.n; pt += m.tpp) {
+                const double2* q = reinterpret_cast<const double2*>(a.corresp + (b * a.n + pt) * 6);
+                const double2 p1 = __ldg(q), p2 = __ldg(q + 1), p3 = __ldg(q + 2);
+                const double p6[6] = {p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+                double X[3];
+                sq += final_point(s.P1, s.P2, s.KR3u3, p6, X);
+                if (a.reconst != nullptr) {
+                    double* dst = a.reconst + (b * a.n + pt) * 3;
+                    dst[0] = ok ? X[0] : qnan; dst[1] = ok ? X[1] : qnan; dst[2] = ok ? X[2] : qnan;
+                }
+            }
+        }
+        rsq[threadIdx.x] = sq;
+        seg_reduce(rsq, m);
+        if (live && m.lpt == 0) {
+            const double err = sqrt(rsq[threadIdx.x] / (3.0 * (double)a.n));   // ReprError.m:65
+            int st = 0;
+            if (s.k2 < 0) st |= ST_NO_POSE_2;
+            if (s.k3 < 0) st |= ST_NO_POSE_3;
+            bool fin = isfinite(err);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) fin = fin && isfinite(s.Rt2[i]) && isfinite(s.Rt3[i]);
+            if (!fin) st |= ST_NONFINITE;
+            if (a.Rt2 != nullptr)
+#pragma unroll
+                for (int i = 0; i < 12; ++i) a.Rt2[b * 12 + i] = ok ? s.Rt2[i] : qnan;
+            if (a.Rt3 != nullptr)
+#pragma unroll
+                for (int i = 0; i < 12; ++i) a.Rt3[b * 12 + i] = ok ? s.Rt3[i] : qnan;
+            if (a.repr_err != nullptr) a.repr_err[b] = ok ? err : qnan;
+            if (a.status != nullptr && st != 0) a.status[b] |= st;
+        }
+        __syncthreads();
+    }
+}
+
+// -------------------------------------------------- T = TFT_from_P(K1[I|0], K2 Rt2, K3 Rt3)
+__global__ void __launch_bounds__(128)
+tft_from_pose_kernel(const double* __restrict__ calm, int calm_batched, const double* __restrict__ Rt2,
+                     const double* __restrict__ Rt3, long long B, double* __restrict__ T) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* cm = calm + (calm_batched ? b * 27 : 0);
+    double K[3][9];
+#pragma unroll
+    for (int v = 0; v < 3; ++v)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) K[v][r + 3 * c] = __ldg(cm + 3 * v + r + 9 * c);
+    double P1[12], P2[12], P3[12], R[12];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) P1[i] = K[0][i];
+    P1[9] = 0.0; P1[10] = 0.0; P1[11] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) R[i] = Rt2[b * 12 + i];
+    mat3_mul(K[1], R, P2); mat3_vec(K[1], R + 9, P2 + 9);
+#pragma unroll
+    for (int i = 0; i < 12; ++i) R[i] = Rt3[b * 12 + i];
+    mat3_mul(K[2], R, P3); mat3_vec(K[2], R + 9, P3 + 9);
+    double t[27];
+    tft_from_p(P1, P2, P3, t);
+#pragma unroll
+    for (int i = 0; i < 27; ++i) T[b * 27 + i] = t[i];
+}
+
+// ------------------------------------------------------- stand-alone batched functions
+__global__ void normalize2d_kernel(const double* __restrict__ pts, int n, long long B, double* __restrict__ out,
+                                   double* __restrict__ Nmat) {
+    // one warp per problem (Normalize2Ddata.m:33-39)
+    const int lane = threadIdx.x & 31;
+    const long long b = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (b >= B) return;
+    const double* p = pts + b * 2 * n;
+    double sx = 0.0, sy = 0.0;
+    for (int i = lane; i < n; i += 32) { sx += p[2 * i]; sy += p[2 * i + 1]; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { sx += __shfl_xor_sync(0xffffffffu, sx, o); sy += __shfl_xor_sync(0xffffffffu, sy, o); }
+    const double cx = sx / n, cy = sy / n;
+    double d = 0.0;
+    for (int i = lane; i < n; i += 32) { const double dx = p[2 * i] - cx, dy = p[2 * i + 1] - cy; d += sqrt(dx * dx + dy * dy); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    const double s = 1.4142135623730951 / (d / n);
+    const double tx = -s * cx, ty = -s * cy;
+    if (out != nullptr)
+        for (int i = lane; i < n; i += 32) { out[b * 2 * n + 2 * i] = s * p[2 * i] + tx; out[b * 2 * n + 2 * i + 1] = s * p[2 * i + 1] + ty; }
+    if (Nmat != nullptr && lane == 0) {
+        double* N = Nmat + b * 9;
+        N[0] = s; N[1] = 0; N[2] = 0; N[3] = 0; N[4] = s; N[5] = 0; N[6] = tx; N[7] = ty; N[8] = 1.0;
+    }
+}
+
+__global__ void transform_tft_kernel(const double* __restrict__ T, const double* __restrict__ M1,
+                                     const double* __restrict__ M2, const double* __restrict__ M3, int mats_batched,
+                                     int inverse, long long B, double* __restrict__ Tout) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const long long mo = mats_batched ? b * 9 : 0;
+    double t[27], m1[9], m2[9], m3[9], o[27];
+#pragma unroll
+    for (int i = 0; i < 27; ++i) t[i] = T[b * 27 + i];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) { m1[i] = M1[mo + i]; m2[i] = M2[mo + i]; m3[i] = M3[mo + i]; }
+    transform_tft(t, m1, m2, m3, inverse, o);
+#pragma unroll
+    for (int i = 0; i < 27; ++i) Tout[b * 27 + i] = o[i];
+}
+
+__global__ void tft_from_p_kernel(const double* __restrict__ P1, const double* __restrict__ P2,
+                                  const double* __restrict__ P3, long long B, double* __restrict__ T) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double a[12], c[12], d[12], t[27];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { a[i] = P1[b * 12 + i]; c[i] = P2[b * 12 + i]; d[i] = P3[b * 12 + i]; }
+    tft_from_p(a, c, d, t);
+#pragma unroll
+    for (int i = 0; i < 27; ++i) T[b * 27 + i] = t[i];
+}
+
+// image point (x,y) of view v for (problem b, point pt); rows = 2 or 3 per view
+__device__ __forceinline__ void load_xy(const double* pts, int M, int rows, int n, long long b, int pt, int v,
+                                        double* x, double* y) {
+    const double* p = pts + ((b * n + pt) * M + v) * rows;
+    double px = p[0], py = p[1];
+    if (rows == 3) { const double w = p[2]; px /= w; py /= w; }     // triangulation3D.m:43-45
+    *x = px; *y = py;
+}
+
+template <int M>
+__device__ __forceinline__ void triangulate_m(const double* P, const double* pts, int rows, int n, long long b, int pt,
+                                              double* X) {
+    double a[2 * M][4];
+#pragma unroll
+    for (int v = 0; v < M; ++v) {
+        double x, y;
+        load_xy(pts, M, rows, n, b, pt, v, &x, &y);
+        dlt_rows(P + 12 * v, x, y, a[2 * v], a[2 * v + 1]);
+    }
+    dlt_null<2 * M>(a, X);
+}
+
+__global__ void triangulate_kernel(const double* __restrict__ P, int M, int cams_batched, const double* __restrict__ pts,
+                                   int rows, int n, long long B, double* __restrict__ X) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * n) return;
+    const long long b = e / n;
+    const int pt = (int)(e - b * n);
+    const double* Pb = P + (cams_batched ? b * 12 * M : 0);
+    double x[4];
+    if (M == 2) triangulate_m<2>(Pb, pts, rows, n, b, pt, x);
+    else triangulate_m<3>(Pb, pts, rows, n, b, pt, x);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) X[e * 4 + i] = x[i];
+}
+
+__global__ void __launch_bounds__(PT_THREADS)
+repr_error_kernel(const double* __restrict__ P, int M, int cams_batched, const double* __restrict__ corresp, int rows,
+                  int n, long long B, const double* __restrict__ pts3d, int pts_rows, double* __restrict__ err) {
+    __shared__ double rsq[PT_THREADS];
+    const PointMap m(n);
+    for (long long b0 = (long long)blockIdx.x * m.ppb; b0 < B; b0 += (long long)gridDim.x * m.ppb) {
+        const long long b = b0 + m.lp;
+        const bool live = (m.lp < m.ppb && b < B);
+        double sq = 0.0;
+        if (live) {
+            const double* Pb = P + (cams_batched ? b * 12 * M : 0);
+            for (int pt = m.lpt; pt < n; pt += m.tpp) {
+                double X[4];
+                if (pts3d == nullptr) {                                           // ReprError.m:43-44
+                    if (M == 2) triangulate_m<2>(Pb, corresp, rows, n, b, pt, X);
+                    else triangulate_m<3>(Pb, corresp, rows, n, b, pt, X);
+                } else {
+                    const double* q = pts3d + (b * n + pt) * pts_rows;
+                    X[0] = q[0]; X[1] = q[1]; X[2] = q[2]; X[3] = (pts_rows == 4) ? q[3] : 1.0;   // :45-48
+                }
+                for (int v = 0; v < M; ++v) {
+                    double x, y, pr[3];
+                    load_xy(corresp, M, rows, n, b, pt, v, &x, &y);
+                    cam_apply(Pb + 12 * v, X, pr);
+                    const double dx = pr[0] / pr[2] - x, dy = pr[1] / pr[2] - y;
+                    sq += dx * dx + dy * dy;
+                }
+            }
+        }
+        rsq[threadIdx.x] = sq;
+        seg_reduce(rsq, m);
+        if (live && m.lpt == 0) err[b] = sqrt(rsq[threadIdx.x] / ((double)M * (double)n));
+        __syncthreads();
+    }
+}
+
+__global__ void ang_error_kernel(const double* __restrict__ Rt_true, int true_batched, const double* __restrict__ Rt_est,
+                                 long long B, double* __restrict__ rot, double* __restrict__ tr) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double a[12], e[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { a[i] = Rt_true[(true_batched ? b * 12 : 0) + i]; e[i] = Rt_est[b * 12 + i]; }
+    double r, t;
+    ang_error(a, e, &r, &t);
+    rot[b] = r; tr[b] = t;
+}
+
+// ------------------------------------------------------------------- launchers
+static inline unsigned grid_for(long long work, int per_block, long long cap) {
+    long long g = (work + per_block - 1) / per_block;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+void launch_candidates(int mode, const double* model, const PoseTailArgs& a, cudaStream_t stream) {
+    if (a.B <= 0) return;
+    candidates_kernel<<<grid_for(a.B, 128, 1LL << 30), 128, 0, stream>>>(mode, model, a);
+}
+
+void launch_pose_tail(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
+    if (a.B <= 0) return;
+    const int tpp = (a.n <= PT_THREADS) ? a.n : PT_THREADS;
+    const int ppb = PT_THREADS / tpp;
+    const unsigned g = grid_for(a.B, ppb, (long long)sm_count * 32);
+    votes_kernel<<<g, PT_THREADS, 0, stream>>>(a);
+    scale_kernel<<<g, PT_THREADS, 0, stream>>>(a);
+    final_kernel<<<g, PT_THREADS, 0, stream>>>(a);
+}
+
+void launch_tft_from_pose(const double* calm, int calm_batched, const double* Rt2, const double* Rt3, long long B,
+                          double* T, cudaStream_t stream) {
+    if (B <= 0) return;
+    tft_from_pose_kernel<<<grid_for(B, 128, 1LL << 30), 128, 0, stream>>>(calm, calm_batched, Rt2, Rt3, B, T);
+}
+
+void launch_normalize2d(const double* pts, int n, long long B, double* out, double* Nmat, cudaStream_t s) {
+    if (B <= 0) return;
+    normalize2d_kernel<<<grid_for(B * 32, 256, 1LL << 30), 256, 0, s>>>(pts, n, B, out, Nmat);
+}
+
+void launch_transform_tft(const double* T, const double* M1, const double* M2, const double* M3, int mats_batched,
+                          int inverse, long long B, double* Tout, cudaStream_t s) {
+    if (B <= 0) return;
+    transform_tft_kernel<<<grid_for(B, 128, 1LL << 30), 128, 0, s>>>(T, M1, M2, M3, mats_batched, inverse, B, Tout);
+}
+
+void launch_tft_from_p(const double* P1, const double* P2, const double* P3, long long B, double* T, cudaStream_t s) {
+    if (B <= 0) return;
+    tft_from_p_kernel<<<grid_for(B, 128, 1LL << 30), 128, 0, s>>>(P1, P2, P3, B, T);
+}
+
+void launch_triangulate(const double* P, int M, int cams_batched, const double* pts, int rows, int n, long long B,
+                        double* X, cudaStream_t s) {
+    if (B <= 0 || n <= 0) return;
+    triangulate_kernel<<<grid_for(B * n, 128, 1LL << 30), 128, 0, s>>>(P, M, cams_batched, pts, rows, n, B, X);
+}
+
+void launch_repr_error(const double* P, int M, int cams_batched, const double* corresp, int rows, int n, long long B,
+                       const double* pts3d, int pts_rows, double* err, cudaStream_t s) {
+    if (B <= 0) return;
+    const int tpp = (n <= PT_THREADS) ? n : PT_THREADS;
+    const int ppb = PT_THREADS / tpp;
+    repr_error_kernel<<<grid_for(B, ppb, 148LL * 32), PT_THREADS, 0, s>>>(P, M, cams_batched, corresp, rows, n, B, pts3d,
+                                                                          pts_rows, err);
+}
+
+void launch_ang_error(const double* Rt_true, int true_batched, const double* Rt_est, long long B, double* rot,
+                      double* tr, cudaStream_t s) {
+    if (B <= 0) return;
+    ang_error_kernel<<<grid_for(B, 128, 1LL << 30), 128, 0, s>>>(Rt_true, true_batched, Rt_est, B, rot, tr);
+}
+
+}  // namespace tvf
