@@ -1,0 +1,432 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the linear three-view pose path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on host cores (oracle port)
+
+A "step" is one pass of LinearTFTPoseEstimation (+ ReprError) over one batch of synthetic trials
+of BASELINE.json config 3: experiments.m's noise sweep, n = 20 points, `--trials` (default
+1 000 000) independent trials per GPU, inputs resident in HBM when the timed region starts.
+Multi-GPU: one process per GPU (torchrun), contiguous ranges of the global trial index per rank,
+no data-path collective (weak scaling: per-GPU work fixed); NCCL only carries the barrier and the
+max-over-ranks of the device time.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "3-view linear TFT pose solves/sec (LinearTFTPoseEstimation + ReprError, n=20)"
+UNIT = "solves/s"
+
+
+# ---- work model: algorithmic figures per solve ------------------------
+def tft_flops(n):
+    return 19458 * n + 438212
+
+
+def f_flops(n):
+    return 8974 * n + 20995
+
+
+def pose_bytes(n):
+    return 72 * n + 416
+
+
+def kernel_flops(n):
+    """App. B.1 rows attributed to the kernels of the TFT method (sums to tft_flops(n))."""
+    return {
+        "tft_stage1_kernel": 5909 * n + 216513,  # normalise x3, design matrix, null vector of A (4n x 27)
+        "tft_epipoles_kernel": 2592,             # 8 svd3 (linearTFT.m:71-79)
+        "tft_stage2_kernel": 5040 * n + 214000,  # svd(E), A*Up, its null vector, Up*tp, a; undo normalisation
+        "candidates_kernel": 4922,               # de-calibrate, 8 svd3, E21/E31, 2 x svd(E) -> R, Rp, t
+        "votes_kernel": 6632 * n,                # 8 two-view DLTs per point + signs
+        "scale_kernel": 846 * n + 60,            # two-view DLT per point + closed-form lambda
+        "final_kernel": 1031 * n + 125,          # three-view DLT per point + ReprError
+    }
+
+
+# ---- oracle-based CPU legs (the only place bench.py touches oracle/) -----------------------------
+def _cpu_worker(args):
+    import oracle as o
+    Cs, CalM = args
+    K = [CalM[0:3], CalM[3:6], CalM[6:9]]
+    acc = 0.0
+    for C_ in Cs:
+        R2, R3, Rec, T, _ = o.LinearTFTPoseEstimation(C_, CalM)
+        acc += o.ReprError([K[0] @ np.eye(3, 4), K[1] @ R2, K[2] @ R3], C_, Rec)
+    return acc
+
+
+def _pool_init():
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(1)
+    except Exception:
+        pass
+
+
+def cpu_solves_per_sec(Corresp, CalM, cores, pool):
+    """Oracle port of LinearTFTPoseEstimation+ReprError over `Corresp` (S,6,n) on `cores` processes."""
+    S = Corresp.shape[0]
+    parts = np.array_split(np.arange(S), cores * 4)
+    jobs = [(Corresp[p], CalM) for p in parts if p.size]
+    t0 = time.perf_counter()
+    if pool is None:
+        for j in jobs:
+            _cpu_worker(j)
+    else:
+        pool.map(_cpu_worker, jobs)
+    dt = time.perf_counter() - t0
+    return S / dt, dt
+
+
+def make_pool(cores):
+    if cores <= 1:
+        return None
+    import multiprocessing as mp
+    return mp.get_context("fork").Pool(cores, initializer=_pool_init)
+
+
+# ---- clocks --------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.path = tempfile.mktemp(prefix="tvf_clocks_", suffix=".csv")
+        self.proc = None
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2])); pw.append(float(p[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, p[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            # "under load": samples in the upper half of the observed power range
+            thr = (max(pw) + min(pw)) / 2.0
+            load = [s for s, w in zip(sm, pw) if w >= thr] or sm
+            out = {"sm_mhz": float(np.median(load)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": float(max(pw))}
+        return out
+
+
+def measured_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ---- reference arm -------------------------------------------------------------------------------
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from tft_vs_fund_b200 import scene
+    cores = os.cpu_count() or 1
+    S = args.cpu_sample if args.cpu_sample > 0 else 250 * cores       # ~2.5 s of oracle work per core and step
+    d = scene.sweep_batch(S, args.n, workers=min(cores, 16))
+    pool = make_pool(cores)
+    for _ in range(args.warmup):
+        cpu_solves_per_sec(d["Corresp"][: max(cores * 8, S // 8)], d["CalM"], cores, pool)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_solves_per_sec(d["Corresp"], d["CalM"], cores, pool)
+    dt = time.perf_counter() - t0
+    if pool is not None:
+        pool.close()
+    value = S * args.steps / dt
+    sample = "first %d trials of the sweep per step (of %d in the GPU arm's step)" % (S, args.trials)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "experiments.m noise sweep, n=%d, %d trials per GPU (BASELINE config 3)" % (args.n, args.trials),
+                   "method": "LinearTFTPoseEstimation", "n_points": args.n, "trials_per_gpu": args.trials},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": "NumPy/LAPACK restatement of the reference's MATLAB (oracle/), not MATLAB itself: "
+                                 "neither MATLAB nor Octave exists in this image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- GPU arm -------------------------------------------------------------------------------------
+def run_gpu(args, rank, local_rank, world):
+    from tft_vs_fund_b200 import scene, _lib
+    n, B = args.n, args.trials
+    cores = os.cpu_count() or 1
+
+    # 1. inputs (host, before CUDA is touched: the generator forks workers)
+    t_gen = time.perf_counter()
+    d = scene.sweep_batch(B, n, first_trial=rank * B, workers=max(1, min(32, cores // max(1, world))))
+    t_gen = time.perf_counter() - t_gen
+    CalM = d["CalM"]
+    corresp_host = np.ascontiguousarray(d["Corresp"].transpose(0, 2, 1))          # (B, n, 6) == 6 x n x B column-major
+
+    # 2. CPU baseline beside it (rank 0, N=1 only), still before CUDA initialisation
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        S = args.cpu_sample if args.cpu_sample > 0 else min(B, 200 * cores)
+        pool = make_pool(cores)
+        cpu_solves_per_sec(d["Corresp"][: max(8, S // 10)], CalM, cores, pool)      # warm the pool
+        v, dt = cpu_solves_per_sec(d["Corresp"][:S], CalM, cores, pool)
+        if pool is not None:
+            pool.close()
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "first %d of the step's %d trials, %.1f s wall" % (S, B, dt),
+                        "note": "oracle/ NumPy+LAPACK restatement of the MATLAB reference, one process per core"}
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    h = _lib.Handle(local_rank)
+    lib = h.lib
+    stream = torch.cuda.Stream(device=dev)
+    h.call("tvf_set_stream", C.c_void_p(stream.cuda_stream))
+
+    # 3. device-resident inputs / outputs
+    d_corresp = torch.from_numpy(corresp_host).to(dev)
+    d_calm = torch.from_numpy(np.ascontiguousarray(CalM.T)).to(dev)
+    d_Rt2 = torch.empty((B, 12), dtype=torch.float64, device=dev)
+    d_Rt3 = torch.empty((B, 12), dtype=torch.float64, device=dev)
+    d_rec = torch.empty((B, 3 * n), dtype=torch.float64, device=dev)
+    d_T = torch.empty((B, 27), dtype=torch.float64, device=dev)
+    d_rep = torch.empty((B,), dtype=torch.float64, device=dev)
+    d_st = torch.zeros((B,), dtype=torch.int32, device=dev)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+
+    def step_tft():
+        h.call("tvf_linear_tft_pose_dev", ptr(d_corresp), ptr(d_calm), 0, n, B, ptr(d_Rt2), ptr(d_Rt3), ptr(d_rec),
+               ptr(d_T), ptr(d_rep), ptr(d_st))
+
+    def step_f():
+        h.call("tvf_linear_f_pose_dev", ptr(d_corresp), ptr(d_calm), 0, n, B, ptr(d_Rt2), ptr(d_Rt3), ptr(d_rec),
+               ptr(d_T), ptr(d_rep), None, None, ptr(d_st))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    def timed(step, steps, profile=False):
+        """K steps on `stream`, bracketed by barrier + synchronize, timed with CUDA events on that stream."""
+        if profile:
+            h.call("tvf_profile_reset"); h.call("tvf_profile_enable", 1)
+        barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            for _ in range(steps):
+                step()
+            e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            tot = (C.c_double * _lib.NUM_KERNELS)(); cnt = (C.c_int64 * _lib.NUM_KERNELS)()
+            h.call("tvf_profile_read", tot, cnt)
+            h.call("tvf_profile_enable", 0)
+            prof = {lib.tvf_kernel_name(i).decode(): (tot[i], cnt[i]) for i in range(_lib.NUM_KERNELS) if cnt[i]}
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, prof
+
+    fp64_peak = lib.tvf_fp64_peak_tflops(h._h)
+
+    # 4. warm-up, then the timed region (with the clock sampler running)
+    for _ in range(max(3, args.warmup)):
+        step_tft()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = lib.tvf_launch_count(h._h)
+    ms, prof = timed(step_tft, args.steps, profile=True)
+    launches = lib.tvf_launch_count(h._h) - l0
+    clocks = sampler.stop() if sampler else None
+    flagged = int(torch.count_nonzero(d_st).item())
+    value = world * B * args.steps / (ms * 1e-3)
+    rep_device_path = d_rep.cpu().numpy()
+
+    # F method, same inputs (reported beside the headline)
+    for _ in range(3):
+        step_f()
+    ms_f, _ = timed(step_f, max(3, args.steps // 2))
+    f_value = world * B * max(3, args.steps // 2) / (ms_f * 1e-3)
+
+    # 5. end to end through the host-pointer C ABI: pinned host buffers, H2D + kernels + D2H inside the timed region
+    lib.tvf_host_alloc.restype = C.c_void_p
+
+    def pinned(shape, dtype=np.float64):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = lib.tvf_host_alloc(nbytes)
+        if not p:
+            raise RuntimeError("tvf_host_alloc failed")
+        buf = (C.c_char * nbytes).from_address(p)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+    h_in, p0 = pinned((B, n, 6)); h_in[...] = corresp_host
+    h_calm = np.ascontiguousarray(CalM.T)
+    h_Rt2, p1 = pinned((B, 12)); h_Rt3, p2 = pinned((B, 12)); h_rec, p3 = pinned((B, 3 * n))
+    h_T, p4 = pinned((B, 27)); h_rep, p5 = pinned((B,)); h_st, p6 = pinned((B,), np.int32)
+    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
+
+    def step_e2e():
+        return h.call("tvf_linear_tft_pose", dp(h_in), dp(h_calm), 0, n, B, dp(h_Rt2), dp(h_Rt3), dp(h_rec), dp(h_T),
+                      dp(h_rep), h_st.ctypes.data_as(_lib.c_int32_p))
+
+    for _ in range(2):
+        step_e2e()
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        step_e2e()
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    barrier()
+    e2e_value = world * B * e2e_steps / dt
+    e2e_check = float(np.abs(h_rep - rep_device_path).max())       # host path and device path agree bit for bit
+    h2d = B * n * 6 * 8 + 27 * 8
+    d2h = B * (12 + 12 + 3 * n + 27 + 1) * 8 + B * 4
+    for p in (p0, p1, p2, p3, p4, p5, p6):
+        lib.tvf_host_free(C.c_void_p(p))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # 6. rooflines
+    peaks = measured_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    hbm_src = "measured (MEASURED_PEAKS.json)" if peaks else "fallback (B200_PROFILING.md)"
+    kf = kernel_flops(n)
+    per_kernel = {}
+    dom, dom_ms = None, -1.0
+    tot_kernel_ms = sum(v[0] for v in prof.values())
+    for name, (tms, cnt) in prof.items():
+        per_kernel[name] = {"ms_total": tms, "launches": int(cnt), "share": tms / tot_kernel_ms if tot_kernel_ms else None}
+        if tms > dom_ms:
+            dom, dom_ms = name, tms
+    units_per_launch = B * args.steps / prof[dom][1]                      # problems one launch of the dominant kernel handles
+    avg_launch_s = dom_ms * 1e-3 / prof[dom][1]
+    achieved_tf = kf[dom] * units_per_launch / avg_launch_s / 1e12
+    fp64_src = "measured on this device by tvf_fp64_peak_tflops (register-resident DFMA loop)"
+    if not (fp64_peak and fp64_peak > 1.0):
+        fp64_peak, fp64_src = 37.2, "nominal 148 SM x 64 FMA/clk x 1.965 GHz"
+    roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp64_peak, "traffic": None,
+                "peak_source": fp64_src,
+                "work_model": "reference-operation FLOP count of SURVEY.md App. B.1 attributed to this kernel "
+                              "(%d flop/solve at n=%d) x %.0f solves per launch" % (kf[dom], n, units_per_launch)}
+    step_s = ms * 1e-3 / args.steps
+    roofline_step = {"bound": "fp64", "achieved": tft_flops(n) * B / step_s / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                     "frac": tft_flops(n) * B / step_s / 1e12 / fp64_peak,
+                     "note": "whole step, %d algorithmic flop/solve (SURVEY.md 8d); the GPU algorithm executes far "
+                             "fewer flops than the reference's SVD count, so this can exceed 1" % tft_flops(n)}
+    roofline_hbm = {"bound": "hbm", "achieved": pose_bytes(n) * B / step_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": pose_bytes(n) * B / step_s / 1e9 / hbm_peak, "peak_source": hbm_src,
+                    "note": "%d algorithmic bytes/solve; this path is FP64-bound at n=20, not HBM-bound" % pose_bytes(n)}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "experiments.m noise sweep (13 levels 0:0.25:3), n=%d points, %d trials per GPU "
+                               "(BASELINE config 3%s)" % (n, B, "" if world == 1 else "/4 sharded"),
+                   "method": "LinearTFTPoseEstimation", "n_points": n, "trials_per_gpu": B, "global_trials": B * world,
+                   "parallelism": "independent trial ranges per GPU, no collective",
+                   "cache": "inputs+outputs per step (%.2f GB) exceed L2; no flush needed" % ((h2d + d2h) / 1e9)},
+        "roofline": roofline, "roofline_step": roofline_step, "roofline_hbm": roofline_hbm,
+        "kernels": per_kernel,
+        "cpu_baseline": cpu_baseline,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_check,
+                "api": "tvf_linear_tft_pose (host pointers, pinned; chunked H2D/compute/D2H over 3 streams)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "f_method": {"metric": "3-view linear F pose solves/sec (LinearFPoseEstimation + ReprError)", "value": f_value,
+                     "unit": UNIT, "ms_per_step": ms_f / max(3, args.steps // 2),
+                     "roofline_step_frac_fp64": f_flops(n) * B / (ms_f * 1e-3 / max(3, args.steps // 2)) / 1e12 / fp64_peak},
+        "flagged_problems": flagged,
+        "input_generation_s": t_gen,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--trials", type=int, default=1000000, help="trials per GPU and step (BASELINE config 3: 1M)")
+    ap.add_argument("--n", type=int, default=20)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="trials in the CPU-baseline sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_gpu(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

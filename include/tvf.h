@@ -142,8 +142,30 @@ int tvf_linear_f_pose_dev(tvf_handle_t h, const double* corresp, const double* c
                           int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
                           double* F21, double* F31, int32_t* status);
 
-/* number of kernel launches issued through this handle since creation (bench bookkeeping) */
+/* ---- measurement support ------------------------------------------------------------------ */
+/* number of kernel launches issued through this handle since creation */
 int64_t tvf_launch_count(tvf_handle_t h);
+/* per-kernel device time: when enabled every kernel launch of the pose entry points is bracketed by
+ * CUDA events on its own stream; tvf_profile_read() returns accumulated milliseconds and launch counts
+ * per kernel id (arrays of TVF_NUM_KERNELS). */
+#define TVF_K_TFT_STAGE1 0
+#define TVF_K_TFT_EPIPOLES 1
+#define TVF_K_TFT_STAGE2 2
+#define TVF_K_F_STAGE1 3
+#define TVF_K_F_FINISH 4
+#define TVF_K_CANDIDATES 5
+#define TVF_K_VOTES 6
+#define TVF_K_SCALE 7
+#define TVF_K_FINAL 8
+#define TVF_K_TFT_FROM_POSE 9
+#define TVF_NUM_KERNELS 10
+int tvf_profile_enable(tvf_handle_t h, int on);
+int tvf_profile_reset(tvf_handle_t h);
+int tvf_profile_read(tvf_handle_t h, double* total_ms, int64_t* launches);
+const char* tvf_kernel_name(int id);
+/* measured FP64 FMA throughput of this device (TFLOP/s; a register-resident DFMA loop on all SMs):
+ * the denominator of the FP64 roofline fractions bench.py reports */
+double tvf_fp64_peak_tflops(tvf_handle_t h);
 
 #ifdef __cplusplus
 }

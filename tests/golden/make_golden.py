@@ -1,0 +1,82 @@
+"""Generate the committed golden vectors under tests/golden/ (run in the build container, where
+/root/reference is mounted):   python tests/golden/make_golden.py
+
+Inputs come from the documented scene generator / the reference's EPFL data files; expected outputs
+from the oracle (oracle/reference_port.py).  The GPU box has no /root/reference, so the `-m gpu`
+tests read only these .npz files (plus the live oracle on the same seeded inputs)."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+import oracle as o  # noqa: E402
+
+REFERENCE = "/root/reference"
+
+
+def run_both(C, CalM):
+    K = [CalM[0:3], CalM[3:6], CalM[6:9]]
+    out = {}
+    R2, R3, Rec, T, _ = o.LinearTFTPoseEstimation(C, CalM)
+    out["tft"] = (R2, R3, Rec, T, o.ReprError([K[0] @ np.eye(3, 4), K[1] @ R2, K[2] @ R3], C, Rec))
+    R2, R3, Rec, T, _, F21, F31 = o.LinearFPoseEstimation(C, CalM, return_F=True)
+    out["f"] = (R2, R3, Rec, T, o.ReprError([K[0] @ np.eye(3, 4), K[1] @ R2, K[2] @ R3], C, Rec), F21, F31)
+    return out
+
+
+def pack(cases):
+    """cases: list of dict(Corresp, CalM, res=run_both(...)) with equal n -> arrays with a leading case axis."""
+    d = dict(Corresp=np.stack([c["Corresp"] for c in cases]), CalM=np.stack([c["CalM"] for c in cases]))
+    for m in ("tft", "f"):
+        names = ["Rt2", "Rt3", "Reconst", "T", "repr"] + (["F21", "F31"] if m == "f" else [])
+        for k, name in enumerate(names):
+            d["%s_%s" % (m, name)] = np.stack([np.asarray(c["res"][m][k]) for c in cases])
+    for key in cases[0]:
+        if key not in ("Corresp", "CalM", "res"):
+            d[key] = np.stack([np.asarray(c[key]) for c in cases])
+    return d
+
+
+def sweep():
+    """experiments.m defaults at the benchmark shape: 13 noise levels x n_sim=20 seeds, n=20."""
+    cases = []
+    for j in range(13 * 20):
+        noise, seed = 0.25 * (j % 13), j // 13 + 1
+        CalM, R_t0, C, _ = o.experiments_subsample(20, noise, seed)
+        cases.append(dict(Corresp=C, CalM=CalM, res=run_both(C, CalM), noise=noise, seed=seed,
+                          Rt0_2=R_t0[0], Rt0_3=R_t0[1]))
+    np.savez_compressed(os.path.join(HERE, "sweep_n20.npz"), **pack(cases))
+
+
+def example():
+    """example.m:22-28: N=100, noise=1, seed=1, f=50, angle=0."""
+    CalM, R_t0, C, _ = o.generateSyntheticScene(100, 1, 1, 50, 0)
+    np.savez_compressed(os.path.join(HERE, "example_n100.npz"),
+                        **pack([dict(Corresp=C, CalM=CalM, res=run_both(C, CalM), Rt0_2=R_t0[0], Rt0_3=R_t0[1])]))
+
+
+def epfl(ntrip=6):
+    """experiments_real.m:78-109 on the first triplets of both datasets (100 sampled inliers each)."""
+    cases = []
+    for ds in ("fountain-P11", "Herz-Jesu-P8"):
+        path = os.path.join(REFERENCE, "Data", ds)
+        idx, cor, names = o.load_corresp_triplets(path)
+        for it in range(1, ntrip + 1):
+            d = o.epfl_triplet(path, idx, cor, names, it)
+            inl = d["Corresp_inliers"]
+            sample = o.SceneRNG(it).randsample(inl.shape[1], min(100, inl.shape[1]))
+            C = inl[:, sample]
+            cases.append(dict(Corresp=C, CalM=d["CalM"], res=run_both(C, d["CalM"]), Rt0_2=d["R_t0"][0],
+                              Rt0_3=d["R_t0"][1], n_inliers=inl.shape[1], gt_repr=d["REr"],
+                              triplet=np.array(d["triplet"])))
+    np.savez_compressed(os.path.join(HERE, "epfl_triplets.npz"), **pack(cases))
+
+
+if __name__ == "__main__":
+    sweep(); example()
+    if os.path.isdir(REFERENCE):
+        epfl()
+    print("golden vectors written to", HERE)

@@ -10,6 +10,14 @@ extern "C" {
 
 void hc_null3(const double* M, double* v) { null3(M, v); }
 
+int hc_jacobi_sweeps(const double* M) {
+    double A[9], V[9], s[3];
+    for (int i = 0; i < 9; ++i) A[i] = M[i];
+    int sweeps = 0;
+    jacobi_svd3(A, V, s, &sweeps);
+    return sweeps;
+}
+
 void hc_svd3(const double* M, double* U, double* s, double* V) { svd3_full(M, U, s, V); }
 
 void hc_inv3(const double* M, double* Mi) { inv3(M, Mi); }

@@ -1,7 +1,7 @@
 """NumPy model of the GPU algorithms (TEST HELPER, not product code).
 
 Mirrors, step for step, what the CUDA kernels in tft_vs_fund_b200/csrc do
-(96 Kronecker moments -> 27x27 Gram -> shifted-Cholesky inverse iteration ->
+(96 Kronecker moments -> 27x27 Gram -> Gauss-Jordan sweep inverse + power iteration ->
 epipoles by one-sided Jacobi -> 15-dim projected Gram -> ... -> QR-based DLT),
 so the numerical design (tolerances, iteration counts) can be validated
 against the oracle on CPU before any GPU time is spent.
@@ -44,24 +44,32 @@ def gram27_from_moments(mom):
     return G
 
 
-def smallest_eigvec_spd(G, max_iter=60, tol=4e-16, rel_shift=1e-13):
-    """Shifted Cholesky + inverse iteration (what the warp-cooperative kernel does)."""
+def smallest_eigvec_spd(G, max_iter=80, tol=1e-15):
+    """What tvf_warp.cuh::smallest_eigvec_spd does: scale to unit trace, relative diagonal shift 1e-13,
+    N Gauss-Jordan sweeps in place (pivot row updated through c_k = d - 1), then power iteration with
+    the (negated) inverse."""
     N = G.shape[0]
-    delta = rel_shift * np.trace(G) / N
-    L = np.linalg.cholesky(G + delta * np.eye(N))
-    # start: solve L^T x = ones
-    x = np.linalg.solve(L.T, np.ones(N))
-    x /= np.linalg.norm(x)
+    A = G / np.trace(G)
+    delta = 1e-13 / N
+    A = A + delta * np.eye(N)
+    floor = 1e-3 * delta
+    for k in range(N):
+        col = A[:, k].copy()
+        d = max(col[k], floor)
+        piv = 1.0 / d
+        rk = col * piv
+        c = col.copy(); c[k] -= 1.0
+        newA = A - np.outer(c, rk)
+        newA[:, k] = rk; newA[k, k] = -piv
+        A = newA
+    x = np.ones(N) / np.sqrt(N)
     its = 0
     for its in range(1, max_iter + 1):
-        y = np.linalg.solve(L, x)
-        z = np.linalg.solve(L.T, y)
+        z = -(A @ x)
         z /= np.linalg.norm(z)
-        if np.dot(z, x) < 0:
-            z = -z
         d = np.max(np.abs(z - x))
         x = z
-        if d < tol:
+        if not d > tol:
             break
     return x, its
 

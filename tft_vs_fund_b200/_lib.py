@@ -61,7 +61,13 @@ SIGNATURES = {
     "tvf_linear_tft_pose_dev": (_I, [_H, C.c_void_p, C.c_void_p, _I, _I, _L] + [C.c_void_p] * 6),
     "tvf_linear_f_pose_dev": (_I, [_H, C.c_void_p, C.c_void_p, _I, _I, _L] + [C.c_void_p] * 8),
     "tvf_launch_count": (_L, [_H]),
+    "tvf_profile_enable": (_I, [_H, _I]),
+    "tvf_profile_reset": (_I, [_H]),
+    "tvf_profile_read": (_I, [_H, _D, C.POINTER(C.c_int64)]),
+    "tvf_kernel_name": (C.c_char_p, [_I]),
+    "tvf_fp64_peak_tflops": (C.c_double, [_H]),
 }
+NUM_KERNELS = 10
 
 _lib = None
 _lock = threading.Lock()

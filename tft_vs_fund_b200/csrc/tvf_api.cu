@@ -44,6 +44,13 @@ struct tvf_context {
     size_t scratch_cap[NSCRATCH] = {};
     std::string err;
     int64_t launches = 0;
+    // optional per-kernel CUDA-event timing (tvf_profile_*): (kernel id, start, stop) per launch
+    bool profiling = false;
+    struct Ev { int id; cudaEvent_t a, b; };
+    std::vector<Ev> events;
+    std::vector<cudaEvent_t> free_events;
+    double prof_ms[TVF_NUM_KERNELS] = {};
+    int64_t prof_n[TVF_NUM_KERNELS] = {};
 };
 
 namespace {
@@ -93,7 +100,7 @@ struct Carver {
 };
 
 struct ChunkBufs {
-    double* in; double* calm; double* T; double* F; double* cand; int* votes; double* scale;
+    double* in; double* calm; double* T; double* F; double* core; double* cand; int* votes; double* scale;
     double* Rt2; double* Rt3; double* reconst; double* repr; int* status;
 };
 
@@ -102,6 +109,7 @@ size_t carve(char* base, int n, int64_t C, bool host_io, bool calm_batched, Chun
     ChunkBufs b{};
     b.T = c.take<double>(27 * C);
     b.F = c.take<double>(18 * C);
+    b.core = c.take<double>((size_t)CORE_WS_TFT * C);
     b.cand = c.take<double>((size_t)CAND_SIZE * C);
     b.votes = c.take<int>(10 * C);
     b.scale = c.take<double>(2 * C);
@@ -121,7 +129,7 @@ size_t carve(char* base, int n, int64_t C, bool host_io, bool calm_batched, Chun
 int64_t pick_chunk(tvf_handle_t h, int n, int64_t B, bool host_io) {
     int64_t c = h->chunk_user > 0 ? h->chunk_user : DEFAULT_CHUNK;
     if (h->chunk_user <= 0) {   // automatic: keep one slot's work space near ARENA_BUDGET
-        size_t payload = (27 + 18 + CAND_SIZE + 2) * 8 + 11 * 4;
+        size_t payload = (27 + 18 + CORE_WS_TFT + CAND_SIZE + 2) * 8 + 11 * 4;
         if (host_io) payload += (size_t)(6 * n + 27 + 24 + 3 * n + 1) * 8;
         const int64_t fit = (int64_t)(ARENA_BUDGET / payload);
         if (c > fit) c = fit;
@@ -133,9 +141,40 @@ int64_t pick_chunk(tvf_handle_t h, int n, int64_t B, bool host_io) {
 
 enum Method { METHOD_TFT = 0, METHOD_F = 1 };
 
+cudaEvent_t get_event(tvf_handle_t h) {
+    if (!h->free_events.empty()) { cudaEvent_t e = h->free_events.back(); h->free_events.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+
+// launch `f` (one kernel) on `st`, bracketed by events when profiling is on
+template <typename F>
+void timed_launch(tvf_handle_t h, int id, cudaStream_t st, F f) {
+    if (!h->profiling) { f(); h->launches += 1; return; }
+    tvf_context::Ev ev{id, get_event(h), get_event(h)};
+    cudaEventRecord(ev.a, st);
+    f();
+    cudaEventRecord(ev.b, st);
+    h->events.push_back(ev);
+    h->launches += 1;
+}
+
+int drain_events(tvf_handle_t h) {
+    for (auto& ev : h->events) {
+        TVF_CK(cudaEventSynchronize(ev.b));
+        float ms = 0.f;
+        TVF_CK(cudaEventElapsedTime(&ms, ev.a, ev.b));
+        h->prof_ms[ev.id] += ms; h->prof_n[ev.id] += 1;
+        h->free_events.push_back(ev.a); h->free_events.push_back(ev.b);
+    }
+    h->events.clear();
+    return TVF_OK;
+}
+
 // kernels of one chunk; all pointers are device pointers
 int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double* d_corresp, const double* d_calm,
-                   int calm_batched, int n, int64_t Bc, double* d_T, double* d_F, double* d_cand, int* d_votes,
+                   int calm_batched, int n, int64_t Bc, double* d_T, double* d_F, double* d_core, double* d_cand, int* d_votes,
                    double* d_scale, double* d_Rt2, double* d_Rt3, double* d_reconst, double* d_repr, int* d_status) {
     CoreInput in{};
     in.p1 = d_corresp; in.p2 = nullptr; in.p3 = nullptr; in.packed = 1; in.rows = 2; in.n = n; in.B = Bc; in.normalize = 1;
@@ -143,18 +182,22 @@ int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double*
     a.corresp = d_corresp; a.calm = d_calm; a.calm_batched = calm_batched; a.n = n; a.B = Bc;
     a.cand = d_cand; a.votes = d_votes; a.scale = d_scale;
     a.Rt2 = d_Rt2; a.Rt3 = d_Rt3; a.reconst = d_reconst; a.repr_err = d_repr; a.status = d_status;
+    const int sm = h->sm_count;
     if (method == METHOD_TFT) {
-        launch_tft_core(in, d_T, nullptr, nullptr, d_status, h->sm_count, st);
-        launch_candidates(0, d_T, a, st);
-        launch_pose_tail(a, h->sm_count, st);
-        h->launches += 5;
+        timed_launch(h, TVF_K_TFT_STAGE1, st, [&] { launch_tft_stage1(in, d_core, d_status, sm, st); });
+        timed_launch(h, TVF_K_TFT_EPIPOLES, st, [&] { launch_tft_epipoles(d_core, Bc, st); });
+        timed_launch(h, TVF_K_TFT_STAGE2, st, [&] { launch_tft_stage2(1, Bc, d_core, d_T, nullptr, nullptr, d_status, sm, st); });
+        timed_launch(h, TVF_K_CANDIDATES, st, [&] { launch_candidates(0, d_T, a, st); });
     } else {
-        launch_f_core(in, d_F, d_status, h->sm_count, st);
-        launch_candidates(1, d_F, a, st);
-        launch_pose_tail(a, h->sm_count, st);
-        if (d_T != nullptr) { launch_tft_from_pose(d_calm, calm_batched, d_Rt2, d_Rt3, Bc, d_T, st); h->launches += 1; }
-        h->launches += 5;
+        timed_launch(h, TVF_K_F_STAGE1, st, [&] { launch_f_stage1(in, d_core, d_status, sm, st); });
+        timed_launch(h, TVF_K_F_FINISH, st, [&] { launch_f_finish(d_core, 1, Bc, d_F, st); });
+        timed_launch(h, TVF_K_CANDIDATES, st, [&] { launch_candidates(1, d_F, a, st); });
     }
+    timed_launch(h, TVF_K_VOTES, st, [&] { launch_votes(a, sm, st); });
+    timed_launch(h, TVF_K_SCALE, st, [&] { launch_scale(a, sm, st); });
+    timed_launch(h, TVF_K_FINAL, st, [&] { launch_final(a, sm, st); });
+    if (method == METHOD_F && d_T != nullptr)
+        timed_launch(h, TVF_K_TFT_FROM_POSE, st, [&] { launch_tft_from_pose(d_calm, calm_batched, d_Rt2, d_Rt3, Bc, d_T, st); });
     TVF_CK(cudaGetLastError());
     return TVF_OK;
 }
@@ -206,7 +249,7 @@ int pose_host(tvf_handle_t h, Method method, const double* corresp, const double
             d_calm = b.calm;
         }
         rc = run_pose_chunk(h, s.stream, method, b.in, d_calm, calm_batched, n, Bc,
-                            (method == METHOD_TFT || T) ? b.T : nullptr, b.F, b.cand, b.votes, b.scale, b.Rt2, b.Rt3,
+                            (method == METHOD_TFT || T) ? b.T : nullptr, b.F, b.core, b.cand, b.votes, b.scale, b.Rt2, b.Rt3,
                             b.reconst, b.repr, b.status);
         if (rc) return rc;
         if (Rt2) TVF_CK(cudaMemcpyAsync(Rt2 + done * 12, b.Rt2, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
@@ -247,7 +290,7 @@ int pose_dev(tvf_handle_t h, Method method, const double* corresp, const double*
         double* dRt2 = Rt2 ? Rt2 + done * 12 : tmpRt2;
         double* dRt3 = Rt3 ? Rt3 + done * 12 : tmpRt3;
         rc = run_pose_chunk(h, st, method, corresp + done * 6 * n, calm + (calm_batched ? done * 27 : 0), calm_batched, n,
-                            Bc, dT, b.F, b.cand, b.votes, b.scale, dRt2, dRt3, reconst ? reconst + done * 3 * n : nullptr,
+                            Bc, dT, b.F, b.core, b.cand, b.votes, b.scale, dRt2, dRt3, reconst ? reconst + done * 3 * n : nullptr,
                             repr_err ? repr_err + done : nullptr, status ? status + done : b.status);
         if (rc) return rc;
         if (method == METHOD_F && F21)
@@ -286,6 +329,18 @@ struct Up {
         return TVF_OK;
     }
 };
+
+// dense, dependency-free-ish DFMA loop: the FP64 roofline denominator measured on this very device
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double seed) {
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-6;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+    }
+    const double r = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+    if (r == 123.456) out[0] = r;      // never true; keeps the loop alive
+}
 
 }  // namespace
 
@@ -333,6 +388,8 @@ void tvf_destroy(tvf_handle_t h) {
     }
     for (int i = 0; i < NSCRATCH; ++i)
         if (h->scratch[i]) cudaFree(h->scratch[i]);
+    for (auto& ev : h->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+    for (auto e : h->free_events) cudaEventDestroy(e);
     delete h;
 }
 
@@ -377,6 +434,58 @@ void tvf_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 int64_t tvf_launch_count(tvf_handle_t h) { return h ? h->launches : 0; }
 
+int tvf_profile_enable(tvf_handle_t h, int on) {
+    if (!h) return TVF_ERR_ARG;
+    if (!on && h->profiling) { int rc = drain_events(h); if (rc) return rc; }
+    h->profiling = on != 0;
+    return TVF_OK;
+}
+
+int tvf_profile_reset(tvf_handle_t h) {
+    if (!h) return TVF_ERR_ARG;
+    int rc = drain_events(h); if (rc) return rc;
+    for (int i = 0; i < TVF_NUM_KERNELS; ++i) { h->prof_ms[i] = 0.0; h->prof_n[i] = 0; }
+    return TVF_OK;
+}
+
+int tvf_profile_read(tvf_handle_t h, double* total_ms, int64_t* launches) {
+    if (!h || !total_ms || !launches) return TVF_ERR_ARG;
+    int rc = drain_events(h); if (rc) return rc;
+    for (int i = 0; i < TVF_NUM_KERNELS; ++i) { total_ms[i] = h->prof_ms[i]; launches[i] = h->prof_n[i]; }
+    return TVF_OK;
+}
+
+double tvf_fp64_peak_tflops(tvf_handle_t h) {
+    if (!h) return -1.0;
+    if (cudaSetDevice(h->device) != cudaSuccess) return -1.0;
+    cudaStream_t st = h->slot[0].stream;
+    void* p = nullptr;
+    if (ensure_scratch(h, NSCRATCH - 1, 64, &p) != TVF_OK) return -1.0;
+    const int iters = 1 << 15, blocks = h->sm_count * 8;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        cudaEventRecord(a, st);
+        fp64_peak_kernel<<<blocks, 256, 0, st>>>((double*)p, iters, 1.0 + rep);
+        cudaEventRecord(b, st);
+        if (cudaEventSynchronize(b) != cudaSuccess) { best = -1.0; break; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, a, b);
+        const double tf = (double)blocks * 256.0 * iters * 8.0 * 2.0 / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;     // first repetition is warm-up
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    return best;
+}
+
+const char* tvf_kernel_name(int id) {
+    static const char* names[TVF_NUM_KERNELS] = {"tft_stage1_kernel", "tft_epipoles_kernel", "tft_stage2_kernel",
+                                                 "f_stage1_kernel", "f_finish_kernel", "candidates_kernel",
+                                                 "votes_kernel", "scale_kernel", "final_kernel", "tft_from_pose_kernel"};
+    return (id >= 0 && id < TVF_NUM_KERNELS) ? names[id] : "";
+}
+
 int tvf_linear_tft_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
                         double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, int32_t* status) {
     return pose_host(h, METHOD_TFT, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, nullptr, nullptr, status);
@@ -415,9 +524,12 @@ int tvf_linear_tft(tvf_handle_t h, const double* p1, const double* p2, const dou
     double* dP2 = u.out<double>(12 * (size_t)B);
     double* dP3 = u.out<double>(12 * (size_t)B);
     int* dst = u.out<int>((size_t)B);
+    double* dws = u.out<double>((size_t)CORE_WS_TFT * B);
     if (u.rc) return u.rc;
-    launch_tft_core(in, dT, dP2, dP3, dst, h->sm_count, u.st);
-    h->launches += 1;
+    launch_tft_stage1(in, dws, dst, h->sm_count, u.st);
+    launch_tft_epipoles(dws, B, u.st);
+    launch_tft_stage2(0, B, dws, dT, dP2, dP3, dst, h->sm_count, u.st);
+    h->launches += 3;
     std::vector<int32_t> tmp; int32_t* sth = status;
     if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }
     u.back(T, dT, 27 * (size_t)B); u.back(P2, dP2, 12 * (size_t)B); u.back(P3, dP3, 12 * (size_t)B);
@@ -441,9 +553,11 @@ int tvf_linear_f(tvf_handle_t h, const double* p1, const double* p2, int rows, i
     in.packed = 0; in.rows = rows; in.n = n; in.B = B; in.normalize = 0;
     double* dF = u.out<double>(9 * (size_t)B);
     int* dst = u.out<int>((size_t)B);
+    double* dws = u.out<double>((size_t)CORE_WS_F * B);
     if (u.rc) return u.rc;
-    launch_f_core(in, dF, dst, h->sm_count, u.st);
-    h->launches += 1;
+    launch_f_stage1(in, dws, dst, h->sm_count, u.st);
+    launch_f_finish(dws, 0, B, dF, u.st);
+    h->launches += 2;
     std::vector<int32_t> tmp; int32_t* sth = status;
     if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }
     u.back(F, dF, 9 * (size_t)B);
@@ -504,7 +618,9 @@ int tvf_rt_from_tft(tvf_handle_t h, const double* T, const double* calm, int cal
     if (u.rc) return u.rc;
     TVF_CK(cudaMemsetAsync(a.status, 0, (size_t)B * sizeof(int), u.st));
     launch_candidates(0, dT, a, u.st);
-    launch_pose_tail(a, h->sm_count, u.st);
+    launch_votes(a, h->sm_count, u.st);
+    launch_scale(a, h->sm_count, u.st);
+    launch_final(a, h->sm_count, u.st);
     h->launches += 4;
     std::vector<int32_t> tmp; int32_t* sth = status;
     if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }

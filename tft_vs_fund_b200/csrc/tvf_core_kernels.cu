@@ -1,14 +1,19 @@
-// tvf_core_kernels.cu -- warp-per-problem kernels for the two model estimators:
-//   tft_core_kernel : Normalize2Ddata x3 (optional) -> 96 Kronecker moments ->
-//                     27x27 Gram -> null vector -> epipoles -> 15-dim constrained
-//                     re-solve -> (optional) undo normalisation
-//                     (Normalize2Ddata.m:33-39, linearTFT.m:36-91,
-//                      LinearTFTPoseEstimation.m:45-53)
-//   f_core_kernel   : same idea for linearF.m:32-62 (36 moments, 9x9 Gram,
-//                     rank-2 projection) and LinearFPoseEstimation.m:46-56
-// One warp owns one triplet problem; the Gram never exists as a 4n x 27 design
-// matrix: G = sum_i (p1 p1') (x) (S3 S3') (x) (S2 S2') is assembled from 96
-// per-problem moments.
+// tvf_core_kernels.cu -- the two model estimators.
+//
+// linearTFT (TFT_methods/linearTFT.m:36-91, called from LinearTFTPoseEstimation.m:45-53):
+//   tft_stage1_kernel   warp per problem   Normalize2Ddata x3 -> 96 Kronecker moments -> 27x27 Gram
+//                                          -> null vector t1 (linearTFT.m:45-67)
+//   tft_epipoles_kernel thread per problem epipoles of t1: eight 3x3 SVDs (linearTFT.m:71-79)
+//   tft_stage2_kernel   warp per problem   15-dim constrained re-solve in range(E), P2/P3, undo the
+//                                          normalisation (linearTFT.m:82-91, LinearTFTPoseEstimation.m:53)
+// linearF (F_methods/linearF.m:32-62, called from LinearFPoseEstimation.m:46-56):
+//   f_stage1_kernel     warp per problem   (re-)normalisation, 36 moments, 9x9 Gram -> null vector
+//   f_finish_kernel     thread per problem undo inner normalisation, rank-2 projection, undo outer one
+//
+// The design matrix never exists: G = A'A = sum_i (p1 p1') (x) (S3 S3') (x) (S2 S2') is assembled from
+// 96 per-problem moments, and the second null-vector problem needs no second pass over
+// the points because (A*Up)'(A*Up) = Up' G Up.  The scalar 3x3 SVD work sits in thread-per-problem
+// kernels so that it runs at 32 problems per warp instead of one.
 #include "tvf_kernels.h"
 #include "tvf_warp.cuh"
 #include "tvf_pose.cuh"
@@ -18,26 +23,19 @@ namespace tvf {
 constexpr int CORE_WARPS = 8;
 constexpr int FEAT_STRIDE = 15;   // 14 features + 1 pad: conflict-free 64-bit lane-strided stores
 
-// per-warp shared scratch (doubles)
-struct __align__(16) WarpScratch {
-    double feat[32 * FEAT_STRIDE];   // per-point features; reused as W (27 x 15) in the constrained step
-    double mom[98];                  // 96 moments + zero sentinel
-    double T[28];                    // current tensor / F vector
-    double vs[18];                   // slice null vectors
-    double epi[6];                   // e21, e31
-    double tp[16];
-    double Nm[27];                   // N1, inv(N2), inv(N3)   (3x3 column-major each)
-};
+// per-problem work-space record handed from stage to stage (doubles)
+constexpr int CW_MOM = 0, CW_STATS = 96, CW_T1 = 106, CW_EPI = 134;      // CORE_WS_TFT = 140
+constexpr int FW_F = 0, FW_STATS = 18;                                   // CORE_WS_F = 36
 
-// index tables: which moment feeds G(r,c); 96 = structural zero
 __device__ __constant__ unsigned char c_sym6[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
 __device__ __constant__ signed char c_m4[9] = {0, -1, 1, -1, 0, 2, 1, 2, 3};
 
 // v[i] for a runtime i without forcing the array into local memory
 __device__ __forceinline__ double sel3(const double* v, int i) { return (i == 0) ? v[0] : ((i == 1) ? v[1] : v[2]); }
 
+template <bool PACKED>
 __device__ __forceinline__ void load_point(const CoreInput& in, long long prob, int i, double* p) {
-    if (in.packed) {
+    if (PACKED) {
         const double2* q = reinterpret_cast<const double2*>(in.p1 + (prob * in.n + i) * 6);
         const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
         p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y; p[4] = c.x; p[5] = c.y;
@@ -55,15 +53,15 @@ __device__ __forceinline__ void load_point(const CoreInput& in, long long prob, 
 }
 
 // Normalize2Ddata.m:34-37 for the three views at once, on points already mapped by
-// x -> s0*x + t0 (identity when the outer map is absent).  Returns per view (sx, tx, ty)
-// with new = s*x + t.
+// x -> s0*x + t0 (identity when there is no outer map).  new = s*x + t.
+template <bool PACKED>
 __device__ __forceinline__ void view_stats(const CoreInput& in, long long prob, int lane,
                                            const double* s0, const double* t0, double* s, double* t) {
     const int n = in.n;
     double sum[6] = {0, 0, 0, 0, 0, 0};
     for (int i = lane; i < n; i += 32) {
         double p[6];
-        load_point(in, prob, i, p);
+        load_point<PACKED>(in, prob, i, p);
 #pragma unroll
         for (int q = 0; q < 6; ++q) sum[q] += s0[q >> 1] * p[q] + t0[q];
     }
@@ -74,7 +72,7 @@ __device__ __forceinline__ void view_stats(const CoreInput& in, long long prob, 
     double d[3] = {0, 0, 0};
     for (int i = lane; i < n; i += 32) {
         double p[6];
-        load_point(in, prob, i, p);
+        load_point<PACKED>(in, prob, i, p);
 #pragma unroll
         for (int v = 0; v < 3; ++v) {
             const double dx = (s0[v] * p[2 * v] + t0[2 * v]) - c[2 * v];
@@ -91,15 +89,8 @@ __device__ __forceinline__ void view_stats(const CoreInput& in, long long prob, 
     }
 }
 
-// ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(CORE_WARPS * 32, 2)
-tft_core_kernel(CoreInput in, double* __restrict__ Tout, double* __restrict__ P2out,
-                double* __restrict__ P3out, int* __restrict__ status) {
-    __shared__ WarpScratch scratch[CORE_WARPS];
-    __shared__ unsigned char gidx[32 * 27];
-
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // G(r,c) -> moment index table (shared by all warps of the CTA)
+// G(r,c) -> moment index (96 = structural zero), one table per CTA
+__device__ __forceinline__ void build_gidx(unsigned char* gidx) {
     for (int e = threadIdx.x; e < 32 * 27; e += blockDim.x) {
         const int r = e / 27, c = e % 27;
         int idx = 96;
@@ -111,40 +102,55 @@ tft_core_kernel(CoreInput in, double* __restrict__ Tout, double* __restrict__ P2
         }
         gidx[e] = (unsigned char)idx;
     }
-    __syncthreads();
+}
 
-    WarpScratch& ws = scratch[warp];
-    const int jr = lane % 3, kr = (lane / 3) % 3, ir = lane / 9;   // tensor indices of this lane's row (lane<27)
+// =========================================================================== TFT stage 1
+struct __align__(16) Stage1Scratch {
+    double sbuf[64];                 // solver row/vector buffers
+    double feat[32 * FEAT_STRIDE];   // per-point features
+    double mom[98];                  // 96 moments + zero sentinel
+};
 
-    for (long long prob = (long long)blockIdx.x * CORE_WARPS + warp; prob < in.B;
-         prob += (long long)gridDim.x * CORE_WARPS) {
-        int st = 0;
-        // ---- normalisation (LinearTFTPoseEstimation.m:45-47) --------------------------
+template <bool PACKED>
+__global__ void __launch_bounds__(CORE_WARPS * 32, 2)
+tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
+    __shared__ Stage1Scratch scratch[CORE_WARPS];
+    __shared__ unsigned char gidx[32 * 27];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    build_gidx(gidx);
+    Stage1Scratch& sc = scratch[warp];
+    const int beta = (lane >> 2) & 3, gamma = lane & 3, alpha0 = lane >> 4;
+
+    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < in.B; base += (long long)gridDim.x * CORE_WARPS) {
+        __syncthreads();             // keeps the CTA's warps in step: they share instruction-cache lines
+        const long long prob = base + warp;
+        if (prob >= in.B) continue;
+        double* rec = ws + prob * CORE_WS_TFT;
+        // ---- normalisation (LinearTFTPoseEstimation.m:45-47) -----------------------------
         double s[3] = {1.0, 1.0, 1.0}, t[6] = {0, 0, 0, 0, 0, 0};
         if (in.normalize) {
             const double s0[3] = {1.0, 1.0, 1.0}, t0[6] = {0, 0, 0, 0, 0, 0};
-            view_stats(in, prob, lane, s0, t0, s, t);
+            view_stats<PACKED>(in, prob, lane, s0, t0, s, t);
         }
-        // ---- 96 moments ----------------------------------------------------------------
-        const int beta = (lane >> 2) & 3, gamma = lane & 3, alpha0 = lane >> 4;
+        // ---- 96 moments: lane l accumulates moments l, l+32, l+64 -----------------------
         double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-        for (int base = 0; base < in.n; base += 32) {
-            const int cnt = min(32, in.n - base);
+        for (int pbase = 0; pbase < in.n; pbase += 32) {
+            const int cnt = min(32, in.n - pbase);
             __syncwarp();
             if (lane < cnt) {
                 double p[6];
-                load_point(in, prob, base + lane, p);
+                load_point<PACKED>(in, prob, pbase + lane, p);
                 const double x1 = s[0] * p[0] + t[0], y1 = s[0] * p[1] + t[1];
                 const double x2 = s[1] * p[2] + t[2], y2 = s[1] * p[3] + t[3];
                 const double x3 = s[2] * p[4] + t[4], y3 = s[2] * p[5] + t[5];
-                double* f = ws.feat + lane * FEAT_STRIDE;
+                double* f = sc.feat + lane * FEAT_STRIDE;
                 f[0] = x1 * x1; f[1] = x1 * y1; f[2] = x1; f[3] = y1 * y1; f[4] = y1; f[5] = 1.0;
                 f[6] = 1.0; f[7] = -x3; f[8] = -y3; f[9] = x3 * x3 + y3 * y3;
                 f[10] = 1.0; f[11] = -x2; f[12] = -y2; f[13] = x2 * x2 + y2 * y2;
             }
             __syncwarp();
             for (int p = 0; p < cnt; ++p) {
-                const double* f = ws.feat + p * FEAT_STRIDE;
+                const double* f = sc.feat + p * FEAT_STRIDE;
                 const double bc = f[6 + beta] * f[10 + gamma];
                 acc0 = fma(f[alpha0], bc, acc0);
                 acc1 = fma(f[alpha0 + 2], bc, acc1);
@@ -152,59 +158,86 @@ tft_core_kernel(CoreInput in, double* __restrict__ Tout, double* __restrict__ P2
             }
         }
         __syncwarp();
-        ws.mom[lane] = acc0; ws.mom[lane + 32] = acc1; ws.mom[lane + 64] = acc2;
-        if (lane == 0) { ws.mom[96] = 0.0; ws.mom[97] = 0.0; }
+        sc.mom[lane] = acc0; sc.mom[lane + 32] = acc1; sc.mom[lane + 64] = acc2;
+        if (lane == 0) { sc.mom[96] = 0.0; sc.mom[97] = 0.0; }
+        rec[CW_MOM + lane] = acc0; rec[CW_MOM + 32 + lane] = acc1; rec[CW_MOM + 64 + lane] = acc2;
+        if (lane < 3) rec[CW_STATS + lane] = sel3(s, lane);
+        if (lane < 6) rec[CW_STATS + 3 + lane] = (lane < 3) ? sel3(t, lane) : sel3(t + 3, lane - 3);
         __syncwarp();
-
-        // ---- stage 1: null vector of the 27x27 Gram (linearTFT.m:64-67) ------------------
+        // ---- null vector of the 27x27 Gram (linearTFT.m:64-67) ---------------------------
         double g[27];
 #pragma unroll
-        for (int c = 0; c < 27; ++c) g[c] = ws.mom[gidx[lane * 27 + c]];
+        for (int c = 0; c < 27; ++c) g[c] = sc.mom[gidx[lane * 27 + c]];
         bool conv;
-        double tl = smallest_eigvec_spd<27>(g, lane, &conv);
-        if (!conv) st |= ST_EIG_NOCONV;
-        if (lane < 27) ws.T[lane] = tl;
-        __syncwarp();
+        const double tl = smallest_eigvec_spd<27>(g, lane, sc.sbuf, &conv);
+        if (lane < 27) rec[CW_T1 + lane] = tl;
+        if (status != nullptr && lane == 0) status[prob] = conv ? 0 : ST_EIG_NOCONV;
+    }
+}
 
-        // ---- epipoles (linearTFT.m:71-79): six slice problems on six lanes ---------------
-        {
-            const int l6 = lane % 6, sl = l6 % 3, tr = l6 / 3;
-            double M[9], v[3];
+// =========================================================================== TFT epipoles
+__global__ void __launch_bounds__(128)
+tft_epipoles_kernel(double* __restrict__ ws, long long B) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double* rec = ws + b * CORE_WS_TFT;
+    double T[27];
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+    for (int i = 0; i < 27; ++i) T[i] = rec[CW_T1 + i];
+    double e21[3], e31[3];
+    tft_epipoles(T, e21, e31);                                             // linearTFT.m:71-79
 #pragma unroll
-                for (int r = 0; r < 3; ++r) M[r + 3 * c] = tr ? ws.T[9 * sl + c + 3 * r] : ws.T[9 * sl + r + 3 * c];
-            null3(M, v);
-            if (lane < 6) { ws.vs[3 * lane] = v[0]; ws.vs[3 * lane + 1] = v[1]; ws.vs[3 * lane + 2] = v[2]; }
-            __syncwarp();
-            const int which = lane & 1;           // 0: e31 from slices, 1: e21 from transposed slices
-            double e[3];
-            epipole_from_nulls(ws.vs + 9 * which, ws.vs + 9 * which + 3, ws.vs + 9 * which + 6, e);
-            if (lane < 2) { ws.epi[3 * (1 - which)] = e[0]; ws.epi[3 * (1 - which) + 1] = e[1]; ws.epi[3 * (1 - which) + 2] = e[2]; }
-            __syncwarp();
-        }
-        double e21[3] = {ws.epi[0], ws.epi[1], ws.epi[2]};
-        double e31[3] = {ws.epi[3], ws.epi[4], ws.epi[5]};
+    for (int i = 0; i < 3; ++i) { rec[CW_EPI + i] = e21[i]; rec[CW_EPI + 3 + i] = e31[i]; }
+}
+
+// =========================================================================== TFT stage 2
+struct __align__(16) Stage2Scratch {
+    double sbuf[64];
+    double W[27 * FEAT_STRIDE + 3];  // G*Up, 27 x 15 (row stride 15)
+    double mom[98];
+    double T[28];
+    double tp[16];
+    double Nm[28];                   // N1, inv(N2), inv(N3)
+};
+
+__global__ void __launch_bounds__(CORE_WARPS * 32, 2)
+tft_stage2_kernel(int normalize, long long B, const double* __restrict__ ws, double* __restrict__ Tout,
+                  double* __restrict__ P2out, double* __restrict__ P3out, int* __restrict__ status) {
+    __shared__ Stage2Scratch scratch[CORE_WARPS];
+    __shared__ unsigned char gidx[32 * 27];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    build_gidx(gidx);
+    Stage2Scratch& sc = scratch[warp];
+    const int jr = lane % 3, kr = (lane / 3) % 3, ir = (lane < 27) ? lane / 9 : 0;
+
+    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < B; base += (long long)gridDim.x * CORE_WARPS) {
+        __syncthreads();
+        const long long prob = base + warp;
+        if (prob >= B) continue;
+        const double* rec = ws + prob * CORE_WS_TFT;
+        sc.mom[lane] = rec[CW_MOM + lane]; sc.mom[lane + 32] = rec[CW_MOM + 32 + lane]; sc.mom[lane + 64] = rec[CW_MOM + 64 + lane];
+        if (lane == 0) { sc.mom[96] = 0.0; sc.mom[97] = 0.0; }
+        const double e21[3] = {rec[CW_EPI], rec[CW_EPI + 1], rec[CW_EPI + 2]};
+        const double e31[3] = {rec[CW_EPI + 3], rec[CW_EPI + 4], rec[CW_EPI + 5]};
         double u1[3], u2[3], v1[3], v2[3];
         onb3(e21, u1, u2);
         onb3(e31, v1, v2);
-
-        // ---- stage 2: constrained re-solve in range(E) (linearTFT.m:82-85) ---------------
-        // basis per slice: B0=e21 e31', B1=e21 v1', B2=e21 v2', B3=u1 e31', B4=u2 e31'
+        __syncwarp();
+        // basis of range(E) per slice: B0=e21 e31', B1=e21 v1', B2=e21 v2', B3=u1 e31', B4=u2 e31'
+        // W = G*Up: first contract j' with {e21,u1,u2}, then k' with {e31,v1,v2}
         {
-            double Ze[9], Zu1[9], Zu2[9];   // Z_p[k'+3i'] = sum_j' G(r,(j',k',i')) p[j']
+            double Ze[9], Zu1[9], Zu2[9];
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
-                const double g0 = ws.mom[gidx[lane * 27 + 3 * q]];
-                const double g1 = ws.mom[gidx[lane * 27 + 3 * q + 1]];
-                const double g2 = ws.mom[gidx[lane * 27 + 3 * q + 2]];
+                const double g0 = sc.mom[gidx[lane * 27 + 3 * q]];
+                const double g1 = sc.mom[gidx[lane * 27 + 3 * q + 1]];
+                const double g2 = sc.mom[gidx[lane * 27 + 3 * q + 2]];
                 Ze[q] = g0 * e21[0] + g1 * e21[1] + g2 * e21[2];
                 Zu1[q] = g0 * u1[0] + g1 * u1[1] + g2 * u1[2];
                 Zu2[q] = g0 * u2[0] + g1 * u2[1] + g2 * u2[2];
             }
-            __syncwarp();   // feat no longer needed -> reuse as W
             if (lane < 27) {
-                double* W = ws.feat + lane * FEAT_STRIDE;
+                double* W = sc.W + lane * FEAT_STRIDE;
 #pragma unroll
                 for (int i2 = 0; i2 < 3; ++i2) {
                     const double* ze = Ze + 3 * i2; const double* zu1 = Zu1 + 3 * i2; const double* zu2 = Zu2 + 3 * i2;
@@ -217,7 +250,9 @@ tft_core_kernel(CoreInput in, double* __restrict__ Tout, double* __restrict__ P2
             }
             __syncwarp();
         }
+        // G15 = Up' W, lane (i,a) owns row 5i+a; then its smallest eigenvector (linearTFT.m:84)
         double tl2;
+        int st = 0;
         {
             const int ia = (lane < 15) ? lane / 5 : 0, aa = (lane < 15) ? lane % 5 : 0;
             double pa[3], qa[3];
@@ -233,38 +268,32 @@ tft_core_kernel(CoreInput in, double* __restrict__ Tout, double* __restrict__ P2
             for (int k = 0; k < 3; ++k)
 #pragma unroll
                 for (int j = 0; j < 3; ++j) {
-                    const double coef = pa[j] * qa[k];
-                    const double* W = ws.feat + (9 * ia + 3 * k + j) * FEAT_STRIDE;
+                    const double coef = (lane < 15) ? pa[j] * qa[k] : 0.0;
+                    const double* W = sc.W + (9 * ia + 3 * k + j) * FEAT_STRIDE;
 #pragma unroll
                     for (int c = 0; c < 15; ++c) g15[c] = fma(coef, W[c], g15[c]);
                 }
-            if (lane >= 15) {
-#pragma unroll
-                for (int c = 0; c < 15; ++c) g15[c] = 0.0;
-            }
             bool conv2;
-            const double tpl = smallest_eigvec_spd<15>(g15, lane, &conv2);
+            const double tpl = smallest_eigvec_spd<15>(g15, lane, sc.sbuf, &conv2);
             if (!conv2) st |= ST_EIG_NOCONV;
-            if (lane < 15) ws.tp[lane] = tpl;
+            if (lane < 15) sc.tp[lane] = tpl;
             __syncwarp();
-            // t = Up*tp  (linearTFT.m:85)
-            double acc = 0.0;
+            double acc = 0.0;                                                   // t = Up*tp  (linearTFT.m:85)
             if (lane < 27) {
-                const double* tp = ws.tp + 5 * ir;
+                const double* tp = sc.tp + 5 * ir;
                 const double pe = sel3(e21, jr), pu1 = sel3(u1, jr), pu2 = sel3(u2, jr);
                 const double qe = sel3(e31, kr), qv1 = sel3(v1, kr), qv2 = sel3(v2, kr);
                 acc = pe * (qe * tp[0] + qv1 * tp[1] + qv2 * tp[2]) + qe * (pu1 * tp[3] + pu2 * tp[4]);
             }
             tl2 = acc * rsqrt(warp_sum(acc * acc));
         }
-        __syncwarp();
-        if (lane < 27) ws.T[lane] = tl2;
+        if (lane < 27) sc.T[lane] = tl2;
         __syncwarp();
 
         // ---- P2, P3 (linearTFT.m:86-90): a = pinv(E) t in closed form --------------------
         if (P2out != nullptr && P3out != nullptr) {
             if (lane < 3) {
-                const double* Ti = ws.T + 9 * lane;
+                const double* Ti = sc.T + 9 * lane;
                 double a[3], b[3];
                 mat3_vec(Ti, e31, a);
                 mat3_tvec(Ti, e21, b);
@@ -280,168 +309,191 @@ tft_core_kernel(CoreInput in, double* __restrict__ Tout, double* __restrict__ P2
             }
         }
 
-        // ---- undo the normalisation (LinearTFTPoseEstimation.m:53) ----------------------
+        // ---- undo the normalisation (LinearTFTPoseEstimation.m:53 -> transform_TFT.m:43-49) ------
         double tout = tl2;
-        if (in.normalize) {
-            // N_v = [s 0 tx; 0 s ty; 0 0 1]; all lanes build the same matrices
-            double N1[9] = {s[0], 0, 0, 0, s[0], 0, t[0], t[1], 1.0};
-            double N2[9] = {s[1], 0, 0, 0, s[1], 0, t[2], t[3], 1.0};
-            double N3[9] = {s[2], 0, 0, 0, s[2], 0, t[4], t[5], 1.0};
+        if (normalize) {
+            const double s0 = rec[CW_STATS], s1 = rec[CW_STATS + 1], s2 = rec[CW_STATS + 2];
+            const double N1[9] = {s0, 0, 0, 0, s0, 0, rec[CW_STATS + 3], rec[CW_STATS + 4], 1.0};
+            const double N2[9] = {s1, 0, 0, 0, s1, 0, rec[CW_STATS + 5], rec[CW_STATS + 6], 1.0};
+            const double N3[9] = {s2, 0, 0, 0, s2, 0, rec[CW_STATS + 7], rec[CW_STATS + 8], 1.0};
             double N2i[9], N3i[9];
             inv3(N2, N2i); inv3(N3, N3i);
-            // dynamic register indexing is avoided by staging through shared memory
             if (lane == 0) {
 #pragma unroll
-                for (int q = 0; q < 9; ++q) { ws.Nm[q] = N1[q]; ws.Nm[9 + q] = N2i[q]; ws.Nm[18 + q] = N3i[q]; }
+                for (int q = 0; q < 9; ++q) { sc.Nm[q] = N1[q]; sc.Nm[9 + q] = N2i[q]; sc.Nm[18 + q] = N3i[q]; }
             }
             __syncwarp();
             double acc = 0.0;
             if (lane < 27) {
-                // T_new(j,k,i) = sum_{a,b} N2i(j,a) * (sum_r N1(r,i) T(a,b,r)) * N3i(k,b)   (transform_TFT.m:43-46)
 #pragma unroll
                 for (int b = 0; b < 3; ++b)
 #pragma unroll
                     for (int a = 0; a < 3; ++a) {
-                        const double sab = ws.Nm[3 * ir] * ws.T[a + 3 * b] + ws.Nm[1 + 3 * ir] * ws.T[9 + a + 3 * b] +
-                                           ws.Nm[2 + 3 * ir] * ws.T[18 + a + 3 * b];
-                        acc = fma(ws.Nm[9 + jr + 3 * a] * ws.Nm[18 + kr + 3 * b], sab, acc);
+                        const double sab = sc.Nm[3 * ir] * sc.T[a + 3 * b] + sc.Nm[1 + 3 * ir] * sc.T[9 + a + 3 * b] +
+                                           sc.Nm[2 + 3 * ir] * sc.T[18 + a + 3 * b];
+                        acc = fma(sc.Nm[9 + jr + 3 * a] * sc.Nm[18 + kr + 3 * b], sab, acc);
                     }
             }
             tout = acc * rsqrt(warp_sum(acc * acc));                                         // :49
         }
         if (lane < 27) Tout[prob * 27 + lane] = tout;
-        if (status != nullptr && lane == 0) status[prob] = st;
-        __syncwarp();
+        if (status != nullptr && lane == 0 && st != 0) status[prob] |= st;
     }
 }
 
-// ---------------------------------------------------------------------------
-// linearF.m:45-62 for one view pair inside the warp.  (s0,t0): outer map applied to the raw
-// points of the two views (identity for a direct linearF call).  Writes the 3x3 F
-// (column-major) into Fout (all lanes hold it).
-__device__ __forceinline__ int linear_f_pair(const CoreInput& in, long long prob, int lane, WarpScratch& ws,
-                                             int va, int vb, const double* s0, const double* t0,
-                                             const double* si, const double* ti, double* F) {
-    // inner map composed with outer: x' = si*(s0*x + t0) + ti
-    const double sa = si[va] * s0[va], sb = si[vb] * s0[vb];
-    const double tax = si[va] * t0[2 * va] + ti[2 * va], tay = si[va] * t0[2 * va + 1] + ti[2 * va + 1];
-    const double tbx = si[vb] * t0[2 * vb] + ti[2 * vb], tby = si[vb] * t0[2 * vb + 1] + ti[2 * vb + 1];
-    // 36 moments: lane l -> (alpha,beta) = (l/6, l%6); lanes 0..3 also take moment 32+l
-    const int m0 = lane, m1 = 32 + lane;
-    const int a0 = m0 / 6, b0 = m0 % 6, a1 = (m1 < 36) ? m1 / 6 : 0, b1 = (m1 < 36) ? m1 % 6 : 0;
-    double acc0 = 0.0, acc1 = 0.0;
-    for (int base = 0; base < in.n; base += 32) {
-        const int cnt = min(32, in.n - base);
-        __syncwarp();
-        if (lane < cnt) {
-            double p[6];
-            load_point(in, prob, base + lane, p);
-            const double x1 = sa * p[2 * va] + tax, y1 = sa * p[2 * va + 1] + tay;
-            const double x2 = sb * p[2 * vb] + tbx, y2 = sb * p[2 * vb + 1] + tby;
-            double* f = ws.feat + lane * FEAT_STRIDE;
-            f[0] = x1 * x1; f[1] = x1 * y1; f[2] = x1; f[3] = y1 * y1; f[4] = y1; f[5] = 1.0;
-            f[6] = x2 * x2; f[7] = x2 * y2; f[8] = x2; f[9] = y2 * y2; f[10] = y2; f[11] = 1.0;
-        }
-        __syncwarp();
-        for (int p = 0; p < cnt; ++p) {
-            const double* f = ws.feat + p * FEAT_STRIDE;
-            acc0 = fma(f[a0], f[6 + b0], acc0);
-            acc1 = fma(f[a1], f[6 + b1], acc1);
-        }
-    }
-    __syncwarp();
-    ws.mom[lane] = acc0;
-    if (lane < 4) ws.mom[32 + lane] = acc1;
-    __syncwarp();
-    // G9(r,c): r = 3*a + b with A row [x1x2, x1y2, x1, y1x2, y1y2, y1, x2, y2, 1]   (linearF.m:51-52)
-    double g[9];
-    {
-        const int ar = (lane < 9) ? lane / 3 : 0, br = (lane < 9) ? lane % 3 : 0;
-#pragma unroll
-        for (int c = 0; c < 9; ++c) {
-            const int ac = c / 3, bc = c % 3;
-            const double v = ws.mom[c_sym6[ar * 3 + ac] * 6 + c_sym6[br * 3 + bc]];
-            g[c] = (lane < 9) ? v : 0.0;
-        }
-    }
-    bool conv;
-    const double fl = smallest_eigvec_spd<9>(g, lane, &conv);
-    __syncwarp();
-    if (lane < 9) ws.T[lane] = fl;
-    __syncwarp();
-    // F = reshape(V(:,9),3,3); F = Normal2.'*F*Normal1 (inner maps only); rank-2 projection (:55-62)
-    double Fv[9];
-#pragma unroll
-    for (int q = 0; q < 9; ++q) Fv[q] = ws.T[q];
-    const double Na[9] = {si[va], 0, 0, 0, si[va], 0, ti[2 * va], ti[2 * va + 1], 1.0};
-    const double Nb[9] = {si[vb], 0, 0, 0, si[vb], 0, ti[2 * vb], ti[2 * vb + 1], 1.0};
-    double tmp[9], Fu[9];
-    mat3_mul_tn(Nb, Fv, tmp);
-    mat3_mul(tmp, Na, Fu);
-    double U[9], sv[3], V[9];
-    svd3_full(Fu, U, sv, V);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int r = 0; r < 3; ++r) F[r + 3 * c] = sv[0] * U[r] * V[c] + sv[1] * U[3 + r] * V[3 + c];
-    return conv ? 0 : ST_EIG_NOCONV;
-}
+// =========================================================================== linearF stage 1
+struct __align__(16) FScratch {
+    double sbuf[64];
+    double feat[32 * FEAT_STRIDE];
+    double mom[40];
+};
 
-// mode 0: direct linearF(p1,p2) -> Fout[9*prob];  mode 1: pose path, F21 -> Fout[18*prob], F31 -> +9
+// mode: in.normalize != 0 -> pose path (two pairs 1-2 and 1-3, outer normalisation); else one pair
+template <bool PACKED>
 __global__ void __launch_bounds__(CORE_WARPS * 32, 2)
-f_core_kernel(CoreInput in, double* __restrict__ Fout, int* __restrict__ status) {
-    __shared__ WarpScratch scratch[CORE_WARPS];
+f_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
+    __shared__ FScratch scratch[CORE_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpScratch& ws = scratch[warp];
-    for (long long prob = (long long)blockIdx.x * CORE_WARPS + warp; prob < in.B;
-         prob += (long long)gridDim.x * CORE_WARPS) {
-        int st = 0;
+    FScratch& sc = scratch[warp];
+    // 36 moments: lane l -> (alpha,beta) = (l/6, l%6); lanes 0..3 also take moment 32+l
+    const int m1 = 32 + lane;
+    const int a0 = lane / 6, b0 = lane % 6, a1 = (m1 < 36) ? m1 / 6 : 0, b1 = (m1 < 36) ? m1 % 6 : 0;
+    const int ar = (lane < 9) ? lane / 3 : 0, br = (lane < 9) ? lane % 3 : 0;
+
+    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < in.B; base += (long long)gridDim.x * CORE_WARPS) {
+        __syncthreads();
+        const long long prob = base + warp;
+        if (prob >= in.B) continue;
+        double* rec = ws + prob * CORE_WS_F;
         const double one3[3] = {1.0, 1.0, 1.0}, zero6[6] = {0, 0, 0, 0, 0, 0};
         double s0[3] = {1.0, 1.0, 1.0}, t0[6] = {0, 0, 0, 0, 0, 0};
-        if (in.normalize) view_stats(in, prob, lane, one3, zero6, s0, t0);   // LinearFPoseEstimation.m:46-48
+        if (in.normalize) view_stats<PACKED>(in, prob, lane, one3, zero6, s0, t0);   // LinearFPoseEstimation.m:46-48
         double si[3], ti[6];
-        view_stats(in, prob, lane, s0, t0, si, ti);                          // linearF.m:45-46 (re-normalisation)
+        view_stats<PACKED>(in, prob, lane, s0, t0, si, ti);                          // linearF.m:45-46
+        int st = 0;
         const int npairs = in.normalize ? 2 : 1;
         for (int pr = 0; pr < npairs; ++pr) {
             const int vb = 1 + pr;
-            double F[9];
-            st |= linear_f_pair(in, prob, lane, ws, 0, vb, s0, t0, si, ti, F);
-            if (in.normalize) {                                              // LinearFPoseEstimation.m:55-56
-                const double Na[9] = {s0[0], 0, 0, 0, s0[0], 0, t0[0], t0[1], 1.0};
-                const double Nb[9] = {s0[vb], 0, 0, 0, s0[vb], 0, t0[2 * vb], t0[2 * vb + 1], 1.0};
-                double tmp[9], Fo[9];
-                mat3_mul_tn(Nb, F, tmp);
-                mat3_mul(tmp, Na, Fo);
-#pragma unroll
-                for (int q = 0; q < 9; ++q) F[q] = Fo[q];
+            // inner map composed with the outer one: x' = si*(s0*x + t0) + ti
+            const double sa = si[0] * s0[0], sb = sel3(si, vb) * sel3(s0, vb);
+            const double tax = si[0] * t0[0] + ti[0], tay = si[0] * t0[1] + ti[1];
+            const double tbx = sel3(si, vb) * (vb == 1 ? t0[2] : t0[4]) + (vb == 1 ? ti[2] : ti[4]);
+            const double tby = sel3(si, vb) * (vb == 1 ? t0[3] : t0[5]) + (vb == 1 ? ti[3] : ti[5]);
+            double acc0 = 0.0, acc1 = 0.0;
+            for (int pbase = 0; pbase < in.n; pbase += 32) {
+                const int cnt = min(32, in.n - pbase);
+                __syncwarp();
+                if (lane < cnt) {
+                    double p[6];
+                    load_point<PACKED>(in, prob, pbase + lane, p);
+                    const double xb = (vb == 1) ? p[2] : p[4], yb = (vb == 1) ? p[3] : p[5];
+                    const double x1 = sa * p[0] + tax, y1 = sa * p[1] + tay;
+                    const double x2 = sb * xb + tbx, y2 = sb * yb + tby;
+                    double* f = sc.feat + lane * FEAT_STRIDE;
+                    f[0] = x1 * x1; f[1] = x1 * y1; f[2] = x1; f[3] = y1 * y1; f[4] = y1; f[5] = 1.0;
+                    f[6] = x2 * x2; f[7] = x2 * y2; f[8] = x2; f[9] = y2 * y2; f[10] = y2; f[11] = 1.0;
+                }
+                __syncwarp();
+                for (int p = 0; p < cnt; ++p) {
+                    const double* f = sc.feat + p * FEAT_STRIDE;
+                    acc0 = fma(f[a0], f[6 + b0], acc0);
+                    acc1 = fma(f[a1], f[6 + b1], acc1);
+                }
             }
-            // lane q writes F[q] without dynamic register indexing
-            double mine = 0.0;
+            __syncwarp();
+            sc.mom[lane] = acc0;
+            if (lane < 4) sc.mom[32 + lane] = acc1;
+            __syncwarp();
+            // G9(r,c), r = 3*a + b for the row [x1x2, x1y2, x1, y1x2, y1y2, y1, x2, y2, 1] (linearF.m:51-52)
+            double g[9];
 #pragma unroll
-            for (int q = 0; q < 9; ++q) mine = (lane == q) ? F[q] : mine;
-            if (lane < 9) Fout[prob * (9 * npairs) + 9 * pr + lane] = mine;
+            for (int c = 0; c < 9; ++c) {
+                const double v = sc.mom[c_sym6[ar * 3 + c / 3] * 6 + c_sym6[br * 3 + c % 3]];
+                g[c] = (lane < 9) ? v : 0.0;
+            }
+            bool conv;
+            const double fl = smallest_eigvec_spd<9>(g, lane, sc.sbuf, &conv);            // linearF.m:54-55
+            if (!conv) st |= ST_EIG_NOCONV;
+            if (lane < 9) rec[FW_F + 9 * pr + lane] = fl;
+        }
+        if (lane < 3) { rec[FW_STATS + lane] = sel3(s0, lane); rec[FW_STATS + 9 + lane] = sel3(si, lane); }
+        if (lane < 6) {
+            rec[FW_STATS + 3 + lane] = (lane < 3) ? sel3(t0, lane) : sel3(t0 + 3, lane - 3);
+            rec[FW_STATS + 12 + lane] = (lane < 3) ? sel3(ti, lane) : sel3(ti + 3, lane - 3);
         }
         if (status != nullptr && lane == 0) status[prob] = st;
-        __syncwarp();
+    }
+}
+
+// linearF.m:58-62 and LinearFPoseEstimation.m:55-56, one thread per problem
+__global__ void __launch_bounds__(128)
+f_finish_kernel(const double* __restrict__ ws, int normalize, long long B, double* __restrict__ Fout) {
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double* rec = ws + b * CORE_WS_F;
+    const double* s0 = rec + FW_STATS; const double* t0 = s0 + 3; const double* si = s0 + 9; const double* ti = s0 + 12;
+    const int npairs = normalize ? 2 : 1;
+    for (int pr = 0; pr < npairs; ++pr) {
+        const int vb = 1 + pr;
+        double Fv[9];
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Fv[q] = rec[FW_F + 9 * pr + q];                       // reshape(V(:,9),3,3)
+        const double Na[9] = {si[0], 0, 0, 0, si[0], 0, ti[0], ti[1], 1.0};
+        const double Nb[9] = {si[vb], 0, 0, 0, si[vb], 0, ti[2 * vb], ti[2 * vb + 1], 1.0};
+        double tmp[9], Fu[9], F[9];
+        mat3_mul_tn(Nb, Fv, tmp);
+        mat3_mul(tmp, Na, Fu);                                                            // linearF.m:58
+        double U[9], sv[3], V[9];
+        svd3_full(Fu, U, sv, V);                                                          // :61, D(3,3)=0
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) F[r + 3 * c] = sv[0] * U[r] * V[c] + sv[1] * U[3 + r] * V[3 + c];   // :62
+        if (normalize) {                                                                  // LinearFPoseEstimation.m:55-56
+            const double Ma[9] = {s0[0], 0, 0, 0, s0[0], 0, t0[0], t0[1], 1.0};
+            const double Mb[9] = {s0[vb], 0, 0, 0, s0[vb], 0, t0[2 * vb], t0[2 * vb + 1], 1.0};
+            mat3_mul_tn(Mb, F, tmp);
+            mat3_mul(tmp, Ma, F);
+        }
+#pragma unroll
+        for (int q = 0; q < 9; ++q) Fout[b * (9 * npairs) + 9 * pr + q] = F[q];
     }
 }
 
 // ---------------------------------------------------------------------------
-void launch_tft_core(const CoreInput& in, double* T, double* P2, double* P3, int* status, int sm_count,
-                     cudaStream_t stream) {
-    if (in.B <= 0) return;
-    long long blocks = (in.B + CORE_WARPS - 1) / CORE_WARPS;
-    const long long cap = (long long)sm_count * 2 * 8;
+static inline unsigned core_grid(long long B, int sm_count) {
+    long long blocks = (B + CORE_WARPS - 1) / CORE_WARPS;
+    const long long cap = (long long)sm_count * 3 * 4;
     if (blocks > cap) blocks = cap;
-    tft_core_kernel<<<(unsigned)blocks, CORE_WARPS * 32, 0, stream>>>(in, T, P2, P3, status);
+    return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
-void launch_f_core(const CoreInput& in, double* F, int* status, int sm_count, cudaStream_t stream) {
+void launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream) {
     if (in.B <= 0) return;
-    long long blocks = (in.B + CORE_WARPS - 1) / CORE_WARPS;
-    const long long cap = (long long)sm_count * 2 * 8;
-    if (blocks > cap) blocks = cap;
-    f_core_kernel<<<(unsigned)blocks, CORE_WARPS * 32, 0, stream>>>(in, F, status);
+    if (in.packed) tft_stage1_kernel<true><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    else tft_stage1_kernel<false><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+}
+
+void launch_tft_epipoles(double* ws, long long B, cudaStream_t stream) {
+    if (B <= 0) return;
+    tft_epipoles_kernel<<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(ws, B);
+}
+
+void launch_tft_stage2(int normalize, long long B, const double* ws, double* T, double* P2, double* P3, int* status,
+                       int sm_count, cudaStream_t stream) {
+    if (B <= 0) return;
+    tft_stage2_kernel<<<core_grid(B, sm_count), CORE_WARPS * 32, 0, stream>>>(normalize, B, ws, T, P2, P3, status);
+}
+
+void launch_f_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream) {
+    if (in.B <= 0) return;
+    if (in.packed) f_stage1_kernel<true><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    else f_stage1_kernel<false><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+}
+
+void launch_f_finish(const double* ws, int normalize, long long B, double* F, cudaStream_t stream) {
+    if (B <= 0) return;
+    f_finish_kernel<<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(ws, normalize, B, F);
 }
 
 }  // namespace tvf

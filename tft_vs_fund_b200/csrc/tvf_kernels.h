@@ -19,9 +19,17 @@ struct CoreInput {
     int normalize;   // 1: *PoseEstimation path (Normalize2Ddata + undo); 0: estimator called directly
 };
 
-void launch_tft_core(const CoreInput& in, double* T, double* P2, double* P3, int* status, int sm_count,
-                     cudaStream_t stream);
-void launch_f_core(const CoreInput& in, double* F, int* status, int sm_count, cudaStream_t stream);
+// per-problem work-space records (doubles) handed between the estimator stages
+constexpr int CORE_WS_TFT = 140;   // 96 moments | 9 normalisation stats (+1) | t1 27 (+1) | e21,e31
+constexpr int CORE_WS_F = 36;      // raw f (2 x 9) | outer stats 9 | inner stats 9
+
+void launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream);
+void launch_tft_epipoles(double* ws, long long B, cudaStream_t stream);
+void launch_tft_stage2(int normalize, long long B, const double* ws, double* T, double* P2, double* P3, int* status,
+                       int sm_count, cudaStream_t stream);
+void launch_f_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream);
+// normalize != 0: two pairs per problem (F21, F31 -> F[18*b]); else one (F[9*b])
+void launch_f_finish(const double* ws, int normalize, long long B, double* F, cudaStream_t stream);
 
 // ---- pose tail -----------------------------------------------------------------------------
 struct PoseTailArgs {
@@ -44,7 +52,9 @@ struct PoseTailArgs {
 
 // mode 0: model = T (27 x B, pixel coordinates); mode 1: model = [F21 F31] (18 x B)
 void launch_candidates(int mode, const double* model, const PoseTailArgs& a, cudaStream_t stream);
-void launch_pose_tail(const PoseTailArgs& a, int sm_count, cudaStream_t stream);
+void launch_votes(const PoseTailArgs& a, int sm_count, cudaStream_t stream);
+void launch_scale(const PoseTailArgs& a, int sm_count, cudaStream_t stream);
+void launch_final(const PoseTailArgs& a, int sm_count, cudaStream_t stream);
 // LinearFPoseEstimation.m:78  T = TFT_from_P(K1*eye(3,4), K2*R_t_2, K3*R_t_3)
 void launch_tft_from_pose(const double* calm, int calm_batched, const double* Rt2, const double* Rt3,
                           long long B, double* T, cudaStream_t stream);

@@ -100,7 +100,7 @@ TVF_HD void jacobi_rot_(double* ap, double* aq, double* vp, double* vq, bool& ro
     const double alpha = ap[0] * ap[0] + ap[1] * ap[1] + ap[2] * ap[2];
     const double beta = aq[0] * aq[0] + aq[1] * aq[1] + aq[2] * aq[2];
     const double gamma = ap[0] * aq[0] + ap[1] * aq[1] + ap[2] * aq[2];
-    const double thr = 1.0e-16 * sqrt(alpha * beta);
+    const double thr = 1.0e-15 * sqrt(alpha * beta);   // ~4.5 eps: below that a rotation only moves rounding noise
     if (!(fabs(gamma) > thr) || fabs(gamma) < 1e-300) return;
     rotated = true;
     const double zeta = (beta - alpha) / (2.0 * gamma);
@@ -125,7 +125,7 @@ TVF_HD void swap_cols_(double* a, double* b, double* va, double* vb, double& sa,
     double t = sa; sa = sb; sb = t;
 }
 
-TVF_HD void jacobi_svd3(double* A, double* V, double* s) {
+TVF_HD void jacobi_svd3(double* A, double* V, double* s, int* sweeps = nullptr) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) V[i] = (i % 4 == 0) ? 1.0 : 0.0;
     for (int sweep = 0; sweep < 30; ++sweep) {
@@ -133,6 +133,7 @@ TVF_HD void jacobi_svd3(double* A, double* V, double* s) {
         jacobi_rot_(A + 0, A + 3, V + 0, V + 3, rotated);
         jacobi_rot_(A + 0, A + 6, V + 0, V + 6, rotated);
         jacobi_rot_(A + 3, A + 6, V + 3, V + 6, rotated);
+        if (sweeps) *sweeps = sweep + 1;
         if (!rotated) break;
     }
     s[0] = sqrt(A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
@@ -336,7 +337,7 @@ TVF_HD void dlt_null(double (&a)[M][4], double* x, int* iters = nullptr) {
         z0 *= inv; z1 *= inv; z2 *= inv; z3 *= inv;
         const double diff = fmax(fmax(fabs(z0 - x0), fabs(z1 - x1)), fmax(fabs(z2 - x2), fabs(z3 - x3)));
         x0 = z0; x1 = z1; x2 = z2; x3 = z3;
-        if (!(diff > 2e-16)) { ++it; break; }
+        if (!(diff > 1e-13)) { ++it; break; }   // linear rate <= ~1e-3: the error left is far below 1e-13
     }
     x[0] = x0; x[1] = x1; x[2] = x2; x[3] = x3;
     if (iters) *iters = it;

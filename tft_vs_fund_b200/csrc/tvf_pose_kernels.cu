@@ -392,14 +392,25 @@ void launch_candidates(int mode, const double* model, const PoseTailArgs& a, cud
     candidates_kernel<<<grid_for(a.B, 128, 1LL << 30), 128, 0, stream>>>(mode, model, a);
 }
 
-void launch_pose_tail(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
-    if (a.B <= 0) return;
+static inline unsigned tail_grid(const PoseTailArgs& a, int sm_count) {
     const int tpp = (a.n <= PT_THREADS) ? a.n : PT_THREADS;
     const int ppb = PT_THREADS / tpp;
-    const unsigned g = grid_for(a.B, ppb, (long long)sm_count * 32);
-    votes_kernel<<<g, PT_THREADS, 0, stream>>>(a);
-    scale_kernel<<<g, PT_THREADS, 0, stream>>>(a);
-    final_kernel<<<g, PT_THREADS, 0, stream>>>(a);
+    return grid_for(a.B, ppb, (long long)sm_count * 32);
+}
+
+void launch_votes(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
+    if (a.B <= 0) return;
+    votes_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
+}
+
+void launch_scale(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
+    if (a.B <= 0) return;
+    scale_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
+}
+
+void launch_final(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
+    if (a.B <= 0) return;
+    final_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
 }
 
 void launch_tft_from_pose(const double* calm, int calm_batched, const double* Rt2, const double* Rt3, long long B,

@@ -3,21 +3,26 @@
 // trilinearity Gram, its 15x15 projection and the 9x9 eight-point Gram.
 //
 // Storage: lane r owns row r of the symmetric matrix in registers g[0..N).
-// A right-looking Cholesky runs in place; because the trailing matrix stays
-// symmetric, lane k's entries g[m], m>k, are dead after step k and are reused
-// to hold column k of L.  After the factorisation lane j therefore holds
-//   g[m] = L(j,m) for m<=j   and   g[m] = L(m,j) for m>j,
-// which is exactly what the forward (L y = b) and backward (L' x = y)
-// substitutions need in their axpy form: one broadcast shuffle + one DFMA per
-// step, no cross-lane reduction.  The eigenvector is obtained by inverse
-// iteration with a tiny relative diagonal shift (keeps the factorisation
-// positive for noise-free, exactly singular data).
+// The matrix is inverted in place by N Gauss-Jordan sweeps (no pivoting: SPD),
+// fully unrolled so every register index is static.  Per sweep k each lane
+// publishes its scaled column entry A(j,k)/d to shared memory (by symmetry
+// that vector is row k), reads the row back as broadcast 128-bit loads and does
+// one DFMA per matrix element:  A(j,m) -= c_j * A(k,m)/d.
+// The pivot lane needs A(k,m) <- A(k,m)/d instead; with the matrix pre-scaled
+// to unit trace every pivot d <= 1 and that is the *same* DFMA with
+// c_k = d - 1 (no cancellation: A + (1-d)*A/d), so the special case costs one
+// scalar select per sweep instead of two per element.
+// The inverse then drives power iteration (= inverse iteration on G): one
+// broadcast mat-vec of N DFMAs per step.  A relative diagonal shift of 1e-13
+// keeps noise-free, exactly singular systems factorable; it does not change
+// the eigenvectors.  tests/kernel_model.py restates this algorithm in NumPy.
 #pragma once
 #include "tvf_math.cuh"
 
 namespace tvf {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int EIG_MAX_ITER = 80;
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
 
@@ -33,72 +38,66 @@ __device__ __forceinline__ double warp_max(double v) {
     return v;
 }
 
-// g: lane's row (lanes >= N must pass zeros).  Returns this lane's component of
-// the unit eigenvector of the smallest eigenvalue; *converged tells whether the
-// iteration met its tolerance (warp-uniform).
+// g: this lane's row (lanes >= N must pass zeros).  sbuf: 64 doubles of shared memory private to
+// the warp, 16-byte aligned.  Returns this lane's component of the unit eigenvector belonging to
+// the smallest eigenvalue; *converged is warp-uniform.
 template <int N>
-__device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int lane, bool* converged) {
-    // relative shift: delta = 1e-13 * trace/N
+__device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int lane, double* sbuf, bool* converged) {
+    static_assert(N <= 32 && N >= 2, "one matrix row per lane");
+    constexpr int NP = (N + 1) & ~1;          // row length padded to a whole number of 128-bit loads
     double diag = 0.0;
 #pragma unroll
     for (int m = 0; m < N; ++m) diag = (lane == m) ? g[m] : diag;
     const double tr = warp_sum(diag);
-    const double delta = 1.0e-13 * tr * (1.0 / N);
-    const double floor_piv = 1.0e-3 * delta + 1e-300;
+    const double sc = 1.0 / tr;
+    const double delta = 1.0e-13 / N;         // relative to the unit trace
+    const double floor_piv = 1.0e-3 * delta;
 #pragma unroll
-    for (int m = 0; m < N; ++m) g[m] += (lane == m) ? delta : 0.0;
+    for (int m = 0; m < N; ++m) g[m] = g[m] * sc + ((lane == m) ? delta : 0.0);
 
-    double dinv = 0.0;
+    __syncwarp();                              // sbuf may still be read by a previous phase
+    if (lane >= N && lane < NP) { sbuf[lane] = 0.0; sbuf[32 + lane] = 0.0; }
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-        double dk = shfl_d(g[k], k);
-        dk = fmax(dk, floor_piv);
-        const double rinv = rsqrt(dk);
-        double lk = g[k] * rinv;
-        if (lane == k) { lk = dk * rinv; dinv = rinv; }
-        if (lane >= k) g[k] = lk;
-        const double lkz = (lane > k) ? lk : 0.0;
+        const double colj = g[k];
+        const double d = fmax(shfl_d(colj, k), floor_piv);
+        const double piv = 1.0 / d;
+        const double rk = colj * piv;
+        double* buf = sbuf + (k & 1) * 32;
+        if (lane < N) buf[lane] = rk;
+        __syncwarp();
+        const double c = colj - ((lane == k) ? 1.0 : 0.0);
+        const double2* b2 = reinterpret_cast<const double2*>(buf);
 #pragma unroll
-        for (int m = k + 1; m < N; ++m) {
-            const double lm = shfl_d(lk, m);
-            const double upd = fma(-lkz, lm, g[m]);
-            g[m] = (lane == k) ? lm : upd;
+        for (int m2 = 0; m2 < NP / 2; ++m2) {
+            const double2 r = b2[m2];
+            if (2 * m2 != k && 2 * m2 < N) g[2 * m2] = fma(-c, r.x, g[2 * m2]);
+            if (2 * m2 + 1 != k && 2 * m2 + 1 < N) g[2 * m2 + 1] = fma(-c, r.y, g[2 * m2 + 1]);
         }
+        g[k] = (lane == k) ? -piv : rk;
     }
-
-    // x0: solve L' x = 1
-    double x = 0.0;
-    {
-        double acc = (lane < N) ? 1.0 : 0.0;
-#pragma unroll
-        for (int j = N - 1; j >= 0; --j) {
-            const double xj = shfl_d(acc * dinv, j);
-            acc = fma(-g[j], xj, acc);
-            x = (lane == j) ? xj : x;
-        }
-        x *= rsqrt(warp_sum(x * x));
-    }
+    __syncwarp();                              // last sweep's row buffer is reused below
+    // g now holds -(G + delta I)^-1 (scaled).  Power iteration on its negative.
+    double x = (lane < N) ? rsqrt((double)N) : 0.0;
     bool ok = false;
 #pragma unroll 1
-    for (int it = 0; it < 60; ++it) {
-        double acc = x, y = 0.0, z = 0.0;
+    for (int it = 0; it < EIG_MAX_ITER; ++it) {
+        double* buf = sbuf + (it & 1) * 32;
+        if (lane < NP) buf[lane] = x;
+        __syncwarp();
+        const double2* b2 = reinterpret_cast<const double2*>(buf);
+        double z0 = 0.0, z1 = 0.0;
 #pragma unroll
-        for (int m = 0; m < N; ++m) {                 // L y = x
-            const double ym = shfl_d(acc * dinv, m);
-            acc = fma(-g[m], ym, acc);
-            y = (lane == m) ? ym : y;
+        for (int m2 = 0; m2 < NP / 2; ++m2) {
+            const double2 r = b2[m2];
+            if (2 * m2 < N) z0 = fma(g[2 * m2], r.x, z0);
+            if (2 * m2 + 1 < N) z1 = fma(g[2 * m2 + 1], r.y, z1);
         }
-        acc = y;
-#pragma unroll
-        for (int j = N - 1; j >= 0; --j) {            // L' z = y
-            const double zj = shfl_d(acc * dinv, j);
-            acc = fma(-g[j], zj, acc);
-            z = (lane == j) ? zj : z;
-        }
+        double z = -(z0 + z1);
         z *= rsqrt(warp_sum(z * z));
         const double diff = warp_max(fabs(z - x));
         x = z;
-        if (!(diff > 1.0e-15)) { ok = true; break; }
+        if (!(diff > 4.0e-15)) { ok = true; break; }
     }
     *converged = ok;
     return x;
