@@ -229,7 +229,8 @@ def test_small_functions(tvf):
     est = np.column_stack([R_t0[0][:, :3], R_t0[0][:, 3] * 1.0])
     for a, b in ((R_t0[0], R_t0[1]), (R_t0[0], est)):
         ro, to = o.AngError(a, b); rg, tg = tvf.AngError(a, b)
-        assert abs(ro - rg) < 1e-6 and abs(to - tg) < 1e-6
+        # acos is ill-conditioned at 0: one ulp in the trace moves the angle by 1.2e-6 degrees
+        assert abs(ro - rg) < 5e-6 and abs(to - tg) < 5e-6
     # R_t_from_TFT on the oracle's own tensor
     R2, R3, Rec, To, _ = o.LinearTFTPoseEstimation(C, CalM)
     g2, g3 = tvf.R_t_from_TFT(To, CalM, C)

@@ -1,0 +1,88 @@
+#!/usr/bin/env python
+"""Summarise ncu artifacts brought back from the GPU box into small, committed text files.
+
+    python tools/ncu_summary.py --launches gpurun_out/X_launches.csv --rep gpurun_out/X_prof.ncu-rep --out profiles/rNN
+
+writes <out>_launches.md (per-kernel share of the device time of one bench command, from the
+`--metrics gpu__time_duration.sum` pass) and <out>_kernels.md (key counters of each kernel captured
+with `--set full`: duration, registers, occupancy, issue/FP64-pipe utilisation, DRAM bytes, stall mix)."""
+import argparse
+import collections
+import csv
+import subprocess
+
+STALLS = ["short_scoreboard", "long_scoreboard", "wait", "math_pipe_throttle", "barrier", "branch_resolving",
+          "no_instruction", "mio_throttle", "lg_throttle", "dispatch_stall", "not_selected"]
+
+
+def launches(path, out):
+    rows = list(csv.reader(open(path)))
+    hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
+    H = rows[hdr]
+    ki, vi, mi, ui = H.index("Kernel Name"), H.index("Metric Value"), H.index("Metric Name"), H.index("Metric Unit")
+    agg = collections.OrderedDict()
+    for r in rows[hdr + 1:]:
+        if len(r) <= vi or r[mi] != "gpu__time_duration.sum":
+            continue
+        scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ui], 1e-3)
+        name = r[ki].split("(")[0]
+        a = agg.setdefault(name, [0, 0.0])
+        a[0] += 1
+        a[1] += float(r[vi].replace(",", "")) * scale
+    ours = {k: v for k, v in agg.items() if "tvf" in k or "kernel" in k and "at::" not in k}
+    tot = sum(v[1] for k, v in ours.items() if "fp64_peak" not in k)
+    with open(out, "w") as f:
+        f.write("# ncu launch list (gpu__time_duration.sum, --clock-control none; cold-cache, serialised: compare shares)\n\n")
+        f.write("source: %s\n\n| kernel | launches | total us | avg us | share of pose kernels |\n|---|---:|---:|---:|---:|\n" % path)
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+            share = "%.3f" % (v[1] / tot) if k in ours and "fp64_peak" not in k else "-"
+            f.write("| %s | %d | %.1f | %.2f | %s |\n" % (k[:70], v[0], v[1], v[1] / v[0], share))
+
+
+def kernels(rep, out):
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H = rows[0]
+    ix = {h: i for i, h in enumerate(H)}
+
+    def g(r, name, default=""):
+        return r[ix[name]] if name in ix else default
+
+    with open(out, "w") as f:
+        f.write("# ncu --set full --clock-control none: key counters per captured kernel\n\nsource: %s\n\n" % rep)
+        for r in rows[2:]:
+            f.write("## %s\n\n" % g(r, "Kernel Name").split("(")[0])
+            f.write("| metric | value |\n|---|---:|\n")
+            for label, name in [
+                ("duration (%s)" % (rows[1][ix["gpu__time_duration.sum"]] if "gpu__time_duration.sum" in ix else ""), "gpu__time_duration.sum"),
+                ("grid / block", None),
+                ("registers per thread", "launch__registers_per_thread"),
+                ("achieved warps active (% of peak)", "sm__warps_active.avg.pct_of_peak_sustained_active"),
+                ("warp instructions executed", "smsp__inst_executed.sum"),
+                ("issue slots busy (%)", "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                ("FP64 pipe active (% of peak)", "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                ("avg active threads per instruction", "smsp__thread_inst_executed_per_inst_executed.ratio"),
+                ("dram bytes read (%s)" % (rows[1][ix["dram__bytes_read.sum"]] if "dram__bytes_read.sum" in ix else ""), "dram__bytes_read.sum"),
+                ("dram bytes written (%s)" % (rows[1][ix["dram__bytes_write.sum"]] if "dram__bytes_write.sum" in ix else ""), "dram__bytes_write.sum"),
+                ("dram throughput (% of peak)", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                ("shared-memory bank conflicts", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+                ("SM cycles elapsed (max)", "sm__cycles_elapsed.max"),
+            ]:
+                if name is None:
+                    f.write("| %s | %s x %s |\n" % (label, g(r, "launch__grid_size"), g(r, "launch__block_size")))
+                else:
+                    f.write("| %s | %s |\n" % (label, g(r, name)))
+            f.write("\nstall mix (warps stalled per issue-active cycle):\n\n| reason | ratio |\n|---|---:|\n")
+            for s in STALLS:
+                f.write("| %s | %s |\n" % (s, g(r, "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio" % s)))
+            f.write("\n")
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--launches"); ap.add_argument("--rep"); ap.add_argument("--out", required=True)
+    a = ap.parse_args()
+    if a.launches:
+        launches(a.launches, a.out + "_launches.md")
+    if a.rep:
+        kernels(a.rep, a.out + "_kernels.md")
