@@ -1,8 +1,10 @@
 """Generate the committed golden vectors under tests/golden/ (run in the build container, where
 /root/reference is mounted):   python tests/golden/make_golden.py
 
-Inputs come from the documented scene generator / the reference's EPFL data files; expected outputs
-from the oracle (oracle/reference_port.py).  The GPU box has no /root/reference, so the `-m gpu`
+Inputs come from the documented scene generator / the reference's EPFL data files.  Expected outputs:
+  tft_*/f_*          from the oracle (oracle/reference_port.py, the NumPy restatement);
+  ref_tft_*/ref_f_*  from the reference's OWN unmodified .m files under /root/reference, executed by
+                     oracle/mini_matlab.py (NumPy/LAPACK built-ins) -- these pin the restatement.  The GPU box has no /root/reference, so the `-m gpu`
 tests read only these .npz files (plus the live oracle on the same seeded inputs)."""
 import os
 import sys
@@ -17,9 +19,33 @@ import oracle as o  # noqa: E402
 REFERENCE = "/root/reference"
 
 
+_interp = None
+
+
+def reference_run(C, CalM):
+    """The reference's own .m files (unmodified, from /root/reference) executed by oracle/mini_matlab.py."""
+    global _interp
+    if not os.path.isdir(REFERENCE):
+        return None
+    from oracle.mini_matlab import reference_interpreter, Cell
+    if _interp is None:
+        _interp = reference_interpreter(REFERENCE, rng_factory=o.SceneRNG)
+    K = [CalM[0:3], CalM[3:6], CalM[6:9]]
+    out = {}
+    for m, fn in (("tft", "LinearTFTPoseEstimation"), ("f", "LinearFPoseEstimation")):
+        R2, R3, Rec, T, it = _interp.call(fn, [C.copy(), CalM.copy()], 5)
+        assert float(np.asarray(it).item()) == 0.0
+        rep = _interp.call("ReprError", [Cell([K[0] @ np.eye(3, 4), K[1] @ R2, K[2] @ R3]), C.copy(), Rec], 1)[0]
+        out[m] = (R2, R3, Rec, T, float(np.asarray(rep).item()))
+    return out
+
+
 def run_both(C, CalM):
     K = [CalM[0:3], CalM[3:6], CalM[6:9]]
     out = {}
+    ref = reference_run(C, CalM)
+    if ref is not None:
+        out["ref_tft"], out["ref_f"] = ref["tft"], ref["f"]
     R2, R3, Rec, T, _ = o.LinearTFTPoseEstimation(C, CalM)
     out["tft"] = (R2, R3, Rec, T, o.ReprError([K[0] @ np.eye(3, 4), K[1] @ R2, K[2] @ R3], C, Rec))
     R2, R3, Rec, T, _, F21, F31 = o.LinearFPoseEstimation(C, CalM, return_F=True)
@@ -30,7 +56,9 @@ def run_both(C, CalM):
 def pack(cases):
     """cases: list of dict(Corresp, CalM, res=run_both(...)) with equal n -> arrays with a leading case axis."""
     d = dict(Corresp=np.stack([c["Corresp"] for c in cases]), CalM=np.stack([c["CalM"] for c in cases]))
-    for m in ("tft", "f"):
+    for m in ("tft", "f", "ref_tft", "ref_f"):
+        if m not in cases[0]["res"]:
+            continue
         names = ["Rt2", "Rt3", "Reconst", "T", "repr"] + (["F21", "F31"] if m == "f" else [])
         for k, name in enumerate(names):
             d["%s_%s" % (m, name)] = np.stack([np.asarray(c["res"][m][k]) for c in cases])

@@ -1,0 +1,109 @@
+"""Pins the oracle restatement against the reference's own source.
+
+tests/golden/*.npz hold `ref_*` arrays produced by executing the UNMODIFIED reference .m files
+(/root/reference/TFT_methods, F_methods, auxiliar_functions) with oracle/mini_matlab.py, a minimal
+MATLAB-subset interpreter whose built-ins are NumPy/LAPACK.  The oracle (oracle/reference_port.py)
+must reproduce them; where /root/reference is mounted the interpreter is also run live."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as o
+from conftest import REFERENCE, ROOT, rel_frob_up_to_sign
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+HAVE_REF = os.path.isdir(REFERENCE)
+
+
+def _run_oracle(method, C, CalM):
+    K = [CalM[0:3], CalM[3:6], CalM[6:9]]
+    fn = o.LinearTFTPoseEstimation if method == "tft" else o.LinearFPoseEstimation
+    R2, R3, Rec, T, it = fn(C, CalM)
+    return R2, R3, Rec, T, o.ReprError([K[0] @ np.eye(3, 4), K[1] @ R2, K[2] @ R3], C, Rec)
+
+
+@pytest.mark.parametrize("name,stride", [("sweep_n20.npz", 7), ("example_n100.npz", 1), ("epfl_triplets.npz", 3)])
+@pytest.mark.parametrize("method", ["tft", "f"])
+def test_oracle_reproduces_reference_source_outputs(name, stride, method):
+    g = np.load(os.path.join(GOLDEN, name))
+    assert "ref_%s_T" % method in g.files, "golden file lacks interpreter outputs: regenerate with make_golden.py"
+    for b in range(0, g["Corresp"].shape[0], stride):
+        got = _run_oracle(method, g["Corresp"][b], g["CalM"][b])
+        for k, key in enumerate(("Rt2", "Rt3", "Reconst", "T", "repr")):
+            ref = g["ref_%s_%s" % (method, key)][b]
+            # same LAPACK underneath: agreement to rounding, not merely to the parity tolerances
+            scale = max(1.0, float(np.max(np.abs(ref))))
+            assert np.max(np.abs(np.asarray(got[k]) - ref)) <= 1e-9 * scale, (name, method, b, key)
+        # and the stored oracle outputs are the ones the GPU tests compare against
+        assert rel_frob_up_to_sign(g["%s_T" % method][b], g["ref_%s_T" % method][b]) < 1e-12
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present on this box")
+def test_interpreter_live_small_functions():
+    from oracle.mini_matlab import reference_interpreter, Cell, MatlabError
+    I = reference_interpreter(REFERENCE, rng_factory=o.SceneRNG)
+    f = lambda x: np.array([[float(x)]])
+    rs = np.random.RandomState(3)
+    # generateSyntheticScene.m (matrix products there are BLAS-ordered: projections agree to rounding only)
+    CalM, R_t, C, X = I.call("generateSyntheticScene", [f(60), f(2), f(5), f(50), f(0)], 4)
+    a = o.generateSyntheticScene(60, 2, 5, 50, 0)
+    assert np.array_equal(CalM, a[0]) and np.array_equal(X, a[3])
+    assert np.abs(C - a[2]).max() < 1e-10 and max(np.abs(R_t[i] - a[1][i]).max() for i in range(2)) < 1e-13
+    # collinear-centres branch (angle in [70,180])
+    CalM2, R_t2, C2, _ = I.call("generateSyntheticScene", [f(30), f(0), f(2), f(100), f(175)], 4)
+    b = o.generateSyntheticScene(30, 0, 2, 100, 175)
+    assert np.abs(C2 - b[2]).max() < 1e-9 and max(np.abs(R_t2[i] - b[1][i]).max() for i in range(2)) < 1e-12
+    # Normalize2Ddata, transform_TFT (both directions), TFT_from_P, crossM, project3Dpoints
+    p, N = I.call("Normalize2Ddata", [C[0:2]], 2)
+    po, No = o.Normalize2Ddata(C[0:2])
+    assert np.abs(p - po).max() < 1e-14 and np.abs(N - No).max() < 1e-15 * np.abs(No).max() + 1e-18
+    T = rs.standard_normal((3, 3, 3)); Ms = [rs.standard_normal((3, 3)) + 2 * np.eye(3) for _ in range(3)]
+    for inv in (0, 1):
+        assert np.abs(I.call("transform_TFT", [T] + Ms + [f(inv)], 1)[0] - o.transform_TFT(T, *Ms, inv)).max() < 1e-14
+    assert np.abs(I.call("transform_TFT", [T] + Ms, 1)[0] - o.transform_TFT(T, *Ms, 0)).max() < 1e-14   # nargin<5
+    K = a[0][:3]
+    Ps = [K @ np.eye(3, 4), K @ a[1][0], K @ a[1][1]]
+    assert np.abs(I.call("TFT_from_P", Ps, 1)[0] - o.TFT_from_P(*Ps)).max() < 1e-14
+    assert np.array_equal(I.call("crossM", [np.array([[1.0], [2.0], [3.0]])], 1)[0], o.crossM([1, 2, 3]))
+    Xe = a[3]
+    assert np.abs(I.call("project3Dpoints", [Xe, Cell(Ps)], 1)[0] - o.project3Dpoints(Xe, Ps)).max() < 1e-9
+    # linearTFT with all four outputs, 2xN and 3xN inputs
+    xs = [o.Normalize2Ddata(a[2][2 * v:2 * v + 2])[0] for v in range(3)]
+    r = I.call("linearTFT", xs, 4)
+    ro = o.linearTFT(*xs)
+    for x, y in zip(r, ro):
+        assert np.abs(x - y).max() < 1e-10
+    hs = [np.vstack([x * 2.0, 2.0 * np.ones((1, x.shape[1]))]) for x in xs]
+    assert np.abs(I.call("linearTFT", hs, 1)[0] - ro[0]).max() < 1e-10
+    # linearF and its error text (linearF.m:35-37)
+    assert rel_frob_up_to_sign(I.call("linearF", [a[2][0:2], a[2][2:4]], 1)[0], o.linearF(a[2][0:2], a[2][2:4])) < 1e-12
+    with pytest.raises(MatlabError, match="At least 8 correspondences are necessary"):
+        I.call("linearF", [a[2][0:2, :7], a[2][2:4, :7]], 1)
+    # triangulation3D + ReprError (with / without 3-D points), AngError
+    X4 = I.call("triangulation3D", [Cell(Ps), a[2]], 1)[0]
+    assert np.abs(np.abs(X4) - np.abs(o.triangulation3D(Ps, a[2]))).max() < 1e-12
+    for pts in ([X4[:3] / X4[3]], [X4], []):
+        assert abs(I.call("ReprError", [Cell(Ps), a[2]] + pts, 1)[0].item() - o.ReprError(Ps, a[2], *pts)) < 1e-11
+    R2, R3 = o.LinearTFTPoseEstimation(a[2], a[0])[:2]
+    ri, ti = I.call("AngError", [a[1][0], R2], 2)
+    ro_, to_ = o.AngError(a[1][0], R2)
+    assert abs(ri.item() - ro_) < 1e-10 and abs(ti.item() - to_) < 1e-10
+    # R_t_from_TFT with the oracle's tensor
+    To = o.LinearTFTPoseEstimation(a[2], a[0])[3]
+    g2, g3 = I.call("R_t_from_TFT", [To, a[0], a[2]], 2)
+    o2, o3 = o.R_t_from_TFT(To, a[0], a[2])
+    assert np.abs(g2 - o2).max() < 1e-12 and np.abs(g3 - o3).max() < 1e-11
+
+
+@pytest.mark.skipif(not HAVE_REF, reason="reference sources not present on this box")
+def test_interpreter_live_pose_methods():
+    from oracle.mini_matlab import reference_interpreter
+    I = reference_interpreter(REFERENCE, rng_factory=o.SceneRNG)
+    for n, noise, seed in ((12, 0.5, 3), (20, 3.0, 11), (33, 1.0, 2)):
+        CalM, _, C, _ = o.experiments_subsample(n, noise, seed)
+        for method, fn in (("tft", "LinearTFTPoseEstimation"), ("f", "LinearFPoseEstimation")):
+            r = I.call(fn, [C.copy(), CalM.copy()], 5)
+            got = _run_oracle(method, C, CalM)
+            for x, y in zip(r[:4], got[:4]):
+                assert np.max(np.abs(np.asarray(x) - y)) <= 1e-9 * max(1.0, np.max(np.abs(y)))
