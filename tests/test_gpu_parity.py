@@ -264,3 +264,24 @@ def test_full_size_properties(tvf):
         assert np.max(np.abs(rp[2] - res[2][sub][:, :, perm])) < 1e-6 * np.max(np.abs(res[2][sub]))
         for b in range(0, 512, 37):
             assert rel_frob_up_to_sign(rp[3][b], res[3][sub][b]) < 1e-9
+
+
+def test_experiments_sweep_table(tvf):
+    """experiments.m:74-124 collapsed into batched calls: per-noise-level mean errors of methods 1 and 7
+    against the same loop written with the oracle (n_sim = 3 seeds here)."""
+    from tft_vs_fund_b200 import experiments
+    n_sim, L = 3, 13
+    table = experiments.run_sweep(L * n_sim, 20, methods=(1, 7))
+    ref = {1: np.zeros((L, 3)), 7: np.zeros((L, 3))}
+    for j in range(L * n_sim):
+        lv, it = j % L, j // L + 1
+        CalM, R_t0, C, _ = o.experiments_subsample(20, 0.25 * lv, it)                       # experiments.m:93-95
+        K = CalM[:3]
+        for m, fn in ((1, o.LinearTFTPoseEstimation), (7, o.LinearFPoseEstimation)):
+            R2, R3, Rec, _, _ = fn(C, CalM)                                                 # :108
+            ref[m][lv, 0] += o.ReprError([K @ np.eye(3, 4), K @ R2, K @ R3], C, Rec) / n_sim     # :112-114
+            r2, t2 = o.AngError(R_t0[0], R2); r3, t3 = o.AngError(R_t0[1], R3)              # :117-118
+            ref[m][lv, 1] += (r2 + r3) / (2 * n_sim); ref[m][lv, 2] += (t2 + t3) / (2 * n_sim)
+    for m in (1, 7):
+        assert np.max(np.abs(table[m][:, 0] - ref[m][:, 0])) < 1e-8                          # px
+        assert np.max(np.abs(table[m][:, 1:] - ref[m][:, 1:])) < 1e-4                        # degrees (1e-6 rad = 5.7e-5 deg)

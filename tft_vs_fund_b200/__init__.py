@@ -12,6 +12,7 @@ from .api import (  # noqa: F401
 )
 from ._lib import TvfError, Handle, handle, load, LIB_PATH  # noqa: F401
 from .scene import generateSyntheticScene, sweep_batch, SceneRNG  # noqa: F401
+from . import experiments, sharding  # noqa: F401
 
 __all__ = [
     "LinearTFTPoseEstimation", "LinearFPoseEstimation", "linearTFT", "linearF",

@@ -1,0 +1,54 @@
+"""The synthetic sweep of experiments.m, batched: every (noise level, seed) trial of
+experiments.m:74-144 for the two linear methods in one (sharded) call.
+
+experiments.m loops `interval` x `n_sim` x methods, calling `methods{m}(Corresp,CalM)` once per trial
+(:107-109) and accumulating ReprError / AngError means per noise level (:112-124).  Here the trial
+loop collapses into one batched call per method and rank; the accumulation is a per-level sum that is
+gathered and added in rank order (tft_vs_fund_b200.sharding)."""
+import numpy as np
+
+from . import api, scene, sharding
+
+NOISE_LEVELS = np.arange(0.0, 3.0 + 1e-9, 0.25)          # experiments.m:40  interval=0:0.25:3
+METHODS = {1: ("Linear TFT", api.LinearTFTPoseEstimation), 7: ("Linear F", api.LinearFPoseEstimation)}
+
+
+def evaluate(res, R_t0, device=None):
+    """Per-trial errors as experiments.m:112-120: (repr_err, rot_err, t_err) with the two views averaged."""
+    B = res[0].shape[0]
+    r2, t2 = api.AngError(R_t0[0], res[0], device=device)
+    r3, t3 = api.AngError(R_t0[1], res[1], device=device)
+    return np.asarray(res.repr_err).reshape(B), (r2 + r3) / 2.0, (t2 + t3) / 2.0
+
+
+def level_sums(level_idx, n_levels, *columns):
+    """Sum each per-trial column per noise level -> (n_levels, len(columns)+1) with the count last."""
+    out = np.zeros((n_levels, len(columns) + 1))
+    for k, col in enumerate(columns):
+        out[:, k] = np.bincount(level_idx, weights=col, minlength=n_levels)
+    out[:, -1] = np.bincount(level_idx, minlength=n_levels)
+    return out
+
+
+def run_sweep(total_trials, n=20, methods=(1, 7), noise_levels=NOISE_LEVELS, focalL=50, angle=0, device=None,
+              solver=None, workers=1):
+    """Sharded sweep.  Returns on rank 0 a dict method -> (n_levels, 3) array of mean [repr_err, rot_err,
+    t_err] per noise level (the `(:,m,1)` slices of experiments.m:68-70), None on the other ranks.
+    `solver(method_id, Corresp, CalM)` may replace the GPU call (used by the CPU plumbing tests)."""
+    rank, size = sharding.world()
+    lo, hi = sharding.shard_range(total_trials, rank, size)
+    d = scene.sweep_batch(hi - lo, n, first_trial=lo, noise_levels=noise_levels, focalL=focalL, angle=angle,
+                          workers=workers)
+    L = len(noise_levels)
+    level_idx = (np.arange(lo, hi) % L).astype(np.int64)
+    out = {}
+    for m in methods:
+        if solver is not None:
+            repr_err, rot_err, t_err = solver(m, d["Corresp"], d["CalM"], d["R_t0"])
+        else:
+            res = METHODS[m][1](d["Corresp"], d["CalM"], device=device)
+            repr_err, rot_err, t_err = evaluate(res, d["R_t0"], device=device)
+        total = sharding.sum_in_rank_order(level_sums(level_idx, L, repr_err, rot_err, t_err))
+        if total is not None:
+            out[m] = total[:, :3] / total[:, 3:4]
+    return out if rank == 0 else None
