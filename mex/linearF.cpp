@@ -1,0 +1,18 @@
+// MEX gateway: F = linearF(p1,p2)   drop-in for F_methods/linearF.m:1 (also called by optimF.m:50).
+#include "tvf_mex_common.h"
+
+void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
+    using namespace tvf_mex;
+    if (nrhs != 2) mexErrMsgIdAndTxt("TFT_vs_Fund:nargin", "linearF(p1,p2) takes two inputs");
+    if (nlhs > 1) mexErrMsgIdAndTxt("TFT_vs_Fund:nargout", "linearF returns one output");
+    require_real_double(prhs[0], "p1"); require_real_double(prhs[1], "p2");
+    const Dims a = dims3(prhs[0]), b = dims3(prhs[1]);
+    if (a.n != b.n || a.n < 8) mexErrMsgIdAndTxt("TFT_vs_Fund:linearF", TVF_LINEARF_ERRMSG);        // linearF.m:35-37
+    if (a.rows != b.rows || a.B != b.B || (a.rows != 2 && a.rows != 3))
+        mexErrMsgIdAndTxt("TFT_vs_Fund:badInput", "p1,p2 must both be 2xN or 3xN");
+    tvf_handle_t h = handle();
+    mxArray* F = make(3, 3, a.B);
+    const int rc = tvf_linear_f(h, mxGetPr(prhs[0]), mxGetPr(prhs[1]), (int)a.rows, (int)a.n, (int64_t)a.B, mxGetPr(F), nullptr);
+    if (rc < 0) { mxDestroyArray(F); check(rc, h); }
+    plhs[0] = F;
+}
