@@ -53,6 +53,7 @@ def kernel_flops(n):
         "votes_kernel": 6632 * n,                # 8 two-view DLTs per point + signs
         "scale_kernel": 846 * n + 60,            # two-view DLT per point + closed-form lambda
         "final_kernel": 1031 * n + 125,          # three-view DLT per point + ReprError
+        "pose_tail_fused_kernel": 8509 * n + 185,  # votes + scale + final in one launch (n <= 256)
     }
 
 

@@ -59,10 +59,17 @@ int hc_pose_tail(int mode, const double* model, const double* CalM, const double
     load_K1_as_P1(CalM, P1);
     int vote[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     int nan2 = 0, nan3 = 0;
-    for (int i = 0; i < n; ++i) {
-        const double* p = corresp + 6 * i;
-        cheirality_point(P1, cand, p[0], p[1], p[2], p[3], vote, &nan2);
-        cheirality_point(P1, cand + CAND_PAIR, p[0], p[1], p[4], p[5], vote + 4, &nan3);
+    {
+        int v2[2] = {0, 0}, v3[2] = {0, 0}, n2 = 0, n3 = 0;
+        for (int i = 0; i < n; ++i) {
+            const double* p = corresp + 6 * i;
+            double ra[4], rb[4];
+            dlt_rows(P1, p[0], p[1], ra, rb);
+            cheirality_point(ra, rb, cand, p[2], p[3], v2, &n2, nullptr, nullptr);
+            cheirality_point(ra, rb, cand + CAND_PAIR, p[4], p[5], v3, &n3, nullptr, nullptr);
+        }
+        expand_votes(v2, n2, vote, &nan2);
+        expand_votes(v3, n3, vote + 4, &nan3);
     }
     for (int k = 0; k < 8; ++k) votes8[k] = vote[k];
     const int k2 = select_candidate(vote, nan2), k3 = select_candidate(vote + 4, nan3);

@@ -67,7 +67,7 @@ SIGNATURES = {
     "tvf_kernel_name": (C.c_char_p, [_I]),
     "tvf_fp64_peak_tflops": (C.c_double, [_H]),
 }
-NUM_KERNELS = 10
+NUM_KERNELS = 11
 
 _lib = None
 _lock = threading.Lock()

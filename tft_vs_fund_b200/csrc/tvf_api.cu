@@ -193,9 +193,13 @@ int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double*
         timed_launch(h, TVF_K_F_FINISH, st, [&] { launch_f_finish(d_core, 1, Bc, d_F, st); });
         timed_launch(h, TVF_K_CANDIDATES, st, [&] { launch_candidates(1, d_F, a, st); });
     }
-    timed_launch(h, TVF_K_VOTES, st, [&] { launch_votes(a, sm, st); });
-    timed_launch(h, TVF_K_SCALE, st, [&] { launch_scale(a, sm, st); });
-    timed_launch(h, TVF_K_FINAL, st, [&] { launch_final(a, sm, st); });
+    if (n >= TAIL_FUSED_MIN_N && n <= TAIL_FUSED_MAX_N) {
+        timed_launch(h, TVF_K_TAIL_FUSED, st, [&] { launch_pose_tail_fused(a, sm, st); });
+    } else {
+        timed_launch(h, TVF_K_VOTES, st, [&] { launch_votes(a, sm, st); });
+        timed_launch(h, TVF_K_SCALE, st, [&] { launch_scale(a, sm, st); });
+        timed_launch(h, TVF_K_FINAL, st, [&] { launch_final(a, sm, st); });
+    }
     if (method == METHOD_F && d_T != nullptr)
         timed_launch(h, TVF_K_TFT_FROM_POSE, st, [&] { launch_tft_from_pose(d_calm, calm_batched, d_Rt2, d_Rt3, Bc, d_T, st); });
     TVF_CK(cudaGetLastError());
@@ -482,7 +486,8 @@ double tvf_fp64_peak_tflops(tvf_handle_t h) {
 const char* tvf_kernel_name(int id) {
     static const char* names[TVF_NUM_KERNELS] = {"tft_stage1_kernel", "tft_epipoles_kernel", "tft_stage2_kernel",
                                                  "f_stage1_kernel", "f_finish_kernel", "candidates_kernel",
-                                                 "votes_kernel", "scale_kernel", "final_kernel", "tft_from_pose_kernel"};
+                                                 "votes_kernel", "scale_kernel", "final_kernel", "tft_from_pose_kernel",
+                                                 "pose_tail_fused_kernel"};
     return (id >= 0 && id < TVF_NUM_KERNELS) ? names[id] : "";
 }
 
@@ -618,10 +623,15 @@ int tvf_rt_from_tft(tvf_handle_t h, const double* T, const double* calm, int cal
     if (u.rc) return u.rc;
     TVF_CK(cudaMemsetAsync(a.status, 0, (size_t)B * sizeof(int), u.st));
     launch_candidates(0, dT, a, u.st);
-    launch_votes(a, h->sm_count, u.st);
-    launch_scale(a, h->sm_count, u.st);
-    launch_final(a, h->sm_count, u.st);
-    h->launches += 4;
+    if (n >= TAIL_FUSED_MIN_N && n <= TAIL_FUSED_MAX_N) {
+        launch_pose_tail_fused(a, h->sm_count, u.st);
+        h->launches += 2;
+    } else {
+        launch_votes(a, h->sm_count, u.st);
+        launch_scale(a, h->sm_count, u.st);
+        launch_final(a, h->sm_count, u.st);
+        h->launches += 4;
+    }
     std::vector<int32_t> tmp; int32_t* sth = status;
     if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }
     u.back(Rt2, a.Rt2, 12 * (size_t)B); u.back(Rt3, a.Rt3, 12 * (size_t)B);

@@ -52,6 +52,10 @@ struct PoseTailArgs {
 
 // mode 0: model = T (27 x B, pixel coordinates); mode 1: model = [F21 F31] (18 x B)
 void launch_candidates(int mode, const double* model, const PoseTailArgs& a, cudaStream_t stream);
+// TAIL_FUSED_MIN_N <= n <= TAIL_FUSED_MAX_N: votes + scale + final in one launch; otherwise the three kernels below
+constexpr int TAIL_FUSED_MIN_N = 7;
+constexpr int TAIL_FUSED_MAX_N = 256;
+void launch_pose_tail_fused(const PoseTailArgs& a, int sm_count, cudaStream_t stream);
 void launch_votes(const PoseTailArgs& a, int sm_count, cudaStream_t stream);
 void launch_scale(const PoseTailArgs& a, int sm_count, cudaStream_t stream);
 void launch_final(const PoseTailArgs& a, int sm_count, cudaStream_t stream);

@@ -120,30 +120,42 @@ TVF_HD void triangulate3(const double* Pa, const double* Pb, const double* Pc, c
     dlt_null<6>(a, X);
 }
 
-// One point's contribution to the four votes of a pair (R_t_from_TFT.m:98-100).
-// vote[k] += sign(X1(3)) + sign(X2(3)); nanmask bit k set when that sum is NaN.
-TVF_HD void cheirality_point(const double* P1, const double* c, double x1, double y1, double x2, double y2,
-                             int* vote, int* nanmask) {
-    double ra[4], rb[4];
-    dlt_rows(P1, x1, y1, ra, rb);
+// One point's contribution to the votes of a pair (R_t_from_TFT.m:98-100).
+// Only candidates (R,t) and (Rp,t) are triangulated: negating t negates the fourth column of the
+// candidate camera, which negates the fourth component of every quantity of the Householder QR and of
+// the inverse iteration *bit for bit* (all operations are sign-symmetric), so the DLT solution of
+// (R,-t) is (X,Y,Z,-W) exactly, both depths change sign, and vote(R,-t) = -vote(R,t),
+// vote(Rp,-t) = -vote(Rp,t) -- not an approximation, the same numbers the four separate DLTs give.
+// v[0] += vote of (R,t), v[1] += vote of (Rp,t); nanmask bit 0/1 set when that sum is NaN.
+// Xa/Xb (may be null) receive the homogeneous solutions for (R,t) and (Rp,t).
+TVF_HD void cheirality_point(const double* ra, const double* rb, const double* c, double x2, double y2,
+                             int* v, int* nanmask, double* Xa, double* Xb) {
 #pragma unroll 1
-    for (int k = 0; k < 4; ++k) {
+    for (int q = 0; q < 2; ++q) {
         double P[12], r3[3], tz;
-        candidate_camera(c, k, P, r3, &tz);
+        candidate_camera(c, q == 0 ? 0 : 3, P, r3, &tz);
         double a[4][4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { a[0][q] = ra[q]; a[1][q] = rb[q]; }
+        for (int e = 0; e < 4; ++e) { a[0][e] = ra[e]; a[1][e] = rb[e]; }
         dlt_rows(P, x2, y2, a[2], a[3]);
         double X[4];
         dlt_null<4>(a, X);
         const double X0 = X[0] / X[3], X1 = X[1] / X[3], X2 = X[2] / X[3], X3 = X[3] / X[3];  // X1./X1(4)
         const double z2 = r3[0] * X0 + r3[1] * X1 + r3[2] * X2 + tz * X3;                      // [R t]*X1
         if (X2 != X2 || z2 != z2) {
-            *nanmask |= (1 << k);
+            *nanmask |= (1 << q);
         } else {
-            vote[k] += (int)sign_(X2) + (int)sign_(z2);
+            v[q] += (int)sign_(X2) + (int)sign_(z2);
         }
+        double* dst = (q == 0) ? Xa : Xb;
+        if (dst != nullptr) { dst[0] = X[0]; dst[1] = X[1]; dst[2] = X[2]; dst[3] = X[3]; }
     }
+}
+
+// votes of the four candidates in the reference's order (R,t),(R,-t),(Rp,-t),(Rp,t) from the two sums
+TVF_HD void expand_votes(const int* v2, int nan2, int* vote4, int* nan4) {
+    vote4[0] = v2[0]; vote4[1] = -v2[0]; vote4[2] = -v2[1]; vote4[3] = v2[1];
+    *nan4 = ((nan2 & 1) ? 3 : 0) | ((nan2 & 2) ? 12 : 0);
 }
 
 // R_t_from_TFT.m:91-104: `>=` with num_points_seen starting at 0, later ties win.
