@@ -20,7 +20,7 @@
 
 namespace tvf {
 
-constexpr int CORE_WARPS = 8;
+constexpr int CORE_WARPS = 4;
 constexpr int FEAT_STRIDE = 15;   // 14 features + 1 pad: conflict-free 64-bit lane-strided stores
 
 // per-problem work-space record handed from stage to stage (doubles)
@@ -112,7 +112,7 @@ struct __align__(16) Stage1Scratch {
 };
 
 template <bool PACKED>
-__global__ void __launch_bounds__(CORE_WARPS * 32, 2)
+__global__ void __launch_bounds__(CORE_WARPS * 32, 5)
 tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
     __shared__ Stage1Scratch scratch[CORE_WARPS];
     __shared__ unsigned char gidx[32 * 27];
@@ -176,7 +176,7 @@ tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ statu
 }
 
 // =========================================================================== TFT epipoles
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 tft_epipoles_kernel(double* __restrict__ ws, long long B) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -200,7 +200,7 @@ struct __align__(16) Stage2Scratch {
     double Nm[28];                   // N1, inv(N2), inv(N3)
 };
 
-__global__ void __launch_bounds__(CORE_WARPS * 32, 2)
+__global__ void __launch_bounds__(CORE_WARPS * 32, 5)
 tft_stage2_kernel(int normalize, long long B, const double* __restrict__ ws, double* __restrict__ Tout,
                   double* __restrict__ P2out, double* __restrict__ P3out, int* __restrict__ status) {
     __shared__ Stage2Scratch scratch[CORE_WARPS];
@@ -350,7 +350,7 @@ struct __align__(16) FScratch {
 
 // mode: in.normalize != 0 -> pose path (two pairs 1-2 and 1-3, outer normalisation); else one pair
 template <bool PACKED>
-__global__ void __launch_bounds__(CORE_WARPS * 32, 2)
+__global__ void __launch_bounds__(CORE_WARPS * 32, 5)
 f_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
     __shared__ FScratch scratch[CORE_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -463,7 +463,7 @@ f_finish_kernel(const double* __restrict__ ws, int normalize, long long B, doubl
 // ---------------------------------------------------------------------------
 static inline unsigned core_grid(long long B, int sm_count) {
     long long blocks = (B + CORE_WARPS - 1) / CORE_WARPS;
-    const long long cap = (long long)sm_count * 3 * 4;
+    const long long cap = (long long)sm_count * 5 * 4;
     if (blocks > cap) blocks = cap;
     return (unsigned)(blocks < 1 ? 1 : blocks);
 }

@@ -44,7 +44,7 @@ __device__ __forceinline__ const double* calm_of(const PoseTailArgs& a, long lon
 }
 
 // ------------------------------------------------------------------ candidates
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
 candidates_kernel(int mode, const double* __restrict__ model, PoseTailArgs a) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
