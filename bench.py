@@ -409,6 +409,91 @@ def run_gpu(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+# ---- BASELINE config 5: large-n triplets (HBM-oriented Gram formation) ------------------------------
+def run_large_n(args, local_rank):
+    """65 536 scenes x n = 10 000 correspondences (defaults: --trials 8192 to keep the default run short;
+    pass --trials 65536 for the full configuration).  Inputs are generated on the device with torch (scene
+    geometry of generateSyntheticScene, 1 px noise; no inside-image rejection) -- labelled in `data`."""
+    import torch
+    from tft_vs_fund_b200 import scene, _lib
+    n, B = args.n, args.trials
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    K, Ps, R_t0 = scene.scene_cameras(50, 0)
+    CalM = np.tile(K, (3, 1))
+    g = torch.Generator(device=dev); g.manual_seed(1)
+    d_corresp = torch.empty((B, n, 6), dtype=torch.float64, device=dev)
+    Pt = [torch.from_numpy(P).to(dev) for P in Ps]
+    step = max(1, (1 << 26) // n)
+    for lo in range(0, B, step):
+        hi = min(B, lo + step)
+        X = torch.rand((hi - lo, n, 3), dtype=torch.float64, device=dev, generator=g) * 400 - 200
+        for v in range(3):
+            x = X @ Pt[v][:, :3].T + Pt[v][:, 3]
+            d_corresp[lo:hi, :, 2 * v:2 * v + 2] = x[..., :2] / x[..., 2:3] + torch.randn((hi - lo, n, 2), dtype=torch.float64, device=dev, generator=g)
+        del X, x
+    h = _lib.Handle(local_rank)
+    lib = h.lib
+    stream = torch.cuda.Stream(device=dev)
+    h.call("tvf_set_stream", C.c_void_p(stream.cuda_stream))
+    d_calm = torch.from_numpy(np.ascontiguousarray(CalM.T)).to(dev)
+    d_Rt2 = torch.empty((B, 12), dtype=torch.float64, device=dev); d_Rt3 = torch.empty_like(d_Rt2)
+    d_rec = torch.empty((B, 3 * n), dtype=torch.float64, device=dev)
+    d_T = torch.empty((B, 27), dtype=torch.float64, device=dev)
+    d_rep = torch.empty((B,), dtype=torch.float64, device=dev); d_st = torch.zeros((B,), dtype=torch.int32, device=dev)
+    ptr = lambda t: C.c_void_p(t.data_ptr())
+
+    def step_fn():
+        h.call("tvf_linear_tft_pose_dev", ptr(d_corresp), ptr(d_calm), 0, n, B, ptr(d_Rt2), ptr(d_Rt3), ptr(d_rec),
+               ptr(d_T), ptr(d_rep), ptr(d_st))
+
+    for _ in range(max(1, args.warmup)):
+        step_fn()
+    torch.cuda.synchronize(dev)
+    h.call("tvf_profile_reset"); h.call("tvf_profile_enable", 1)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    steps = max(1, min(args.steps, 5))
+    sampler = ClockSampler(local_rank)
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(steps):
+            step_fn()
+        e1.record(stream)
+    torch.cuda.synchronize(dev)
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+    tot = (C.c_double * _lib.NUM_KERNELS)(); cnt = (C.c_int64 * _lib.NUM_KERNELS)()
+    h.call("tvf_profile_read", tot, cnt); h.call("tvf_profile_enable", 0)
+    prof = {lib.tvf_kernel_name(i).decode(): (tot[i], cnt[i]) for i in range(_lib.NUM_KERNELS) if cnt[i]}
+    peaks = measured_peaks()
+    hbm_peak = peaks["hbm_gbs"] if peaks else 6650.0
+    fp64_peak = lib.tvf_fp64_peak_tflops(h._h)
+    gram_ms, gram_n = prof.get("tft_moments_large_kernel", (float("nan"), 1))
+    gram_s = gram_ms * 1e-3 / max(1, gram_n)                       # one launch = all B scenes of the step (or a chunk)
+    scenes_per_launch = B * steps / max(1, gram_n)
+    gram_bytes = (48 * n + 216) * scenes_per_launch
+    line = {
+        "metric": "large-n linearTFT Gram formation (normalisation + 96 moments), scenes/s", "unit": "scenes/s",
+        "value": scenes_per_launch / gram_s, "n_gpus": 1, "steps": steps, "warmup": max(1, args.warmup),
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (device-generated scenes of generateSyntheticScene's geometry, 1 px noise, no inside-image rejection)",
+        "config": {"workload": "large-n triplets: %d correspondences per scene x %d scenes (BASELINE config 5)" % (n, B),
+                   "n_points": n, "scenes": B, "cache": "%.1f GB of input per step, far beyond L2" % (B * n * 48 / 1e9)},
+        "roofline": {"bound": "hbm", "kernel": "tft_moments_large_kernel", "achieved": gram_bytes / gram_s / 1e9,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": gram_bytes / gram_s / 1e9 / hbm_peak, "traffic": None,
+                     "work_model": "48*n+216 algorithmic bytes per scene (SURVEY.md 8d)"},
+        "roofline_fp64": {"bound": "fp64", "achieved": 624.0 * n * scenes_per_launch / gram_s / 1e12, "peak": fp64_peak,
+                          "unit": "TFLOP/s", "frac": 624.0 * n * scenes_per_launch / gram_s / 1e12 / fp64_peak,
+                          "work_model": "624*n algorithmic flop per scene (12-nnz rows, symmetric half; SURVEY.md B.3)"},
+        "full_pipeline": {"metric": "LinearTFTPoseEstimation + ReprError solves/s at n=%d" % n, "value": B * steps / (ms * 1e-3),
+                          "unit": "solves/s", "fp64_frac_algorithmic": tft_flops(n) * B * steps / (ms * 1e-3) / 1e12 / fp64_peak},
+        "kernels": {k: {"ms_total": v[0], "launches": int(v[1])} for k, v in prof.items()},
+        "flagged_problems": int(torch.count_nonzero(d_st).item()), "clocks": clocks,
+        "gpu_launches": int(sum(v[1] for v in prof.values())),
+    }
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -419,12 +504,17 @@ def main():
     ap.add_argument("--n", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=0, help="trials in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="sweep", choices=["sweep", "large-n"],
+                    help="sweep = BASELINE config 3/4 (headline); large-n = config 5 (use with --n 10000 --trials 65536)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+    elif args.workload == "large-n":
+        if rank == 0:
+            run_large_n(args, local_rank)
     else:
         run_gpu(args, rank, local_rank, world)
 

@@ -159,7 +159,9 @@ int64_t tvf_launch_count(tvf_handle_t h);
 #define TVF_K_FINAL 8
 #define TVF_K_TFT_FROM_POSE 9
 #define TVF_K_TAIL_FUSED 10
-#define TVF_NUM_KERNELS 11
+#define TVF_K_TFT_MOMENTS_LARGE 11
+#define TVF_K_TFT_STAGE1_SOLVE 12
+#define TVF_NUM_KERNELS 13
 int tvf_profile_enable(tvf_handle_t h, int on);
 int tvf_profile_reset(tvf_handle_t h);
 int tvf_profile_read(tvf_handle_t h, double* total_ms, int64_t* launches);

@@ -285,3 +285,24 @@ def test_experiments_sweep_table(tvf):
     for m in (1, 7):
         assert np.max(np.abs(table[m][:, 0] - ref[m][:, 0])) < 1e-8                          # px
         assert np.max(np.abs(table[m][:, 1:] - ref[m][:, 1:])) < 1e-4                        # degrees (1e-6 rad = 5.7e-5 deg)
+
+
+@pytest.mark.parametrize("n", [1024, 1027, 1100])
+def test_large_n_cluster_tma_path(tvf, n):
+    """n >= 1024 takes the cluster/TMA moments kernel (tvf_large_kernels.cu) + the three-kernel pose tail."""
+    Cs = []
+    for s_ in (1, 2):
+        CalM, R_t0, C, _ = o.generateSyntheticScene(n, 1.0, s_, 50, 0)
+        Cs.append(C)
+    Cs = np.stack(Cs)
+    res = tvf.LinearTFTPoseEstimation(Cs, CalM)
+    assert np.all(res.status == 0)
+    K = CalM[:3]
+    for b in range(2):
+        R2, R3, Rec, T, _ = o.LinearTFTPoseEstimation(Cs[b], CalM)
+        rep = o.ReprError([K @ np.eye(3, 4), K @ R2, K @ R3], Cs[b], Rec)
+        assert_pose_close((R2, R3, Rec, T, rep), (res[0][b], res[1][b], res[2][b], res[3][b], res.repr_err[b]),
+                          "large n=%d scene %d" % (n, b))
+    # the generic warp-per-problem stage 1 gives the same tensor (n just below the threshold exercises it at similar size)
+    one = tvf.LinearTFTPoseEstimation(Cs[0], CalM)
+    assert np.array_equal(one[3], res[3][0])

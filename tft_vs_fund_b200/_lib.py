@@ -67,7 +67,7 @@ SIGNATURES = {
     "tvf_kernel_name": (C.c_char_p, [_I]),
     "tvf_fp64_peak_tflops": (C.c_double, [_H]),
 }
-NUM_KERNELS = 11
+NUM_KERNELS = 13
 
 _lib = None
 _lock = threading.Lock()

@@ -184,7 +184,16 @@ int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double*
     a.Rt2 = d_Rt2; a.Rt3 = d_Rt3; a.reconst = d_reconst; a.repr_err = d_repr; a.status = d_status;
     const int sm = h->sm_count;
     if (method == METHOD_TFT) {
-        timed_launch(h, TVF_K_TFT_STAGE1, st, [&] { launch_tft_stage1(in, d_core, d_status, sm, st); });
+        bool large_done = false;
+        if (n >= LARGE_N_MIN) {
+            timed_launch(h, TVF_K_TFT_MOMENTS_LARGE, st, [&] {
+                large_done = launch_tft_moments_large(d_corresp, n, Bc, 1, d_core, sm, st) != 0;
+            });
+            if (large_done)
+                timed_launch(h, TVF_K_TFT_STAGE1_SOLVE, st, [&] { launch_tft_stage1_solve(Bc, d_core, d_status, sm, st); });
+        }
+        if (!large_done)
+            timed_launch(h, TVF_K_TFT_STAGE1, st, [&] { launch_tft_stage1(in, d_core, d_status, sm, st); });
         timed_launch(h, TVF_K_TFT_EPIPOLES, st, [&] { launch_tft_epipoles(d_core, Bc, st); });
         timed_launch(h, TVF_K_TFT_STAGE2, st, [&] { launch_tft_stage2(1, Bc, d_core, d_T, nullptr, nullptr, d_status, sm, st); });
         timed_launch(h, TVF_K_CANDIDATES, st, [&] { launch_candidates(0, d_T, a, st); });
@@ -487,7 +496,8 @@ const char* tvf_kernel_name(int id) {
     static const char* names[TVF_NUM_KERNELS] = {"tft_stage1_kernel", "tft_epipoles_kernel", "tft_stage2_kernel",
                                                  "f_stage1_kernel", "f_finish_kernel", "candidates_kernel",
                                                  "votes_kernel", "scale_kernel", "final_kernel", "tft_from_pose_kernel",
-                                                 "pose_tail_fused_kernel"};
+                                                 "pose_tail_fused_kernel", "tft_moments_large_kernel",
+                                                 "tft_stage1_solve_kernel"};
     return (id >= 0 && id < TVF_NUM_KERNELS) ? names[id] : "";
 }
 

@@ -111,6 +111,18 @@ struct __align__(16) Stage1Scratch {
     double mom[98];                  // 96 moments + zero sentinel
 };
 
+// null vector of the 27x27 Gram assembled from the 96 moments in sc.mom (linearTFT.m:64-67)
+__device__ __forceinline__ void solve_from_moments(Stage1Scratch& sc, const unsigned char* gidx, double* rec, int lane,
+                                                   int* status, long long prob) {
+    double g[27];
+#pragma unroll
+    for (int c = 0; c < 27; ++c) g[c] = sc.mom[gidx[lane * 27 + c]];
+    bool conv;
+    const double tl = smallest_eigvec_spd<27>(g, lane, sc.sbuf, &conv);
+    if (lane < 27) rec[CW_T1 + lane] = tl;
+    if (status != nullptr && lane == 0) status[prob] = conv ? 0 : ST_EIG_NOCONV;
+}
+
 template <bool PACKED>
 __global__ void __launch_bounds__(CORE_WARPS * 32, 5)
 tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
@@ -164,14 +176,28 @@ tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ statu
         if (lane < 3) rec[CW_STATS + lane] = sel3(s, lane);
         if (lane < 6) rec[CW_STATS + 3 + lane] = (lane < 3) ? sel3(t, lane) : sel3(t + 3, lane - 3);
         __syncwarp();
-        // ---- null vector of the 27x27 Gram (linearTFT.m:64-67) ---------------------------
-        double g[27];
-#pragma unroll
-        for (int c = 0; c < 27; ++c) g[c] = sc.mom[gidx[lane * 27 + c]];
-        bool conv;
-        const double tl = smallest_eigvec_spd<27>(g, lane, sc.sbuf, &conv);
-        if (lane < 27) rec[CW_T1 + lane] = tl;
-        if (status != nullptr && lane == 0) status[prob] = conv ? 0 : ST_EIG_NOCONV;
+        solve_from_moments(sc, gidx, rec, lane, status, prob);
+    }
+}
+
+// Large-n path: the moments were produced by tft_moments_large_kernel (tvf_large_kernels.cu); this is the
+// second half of stage 1 on its own (27x27 Gram from the 96 moments -> null vector).
+__global__ void __launch_bounds__(CORE_WARPS * 32, 5)
+tft_stage1_solve_kernel(long long B, double* __restrict__ ws, int* __restrict__ status) {
+    __shared__ Stage1Scratch scratch[CORE_WARPS];
+    __shared__ unsigned char gidx[32 * 27];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    build_gidx(gidx);
+    Stage1Scratch& sc = scratch[warp];
+    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < B; base += (long long)gridDim.x * CORE_WARPS) {
+        __syncthreads();
+        const long long prob = base + warp;
+        if (prob >= B) continue;
+        double* rec = ws + prob * CORE_WS_TFT;
+        sc.mom[lane] = rec[CW_MOM + lane]; sc.mom[lane + 32] = rec[CW_MOM + 32 + lane]; sc.mom[lane + 64] = rec[CW_MOM + 64 + lane];
+        if (lane == 0) { sc.mom[96] = 0.0; sc.mom[97] = 0.0; }
+        __syncwarp();
+        solve_from_moments(sc, gidx, rec, lane, status, prob);
     }
 }
 
@@ -472,6 +498,11 @@ void launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_coun
     if (in.B <= 0) return;
     if (in.packed) tft_stage1_kernel<true><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
     else tft_stage1_kernel<false><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+}
+
+void launch_tft_stage1_solve(long long B, double* ws, int* status, int sm_count, cudaStream_t stream) {
+    if (B <= 0) return;
+    tft_stage1_solve_kernel<<<core_grid(B, sm_count), CORE_WARPS * 32, 0, stream>>>(B, ws, status);
 }
 
 void launch_tft_epipoles(double* ws, long long B, cudaStream_t stream) {

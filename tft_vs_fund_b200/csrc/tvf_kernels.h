@@ -24,6 +24,12 @@ constexpr int CORE_WS_TFT = 140;   // 96 moments | 9 normalisation stats (+1) | 
 constexpr int CORE_WS_F = 36;      // raw f (2 x 9) | outer stats 9 | inner stats 9
 
 void launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream);
+// large-n stage 1: cluster/TMA moments kernel (returns 0 if the shape is unsupported -> use launch_tft_stage1)
+// followed by the solve-only half of stage 1
+constexpr int LARGE_N_MIN = 1024;
+int launch_tft_moments_large(const double* corresp, int n, long long B, int normalize, double* ws, int sm_count,
+                             cudaStream_t stream);
+void launch_tft_stage1_solve(long long B, double* ws, int* status, int sm_count, cudaStream_t stream);
 void launch_tft_epipoles(double* ws, long long B, cudaStream_t stream);
 void launch_tft_stage2(int normalize, long long B, const double* ws, double* T, double* P2, double* P3, int* status,
                        int sm_count, cudaStream_t stream);
