@@ -195,7 +195,7 @@ int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double*
         if (!large_done)
             timed_launch(h, TVF_K_TFT_STAGE1, st, [&] { launch_tft_stage1(in, d_core, d_status, sm, st); });
         timed_launch(h, TVF_K_TFT_EPIPOLES, st, [&] { launch_tft_epipoles(d_core, Bc, st); });
-        timed_launch(h, TVF_K_TFT_STAGE2, st, [&] { launch_tft_stage2(1, Bc, d_core, d_T, nullptr, nullptr, d_status, sm, st); });
+        timed_launch(h, TVF_K_TFT_STAGE2, st, [&] { launch_tft_stage2(in, d_core, d_T, nullptr, nullptr, d_status, sm, st); });
         timed_launch(h, TVF_K_CANDIDATES, st, [&] { launch_candidates(0, d_T, a, st); });
     } else {
         timed_launch(h, TVF_K_F_STAGE1, st, [&] { launch_f_stage1(in, d_core, d_status, sm, st); });
@@ -543,7 +543,7 @@ int tvf_linear_tft(tvf_handle_t h, const double* p1, const double* p2, const dou
     if (u.rc) return u.rc;
     launch_tft_stage1(in, dws, dst, h->sm_count, u.st);
     launch_tft_epipoles(dws, B, u.st);
-    launch_tft_stage2(0, B, dws, dT, dP2, dP3, dst, h->sm_count, u.st);
+    launch_tft_stage2(in, dws, dT, dP2, dP3, dst, h->sm_count, u.st);
     h->launches += 3;
     std::vector<int32_t> tmp; int32_t* sth = status;
     if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }

@@ -89,6 +89,84 @@ __device__ __forceinline__ void view_stats(const CoreInput& in, long long prob, 
     }
 }
 
+constexpr int REFINE_N_MAX = 12;      // systems with fewer points get refinement steps (needs n <= 32: one point per lane)
+
+// (A'A) x for the trilinearity design matrix of linearTFT.m:45-62, from the rows themselves: lane = point
+// computes its 4 residuals y = A_i x and its contribution A_i' y; a transposed butterfly leaves component r
+// of the total on lane r.  xs: 27 doubles in shared memory.  (s,t): normalisation of the three views.
+template <bool PACKED>
+__device__ __forceinline__ double tft_apply_AtA(const CoreInput& in, long long prob, int lane, const double* s,
+                                                const double* t, const double* xs) {
+    double c[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) c[k] = 0.0;
+    if (lane < in.n) {
+        double p[6];
+        load_point<PACKED>(in, prob, lane, p);
+        const double x1 = s[0] * p[0] + t[0], y1 = s[0] * p[1] + t[1];
+        const double x2 = s[1] * p[2] + t[2], y2 = s[1] * p[3] + t[3];
+        const double x3 = s[2] * p[4] + t[4], y3 = s[2] * p[5] + t[5];
+        // rows are p1' (x) b' (x) a' with a in {(1,0,-x2),(0,1,-y2)}, b in {(1,0,-x3),(0,1,-y3)}
+        double v[2][2][3];      // [a][b][i]
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            double u0[3], u1[3];    // contraction with a, per k
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const double X0 = xs[3 * k + 9 * i], X1 = xs[1 + 3 * k + 9 * i], X2 = xs[2 + 3 * k + 9 * i];
+                u0[k] = X0 - x2 * X2; u1[k] = X1 - y2 * X2;
+            }
+            v[0][0][i] = u0[0] - x3 * u0[2]; v[0][1][i] = u0[1] - y3 * u0[2];
+            v[1][0][i] = u1[0] - x3 * u1[2]; v[1][1][i] = u1[1] - y3 * u1[2];
+        }
+        const double y00 = x1 * v[0][0][0] + y1 * v[0][0][1] + v[0][0][2];
+        const double y01 = x1 * v[0][1][0] + y1 * v[0][1][1] + v[0][1][2];
+        const double y10 = x1 * v[1][0][0] + y1 * v[1][0][1] + v[1][0][2];
+        const double y11 = x1 * v[1][1][0] + y1 * v[1][1][1] + v[1][1][2];
+        // z[k][j] = sum_ab y_ab b_b[k] a_a[j]
+        double z[3][3];
+        z[0][0] = y00; z[0][1] = y10; z[0][2] = -x2 * y00 - y2 * y10;
+        z[1][0] = y01; z[1][1] = y11; z[1][2] = -x2 * y01 - y2 * y11;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) z[2][j] = -x3 * z[0][j] - y3 * z[1][j];
+        const double p1[3] = {x1, y1, 1.0};
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) c[j + 3 * k + 9 * i] = p1[i] * z[k][j];
+    }
+    return warp_reduce_transposed32(c, lane);
+}
+
+// (A'A) f for the eight-point design matrix of linearF.m:49-53 (rows [x1x2,x1y2,x1,y1x2,y1y2,y1,x2,y2,1]).
+// (sa,ta*) / (sb,tb*): composed normalisation of the two views; va,vb: which views.
+template <bool PACKED>
+__device__ __forceinline__ double f_apply_AtA(const CoreInput& in, long long prob, int lane, int vb, double sa, double tax,
+                                              double tay, double sb, double tbx, double tby, const double* fs) {
+    double c[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) c[k] = 0.0;
+    if (lane < in.n) {
+        double p[6];
+        load_point<PACKED>(in, prob, lane, p);
+        const double xb = (vb == 1) ? p[2] : p[4], yb = (vb == 1) ? p[3] : p[5];
+        const double a[3] = {sa * p[0] + tax, sa * p[1] + tay, 1.0};
+        const double b[3] = {sb * xb + tbx, sb * yb + tby, 1.0};
+        double y = 0.0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) y = fma(a[q] * b[r], fs[3 * q + r], y);
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) c[3 * q + r] = y * a[q] * b[r];
+    }
+    return warp_reduce_transposed32(c, lane);
+}
+
 // G(r,c) -> moment index (96 = structural zero), one table per CTA
 __device__ __forceinline__ void build_gidx(unsigned char* gidx) {
     for (int e = threadIdx.x; e < 32 * 27; e += blockDim.x) {
@@ -112,19 +190,20 @@ struct __align__(16) Stage1Scratch {
 };
 
 // null vector of the 27x27 Gram assembled from the 96 moments in sc.mom (linearTFT.m:64-67)
+template <class Resid>
 __device__ __forceinline__ void solve_from_moments(Stage1Scratch& sc, const unsigned char* gidx, double* rec, int lane,
-                                                   int* status, long long prob) {
+                                                   int* status, long long prob, Resid resid, int nrefine) {
     double g[27];
 #pragma unroll
     for (int c = 0; c < 27; ++c) g[c] = sc.mom[gidx[lane * 27 + c]];
     bool conv;
-    const double tl = smallest_eigvec_spd<27>(g, lane, sc.sbuf, &conv);
+    const double tl = smallest_eigvec_spd<27>(g, lane, sc.sbuf, &conv, resid, nrefine);
     if (lane < 27) rec[CW_T1 + lane] = tl;
     if (status != nullptr && lane == 0) status[prob] = conv ? 0 : ST_EIG_NOCONV;
 }
 
-template <bool PACKED>
-__global__ void __launch_bounds__(CORE_WARPS * 32, 5)
+template <bool PACKED, bool REFINE>
+__global__ void __launch_bounds__(CORE_WARPS * 32, REFINE ? 3 : 5)
 tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
     __shared__ Stage1Scratch scratch[CORE_WARPS];
     __shared__ unsigned char gidx[32 * 27];
@@ -176,7 +255,12 @@ tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ statu
         if (lane < 3) rec[CW_STATS + lane] = sel3(s, lane);
         if (lane < 6) rec[CW_STATS + 3 + lane] = (lane < 3) ? sel3(t, lane) : sel3(t + 3, lane - 3);
         __syncwarp();
-        solve_from_moments(sc, gidx, rec, lane, status, prob);
+        if constexpr (REFINE) {
+            solve_from_moments(sc, gidx, rec, lane, status, prob,
+                               [&](const double* xs) { return tft_apply_AtA<PACKED>(in, prob, lane, s, t, xs); }, 2);
+        } else {
+            solve_from_moments(sc, gidx, rec, lane, status, prob, NoRefine(), 0);
+        }
     }
 }
 
@@ -197,7 +281,7 @@ tft_stage1_solve_kernel(long long B, double* __restrict__ ws, int* __restrict__ 
         sc.mom[lane] = rec[CW_MOM + lane]; sc.mom[lane + 32] = rec[CW_MOM + 32 + lane]; sc.mom[lane + 64] = rec[CW_MOM + 64 + lane];
         if (lane == 0) { sc.mom[96] = 0.0; sc.mom[97] = 0.0; }
         __syncwarp();
-        solve_from_moments(sc, gidx, rec, lane, status, prob);
+        solve_from_moments(sc, gidx, rec, lane, status, prob, NoRefine(), 0);
     }
 }
 
@@ -226,9 +310,12 @@ struct __align__(16) Stage2Scratch {
     double Nm[28];                   // N1, inv(N2), inv(N3)
 };
 
-__global__ void __launch_bounds__(CORE_WARPS * 32, 5)
-tft_stage2_kernel(int normalize, long long B, const double* __restrict__ ws, double* __restrict__ Tout,
+template <bool PACKED, bool REFINE>
+__global__ void __launch_bounds__(CORE_WARPS * 32, REFINE ? 3 : 5)
+tft_stage2_kernel(CoreInput in, const double* __restrict__ ws, double* __restrict__ Tout,
                   double* __restrict__ P2out, double* __restrict__ P3out, int* __restrict__ status) {
+    const int normalize = in.normalize;
+    const long long B = in.B;
     __shared__ Stage2Scratch scratch[CORE_WARPS];
     __shared__ unsigned char gidx[32 * 27];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -299,16 +386,43 @@ tft_stage2_kernel(int normalize, long long B, const double* __restrict__ ws, dou
 #pragma unroll
                     for (int c = 0; c < 15; ++c) g15[c] = fma(coef, W[c], g15[c]);
                 }
+            const double pe = sel3(e21, jr), pu1 = sel3(u1, jr), pu2 = sel3(u2, jr);
+            const double qe = sel3(e31, kr), qv1 = sel3(v1, kr), qv2 = sel3(v2, kr);
+            const double st_s[3] = {rec[CW_STATS], rec[CW_STATS + 1], rec[CW_STATS + 2]};
+            const double st_t[6] = {rec[CW_STATS + 3], rec[CW_STATS + 4], rec[CW_STATS + 5], rec[CW_STATS + 6],
+                                    rec[CW_STATS + 7], rec[CW_STATS + 8]};
+            // Up' A'A Up tp from the design rows (refinement of the projected problem, small n only)
+            auto resid15 = [&](const double* xs) {
+                double a27 = 0.0;
+                if (lane < 27) {
+                    const double* tp = xs + 5 * ir;
+                    a27 = pe * (qe * tp[0] + qv1 * tp[1] + qv2 * tp[2]) + qe * (pu1 * tp[3] + pu2 * tp[4]);
+                }
+                __syncwarp();
+                if (lane < 27) sc.W[lane] = a27;
+                __syncwarp();
+                const double g27 = tft_apply_AtA<PACKED>(in, prob, lane, st_s, st_t, sc.W);
+                __syncwarp();
+                if (lane < 27) sc.W[32 + lane] = g27;
+                __syncwarp();
+                double r = 0.0;
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) r = fma(pa[j] * qa[k], sc.W[32 + 9 * ia + 3 * k + j], r);
+                return (lane < 15) ? r : 0.0;
+            };
             bool conv2;
-            const double tpl = smallest_eigvec_spd<15>(g15, lane, sc.sbuf, &conv2);
+            double tpl;
+            if constexpr (REFINE) tpl = smallest_eigvec_spd<15>(g15, lane, sc.sbuf, &conv2, resid15, 1);
+            else tpl = smallest_eigvec_spd<15>(g15, lane, sc.sbuf, &conv2);
             if (!conv2) st |= ST_EIG_NOCONV;
+            __syncwarp();
             if (lane < 15) sc.tp[lane] = tpl;
             __syncwarp();
             double acc = 0.0;                                                   // t = Up*tp  (linearTFT.m:85)
             if (lane < 27) {
                 const double* tp = sc.tp + 5 * ir;
-                const double pe = sel3(e21, jr), pu1 = sel3(u1, jr), pu2 = sel3(u2, jr);
-                const double qe = sel3(e31, kr), qv1 = sel3(v1, kr), qv2 = sel3(v2, kr);
                 acc = pe * (qe * tp[0] + qv1 * tp[1] + qv2 * tp[2]) + qe * (pu1 * tp[3] + pu2 * tp[4]);
             }
             tl2 = acc * rsqrt(warp_sum(acc * acc));
@@ -375,8 +489,8 @@ struct __align__(16) FScratch {
 };
 
 // mode: in.normalize != 0 -> pose path (two pairs 1-2 and 1-3, outer normalisation); else one pair
-template <bool PACKED>
-__global__ void __launch_bounds__(CORE_WARPS * 32, 5)
+template <bool PACKED, bool REFINE>
+__global__ void __launch_bounds__(CORE_WARPS * 32, REFINE ? 3 : 5)
 f_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
     __shared__ FScratch scratch[CORE_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -438,7 +552,12 @@ f_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status)
                 g[c] = (lane < 9) ? v : 0.0;
             }
             bool conv;
-            const double fl = smallest_eigvec_spd<9>(g, lane, sc.sbuf, &conv);            // linearF.m:54-55
+            double fl;                                                                     // linearF.m:54-55
+            if constexpr (REFINE)
+                fl = smallest_eigvec_spd<9>(g, lane, sc.sbuf, &conv, [&](const double* xs) {
+                    return f_apply_AtA<PACKED>(in, prob, lane, vb, sa, tax, tay, sb, tbx, tby, xs); }, 2);
+            else
+                fl = smallest_eigvec_spd<9>(g, lane, sc.sbuf, &conv);
             if (!conv) st |= ST_EIG_NOCONV;
             if (lane < 9) rec[FW_F + 9 * pr + lane] = fl;
         }
@@ -496,8 +615,12 @@ static inline unsigned core_grid(long long B, int sm_count) {
 
 void launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream) {
     if (in.B <= 0) return;
-    if (in.packed) tft_stage1_kernel<true><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
-    else tft_stage1_kernel<false><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    const unsigned g = core_grid(in.B, sm_count);
+    const bool refine = in.n < REFINE_N_MAX;       // barely determined systems: polish with the un-squared rows
+    if (in.packed && refine) tft_stage1_kernel<true, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    else if (in.packed) tft_stage1_kernel<true, false><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    else if (refine) tft_stage1_kernel<false, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    else tft_stage1_kernel<false, false><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
 }
 
 void launch_tft_stage1_solve(long long B, double* ws, int* status, int sm_count, cudaStream_t stream) {
@@ -510,16 +633,25 @@ void launch_tft_epipoles(double* ws, long long B, cudaStream_t stream) {
     tft_epipoles_kernel<<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(ws, B);
 }
 
-void launch_tft_stage2(int normalize, long long B, const double* ws, double* T, double* P2, double* P3, int* status,
+void launch_tft_stage2(const CoreInput& in, const double* ws, double* T, double* P2, double* P3, int* status,
                        int sm_count, cudaStream_t stream) {
-    if (B <= 0) return;
-    tft_stage2_kernel<<<core_grid(B, sm_count), CORE_WARPS * 32, 0, stream>>>(normalize, B, ws, T, P2, P3, status);
+    if (in.B <= 0) return;
+    const unsigned g = core_grid(in.B, sm_count);
+    const bool refine = in.n < REFINE_N_MAX;
+    if (in.packed && refine) tft_stage2_kernel<true, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, T, P2, P3, status);
+    else if (in.packed) tft_stage2_kernel<true, false><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, T, P2, P3, status);
+    else if (refine) tft_stage2_kernel<false, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, T, P2, P3, status);
+    else tft_stage2_kernel<false, false><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, T, P2, P3, status);
 }
 
 void launch_f_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream) {
     if (in.B <= 0) return;
-    if (in.packed) f_stage1_kernel<true><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
-    else f_stage1_kernel<false><<<core_grid(in.B, sm_count), CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    const unsigned g = core_grid(in.B, sm_count);
+    const bool refine = in.n < REFINE_N_MAX;
+    if (in.packed && refine) f_stage1_kernel<true, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    else if (in.packed) f_stage1_kernel<true, false><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    else if (refine) f_stage1_kernel<false, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    else f_stage1_kernel<false, false><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
 }
 
 void launch_f_finish(const double* ws, int normalize, long long B, double* F, cudaStream_t stream) {

@@ -31,7 +31,7 @@ int launch_tft_moments_large(const double* corresp, int n, long long B, int norm
                              cudaStream_t stream);
 void launch_tft_stage1_solve(long long B, double* ws, int* status, int sm_count, cudaStream_t stream);
 void launch_tft_epipoles(double* ws, long long B, cudaStream_t stream);
-void launch_tft_stage2(int normalize, long long B, const double* ws, double* T, double* P2, double* P3, int* status,
+void launch_tft_stage2(const CoreInput& in, const double* ws, double* T, double* P2, double* P3, int* status,
                        int sm_count, cudaStream_t stream);
 void launch_f_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream);
 // normalize != 0: two pairs per problem (F21, F31 -> F[18*b]); else one (F[9*b])

@@ -17,7 +17,7 @@
 #include <cooperative_groups.h>
 
 #include "tvf_kernels.h"
-#include "tvf_math.cuh"
+#include "tvf_warp.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -60,22 +60,6 @@ __device__ __forceinline__ double warp_sum_l(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
-}
-
-// Transposed butterfly: every lane holds 32 partial values v[0..31]; afterwards lane L holds the warp-wide
-// total of value index L (31 shuffles instead of 32 x 5).
-__device__ __forceinline__ double warp_reduce_transposed32(double (&v)[32], int lane) {
-#pragma unroll
-    for (int half = 16; half >= 1; half >>= 1) {
-        const bool hi = (lane & half) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const double send = hi ? v[i] : v[i + half];
-            const double keep = hi ? v[i + half] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-        }
-    }
-    return v[0];
 }
 
 // shared-memory layout (dynamic): [slice bytes] | Scratch

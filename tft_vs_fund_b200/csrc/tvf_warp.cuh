@@ -52,8 +52,33 @@ __device__ __forceinline__ double warp_max(double v) {
 // g: this lane's row (lanes >= N must pass zeros).  sbuf: 64 doubles of shared memory private to
 // the warp, 16-byte aligned.  Returns this lane's component of the unit eigenvector belonging to
 // the smallest eigenvalue; *converged is warp-uniform.
-template <int N>
-__device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int lane, double* sbuf, bool* converged) {
+struct NoRefine {
+    __device__ __forceinline__ double operator()(const double*) const { return 0.0; }
+};
+
+// Transposed butterfly over 32 per-lane values: afterwards lane L holds the warp-wide total of v[L].
+__device__ __forceinline__ double warp_reduce_transposed32(double (&v)[32], int lane) {
+#pragma unroll
+    for (int half = 16; half >= 1; half >>= 1) {
+        const bool hi = (lane & half) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = hi ? v[i] : v[i + half];
+            const double keep = hi ? v[i + half] : v[i];
+            v[i] = keep + __shfl_xor_sync(FULL, send, half);
+        }
+    }
+    return v[0];
+}
+
+// `resid(xbuf)`: optional functor returning this lane's component of (A'A) x for the x stored in shared
+// memory at xbuf[0..N), computed from the UN-squared design rows.  With nrefine > 0 the eigenvector is then
+// polished by iterative refinement, x <- x - (G+dI)^-1 (A'(A x) - rho x): the residual carries an error of
+// eps*|A|*|Ax| instead of the eps*|A|^2 of the Gram route, which matters for barely determined systems
+// (n = 7..11) where sigma_{N-1} is tiny.  nrefine is warp-uniform.
+template <int N, class Resid = NoRefine>
+__device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int lane, double* sbuf, bool* converged,
+                                                      Resid resid = Resid(), int nrefine = 0) {
     static_assert(N <= 32 && N >= 2, "one matrix row per lane");
     constexpr int NP = (N + 1) & ~1;          // row length padded to a whole number of 128-bit loads
     double diag = 0.0;
@@ -109,6 +134,27 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
         const double diff = warp_max(fabs(z - x));
         x = z;
         if (!(diff > 4.0e-15)) { ok = true; break; }
+    }
+    for (int step = 0; step < nrefine; ++step) {
+        __syncwarp();
+        if (lane < NP) sbuf[lane] = x;
+        __syncwarp();
+        const double gl = resid(sbuf) * sc;                  // (G x)_lane of the unit-trace matrix, from the rows
+        const double rho = warp_sum(x * gl);
+        const double r = (lane < N) ? gl - rho * x : 0.0;
+        __syncwarp();
+        if (lane < NP) sbuf[32 + lane] = r;
+        __syncwarp();
+        const double2* b2 = reinterpret_cast<const double2*>(sbuf + 32);
+        double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+        for (int m2 = 0; m2 < NP / 2; ++m2) {
+            const double2 rr = b2[m2];
+            if (2 * m2 < N) z0 = fma(g[2 * m2], rr.x, z0);
+            if (2 * m2 + 1 < N) z1 = fma(g[2 * m2 + 1], rr.y, z1);
+        }
+        x += z0 + z1;                                        // g holds -(G+dI)^-1
+        x *= rsqrt(warp_sum(x * x));
     }
     *converged = ok;
     return x;
