@@ -200,20 +200,18 @@ def run_gpu(args, rank, local_rank, world):
     n, B = args.n, args.trials
     cores = os.cpu_count() or 1
 
-    # 1. inputs (host, before CUDA is touched: the generator forks workers)
-    t_gen = time.perf_counter()
-    d = scene.sweep_batch(B, n, first_trial=rank * B, workers=max(1, min(32, cores // max(1, world))))
-    t_gen = time.perf_counter() - t_gen
-    CalM = d["CalM"]
-    corresp_host = np.ascontiguousarray(d["Corresp"].transpose(0, 2, 1))          # (B, n, 6) == 6 x n x B column-major
-
-    # 2. CPU baseline beside it (rank 0, N=1 only), still before CUDA initialisation
+    # 1. a host-generated sample of the step's first trials: CPU-baseline input and cross-check of the device generator
+    CalM = scene.sweep_batch(1, n)["CalM"]
+    S = 0
+    sample = None
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         S = args.cpu_sample if args.cpu_sample > 0 else min(B, 200 * cores)
+        sample = scene.sweep_batch(S, n, first_trial=rank * B, workers=max(1, min(16, cores)))
+        # 2. CPU baseline beside it (rank 0, N=1 only), before CUDA is initialised (the pool forks)
         pool = make_pool(cores)
-        cpu_solves_per_sec(d["Corresp"][: max(8, S // 10)], CalM, cores, pool)      # warm the pool
-        v, dt = cpu_solves_per_sec(d["Corresp"][:S], CalM, cores, pool)
+        cpu_solves_per_sec(sample["Corresp"][: max(8, S // 10)], CalM, cores, pool)      # warm the pool
+        v, dt = cpu_solves_per_sec(sample["Corresp"][:S], CalM, cores, pool)
         if pool is not None:
             pool.close()
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
@@ -231,8 +229,17 @@ def run_gpu(args, rank, local_rank, world):
     stream = torch.cuda.Stream(device=dev)
     h.call("tvf_set_stream", C.c_void_p(stream.cuda_stream))
 
-    # 3. device-resident inputs / outputs
-    d_corresp = torch.from_numpy(corresp_host).to(dev)
+    # 3. inputs generated on the device (tvf_generate_sweep_dev: one thread per trial), outputs preallocated
+    t_gen = time.perf_counter()
+    d_corresp = torch.empty((B, n, 6), dtype=torch.float64, device=dev)
+    scene.sweep_batch_device(B, n, first_trial=rank * B, device=local_rank, out_ptr=d_corresp.data_ptr())
+    torch.cuda.synchronize(dev)
+    t_gen = time.perf_counter() - t_gen
+    corresp_host = d_corresp.cpu().numpy()                                   # for the end-to-end (host-pointer) leg
+    gen_check = None
+    if sample is not None:
+        dd = np.abs(corresp_host[:S] - sample["Corresp"].transpose(0, 2, 1))
+        gen_check = {"trials": int(S), "max_abs_diff_vs_host_generator": float(dd.max()), "bitwise_equal_fraction": float(np.mean(dd == 0.0))}
     d_calm = torch.from_numpy(np.ascontiguousarray(CalM.T)).to(dev)
     d_Rt2 = torch.empty((B, 12), dtype=torch.float64, device=dev)
     d_Rt3 = torch.empty((B, 12), dtype=torch.float64, device=dev)
@@ -384,7 +391,7 @@ def run_gpu(args, rank, local_rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
+        "dtype": "f64", "data": "synthetic (generateSyntheticScene + experiments.m sub-sampling, generated on the device)",
         "config": {"workload": "experiments.m noise sweep (13 levels 0:0.25:3), n=%d points, %d trials per GPU "
                                "(BASELINE config 3%s)" % (n, B, "" if world == 1 else "/4 sharded"),
                    "method": "LinearTFTPoseEstimation", "n_points": n, "trials_per_gpu": B, "global_trials": B * world,
@@ -402,7 +409,7 @@ def run_gpu(args, rank, local_rank, world):
                      "unit": UNIT, "ms_per_step": ms_f / max(3, args.steps // 2),
                      "roofline_step_frac_fp64": f_flops(n) * B / (ms_f * 1e-3 / max(3, args.steps // 2)) / 1e12 / fp64_peak},
         "flagged_problems": flagged,
-        "input_generation_s": t_gen,
+        "input_generation": {"where": "device (tvf_generate_sweep_dev, TVF scene RNG v1)", "seconds": t_gen, "check": gen_check},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -128,10 +128,27 @@ int tvf_triangulate(tvf_handle_t h, const double* P, int M, int cams_batched, co
 int tvf_repr_error(tvf_handle_t h, const double* P, int M, int cams_batched, const double* corresp, int rows, int n,
                    int64_t B, const double* points3d, int pts_rows, double* err);
 
+/* Corresp = project3Dpoints(Points3D,Pcam)   auxiliar_functions/project3Dpoints.m:1,28-35.
+ * points3d 3 x n x B; P 3 x 4 x M (or x B); corresp (2M) x n x B.  Used by the real-data pre-filter
+ * (experiments_real.m:94-99). */
+int tvf_project3d(tvf_handle_t h, const double* points3d, const double* P, int M, int cams_batched, int n, int64_t B,
+                  double* corresp);
+
 /* [rot_err,t_err] = AngError(R_t_true,R_t_est)   auxiliar_functions/AngError.m:1,21-28 (degrees).
  * Rt_true 3x4 (true_batched = 0) or 3x4xB. */
 int tvf_ang_error(tvf_handle_t h, const double* Rt_true, int true_batched, const double* Rt_est, int64_t B,
                   double* rot_err, double* t_err);
+
+/* ---- inputs of the measured configurations, generated where they are consumed ------------------------
+ * Trials [first_trial, first_trial+B) of experiments.m's sweep: trial j uses noise_levels[j mod L] and
+ * seed j div L + 1; each is generateSyntheticScene(n+100, noise, seed, ...) followed by the column
+ * sub-sampling of experiments.m:94-95 (auxiliar_functions/generateSyntheticScene.m:75-111).  P: the three
+ * scaled 3x4 cameras, ROW-major (36 doubles); (hi_x, hi_y): image size in pixels.  RNG = "TVF scene RNG v1"
+ * (MT19937 genrand_res53 + NumPy's legacy polar Gaussian and shuffle); n <= 60.  corresp: 6 x n x B. */
+int tvf_generate_sweep(tvf_handle_t h, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
+                       const double* P, double hi_x, double hi_y, double* corresp);
+int tvf_generate_sweep_dev(tvf_handle_t h, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
+                           const double* P, double hi_x, double hi_y, double* d_corresp);
 
 /* ---- device-pointer forms (inputs/outputs already in HBM; asynchronous on the handle's stream,
  *      return 0 without synchronising -- read `status` after tvf_synchronize) ----------------- */

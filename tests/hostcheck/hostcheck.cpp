@@ -3,6 +3,7 @@
 // the oracle on a machine without a GPU.  Not linked into the product library,
 // never on the product path.
 #include "tvf_pose.cuh"
+#include "tvf_scene.cuh"
 
 using namespace tvf;
 
@@ -91,6 +92,23 @@ int hc_pose_tail(int mode, const double* model, const double* CalM, const double
     for (int i = 0; i < n; ++i) sq += final_point(P1, P2, P3, corresp + 6 * i, reconst + 3 * i);
     *repr = sqrt(sq / (3.0 * n));
     return st;
+}
+
+// one sweep trial on the host with the very code the device kernel runs (RNG streams exposed for checks)
+void hc_scene_trial(const double* P, int n, double noise, unsigned seed, double hi_x, double hi_y, double* out) {
+    static MT19937 rng;
+    static double c[6 * SCENE_MAX_POINTS];
+    static unsigned char arr[SCENE_MAX_POINTS];
+    static signed char outpos[SCENE_MAX_POINTS];
+    scene_trial(rng, P, n, noise, seed, hi_x, hi_y, out, c, arr, outpos);
+}
+
+void hc_mt_streams(unsigned seed, int n, double* uniform, double* normal, unsigned* ints, unsigned maxv) {
+    MT19937 r;
+    r.seed(seed);
+    for (int i = 0; i < n; ++i) uniform[i] = r.res53();
+    for (int i = 0; i < n; ++i) normal[i] = r.normal();
+    for (int i = 0; i < n; ++i) ints[i] = r.interval(maxv);
 }
 
 }  // extern "C"

@@ -302,3 +302,39 @@ def test_large_n_cluster_tma_path(tvf, n):
     # the generic warp-per-problem stage 1 gives the same tensor (n just below the threshold exercises it at similar size)
     one = tvf.LinearTFTPoseEstimation(Cs[0], CalM)
     assert np.array_equal(one[3], res[3][0])
+
+
+def test_epfl_prefilter_pipeline(tvf):
+    """f2: experiments_real.m:94-101 on the GPU for the full match list of fountain-P11 triplet (5,6,7):
+    1400 matches -> 1360 inliers at 1 px, ground-truth reprojection RMS 0.2586 px."""
+    g = _golden("epfl_full_triplet.npz")
+    CalM, R_t0 = tvf.epfl.relative_poses([(g["K"][i], g["R"][i], g["t"][i]) for i in range(3)])
+    assert np.array_equal(CalM, g["CalM"]) and np.abs(R_t0[0] - g["Rt0_2"]).max() < 1e-15
+    inl, mask, REr = tvf.epfl.inlier_filter(g["Corresp"], CalM, R_t0)
+    assert np.array_equal(mask, g["inlier_mask"]) and inl.shape == (6, 1360)           # integer indexing: exact
+    assert abs(REr - float(g["REr"])) < TOL_REPR and abs(REr - 0.2586) < 5e-5
+    K = CalM[:3]
+    Ps = [K @ np.eye(3, 4), CalM[3:6] @ R_t0[0], CalM[6:9] @ R_t0[1]]
+    X = o.triangulation3D(Ps, g["Corresp"])
+    proj = tvf.project3Dpoints(X[:3] / X[3], Ps)
+    assert np.abs(proj - o.project3Dpoints(X[:3] / X[3], Ps)).max() < 1e-9
+
+
+def test_device_scene_generator(tvf):
+    """f1: trials generated by the CUDA kernel == host generator.  Integer work (MT19937 stream, inside-image
+    mask, compaction order, sub-sample indices) and the projections are exact; the Gaussian goes through the
+    device log(), so noisy coordinates may differ in the last ulp."""
+    from tft_vs_fund_b200 import scene
+    B = 13 * 300
+    host = scene.sweep_batch(B, 20, first_trial=1300)
+    dev = scene.sweep_batch_device(B, 20, first_trial=1300)
+    assert np.array_equal(host["noise"], dev["noise"]) and np.array_equal(host["seed"], dev["seed"])
+    clean = host["noise"] == 0.0
+    assert np.array_equal(host["Corresp"][clean], dev["Corresp"][clean])          # projected points: bit-exact
+    diff = np.abs(host["Corresp"] - dev["Corresp"])
+    assert diff.max() < 1e-11                                                      # same points selected everywhere
+    assert np.mean(diff == 0.0) > 0.95
+    # downstream: the solver sees the same problems
+    a = tvf.LinearTFTPoseEstimation(host["Corresp"][:500], host["CalM"])
+    b = tvf.LinearTFTPoseEstimation(dev["Corresp"][:500], dev["CalM"])
+    assert np.max(np.abs(a.repr_err - b.repr_err)) < 1e-7

@@ -82,3 +82,30 @@ def test_pose_tail_matches_oracle(hostcheck, mode, n, noise):
         assert_pose_close((R2, R3, Rec, T, rep), got, "n=%d noise=%g seed=%d" % (n, noise, seed))
         # votes: one candidate sees every point in front of both cameras
         assert sorted(v[:4])[-1] == 2 * n and sorted(v[4:])[-1] == 2 * n
+
+
+def test_scene_generator_code_is_bit_exact_with_host_generator(hostcheck):
+    """csrc/tvf_scene.cuh (MT19937 genrand_res53, legacy polar Gaussian, legacy shuffle, fixed-order projection,
+    rejection loop, compaction, sub-sampling) compiled for the host == tft_vs_fund_b200.scene, bit for bit."""
+    from tft_vs_fund_b200 import scene
+    n = 2000
+    u = np.zeros(n); z = np.zeros(n); k = np.zeros(n, dtype=np.uint32)
+    hostcheck.hc_mt_streams(C.c_uint(987654321), n, dp(u), dp(z), k.ctypes.data_as(C.POINTER(C.c_uint)), C.c_uint(119))
+    rs = np.random.RandomState(987654321)
+    assert np.array_equal(u, rs.random_sample(n)) and np.array_equal(z, rs.standard_normal(n))
+    assert k.max() <= 119
+    K, Ps, _ = scene.scene_cameras(50, 0)
+    P = np.ascontiguousarray(np.stack(Ps))
+    d = scene.sweep_batch(13 * 12, 20)
+    for j in range(13 * 12):
+        out = np.zeros((20, 6))
+        hostcheck.hc_scene_trial(dp(P), 20, C.c_double(d["noise"][j]), C.c_uint(int(d["seed"][j])), C.c_double(1800.0),
+                                 C.c_double(1200.0), dp(out))
+        assert np.array_equal(out.T, d["Corresp"][j]), j
+    # another shape: n = 12 (experiments.m's default N), high noise -> more rejections
+    d = scene.sweep_batch(26, 12, noise_levels=[3.0, 20.0])
+    for j in range(26):
+        out = np.zeros((12, 6))
+        hostcheck.hc_scene_trial(dp(P), 12, C.c_double(d["noise"][j]), C.c_uint(int(d["seed"][j])), C.c_double(1800.0),
+                                 C.c_double(1200.0), dp(out))
+        assert np.array_equal(out.T, d["Corresp"][j]), j

@@ -45,3 +45,18 @@ def test_sweep_batch_workers_identical():
     a = scene.sweep_batch(5000, 20)
     b = scene.sweep_batch(5000, 20, workers=3)
     assert np.array_equal(a["Corresp"], b["Corresp"])
+
+
+def test_epfl_loaders_match_oracle():
+    """Product-side .camera / .mat loaders == oracle restatement (skipped where the reference data is absent)."""
+    import os
+    from conftest import REFERENCE
+    if not os.path.isdir(REFERENCE):
+        pytest.skip("reference data not present on this box")
+    from tft_vs_fund_b200 import epfl
+    path = os.path.join(REFERENCE, "Data", "Herz-Jesu-P8")
+    a = epfl.load_corresp_triplets(path); b = o.load_corresp_triplets(path)
+    assert np.array_equal(a[0], b[0]) and a[2] == b[2]
+    for name in a[2][:3]:
+        x = epfl.readCalibrationOrientation_EPFL(path, name); y = o.readCalibrationOrientation_EPFL(path, name)
+        assert all(np.array_equal(p, q) for p, q in zip(x, y))

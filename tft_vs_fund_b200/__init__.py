@@ -8,15 +8,15 @@ no CPU fallback; importing is cheap, the library is loaded on first use.
 from .api import (  # noqa: F401
     LinearTFTPoseEstimation, LinearFPoseEstimation, linearTFT, linearF,
     Normalize2Ddata, transform_TFT, R_t_from_TFT, TFT_from_P, triangulation3D,
-    ReprError, AngError, crossM, PoseResult,
+    ReprError, AngError, crossM, project3Dpoints, PoseResult,
 )
 from ._lib import TvfError, Handle, handle, load, LIB_PATH  # noqa: F401
 from .scene import generateSyntheticScene, sweep_batch, SceneRNG  # noqa: F401
-from . import experiments, sharding  # noqa: F401
+from . import experiments, sharding, epfl  # noqa: F401
 
 __all__ = [
     "LinearTFTPoseEstimation", "LinearFPoseEstimation", "linearTFT", "linearF",
     "Normalize2Ddata", "transform_TFT", "R_t_from_TFT", "TFT_from_P",
-    "triangulation3D", "ReprError", "AngError", "crossM",
+    "triangulation3D", "ReprError", "AngError", "crossM", "project3Dpoints",
     "generateSyntheticScene", "sweep_batch", "Handle", "handle", "TvfError",
 ]

@@ -232,6 +232,17 @@ def ReprError(ProjM, Corresp, Points3D=None, device=None):
     return err if batched else float(err[0])
 
 
+def project3Dpoints(Points3D, Pcam, device=None):
+    """Corresp=project3Dpoints(Points3D,Pcam) (auxiliar_functions/project3Dpoints.m:1,28-35): 3xN -> 2MxN."""
+    h = _lib.handle(device)
+    x, batched, B = _cm(Points3D, 2)
+    n = x.shape[1]
+    buf, M, cb = _cams(Pcam, B, batched)
+    out = np.empty((B, 2 * M * n))
+    h.call("tvf_project3d", _p(x), _p(buf), M, cb, n, B, _p(out))
+    return _from_cm(out, B, (2 * M, n), batched)
+
+
 def AngError(R_t_true, R_t_est, device=None):
     """[rot_err,t_err]=AngError(R_t_true,R_t_est) (auxiliar_functions/AngError.m:1,21-28), degrees."""
     h = _lib.handle(device)

@@ -702,6 +702,69 @@ int tvf_repr_error(tvf_handle_t h, const double* P, int M, int cams_batched, con
     return u.finish();
 }
 
+int tvf_project3d(tvf_handle_t h, const double* points3d, const double* P, int M, int cams_batched, int n, int64_t B,
+                  double* corresp) {
+    if (!h) return TVF_ERR_ARG;
+    if (!points3d || !P || !corresp || n < 1 || B < 0 || M < 1) return fail(h, TVF_ERR_ARG, "NULL argument or bad size");
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    const double* dx = u.in(points3d, (size_t)3 * n * B);
+    const double* dP = u.in(P, (size_t)12 * M * (cams_batched ? B : 1));
+    double* o = u.out<double>((size_t)2 * M * n * B);
+    if (u.rc) return u.rc;
+    launch_project3d(dx, dP, M, cams_batched, n, B, o, u.st); h->launches += 1;
+    u.back(corresp, o, (size_t)2 * M * n * B);
+    return u.finish();
+}
+
+static int sweep_common(tvf_handle_t h, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
+                        const double* P, double hi_x, double hi_y, double* d_out, cudaStream_t st) {
+    void* p0; void* p1;
+    int rc = ensure_scratch(h, NSCRATCH - 2, (size_t)L * sizeof(double), &p0); if (rc) return rc;
+    rc = ensure_scratch(h, NSCRATCH - 3, 36 * sizeof(double), &p1); if (rc) return rc;
+    TVF_CK(cudaMemcpyAsync(p0, noise_levels, (size_t)L * sizeof(double), cudaMemcpyHostToDevice, st));
+    TVF_CK(cudaMemcpyAsync(p1, P, 36 * sizeof(double), cudaMemcpyHostToDevice, st));
+    launch_sweep_trials(first_trial, B, n, (const double*)p0, L, (const double*)p1, hi_x, hi_y, d_out, st);
+    h->launches += 1;
+    TVF_CK(cudaGetLastError());
+    return TVF_OK;
+}
+
+static int sweep_check(tvf_handle_t h, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
+                       const double* P, const double* out) {
+    if (!h) return TVF_ERR_ARG;
+    if (!noise_levels || !P || !out || L < 1 || B < 0 || first_trial < 0) return fail(h, TVF_ERR_ARG, "NULL argument or bad size");
+    if (n < 1 || n > SWEEP_MAX_N) return fail(h, TVF_ERR_ARG, "device scene generator supports 1 <= n <= 60");
+    if ((first_trial + B) / L + 1 > 0xffffffffLL) return fail(h, TVF_ERR_ARG, "seed exceeds 32 bits");
+    return TVF_OK;
+}
+
+int tvf_generate_sweep_dev(tvf_handle_t h, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
+                           const double* P, double hi_x, double hi_y, double* d_corresp) {
+    int rc = sweep_check(h, first_trial, B, n, noise_levels, L, P, d_corresp); if (rc) return rc;
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    cudaStream_t st = h->use_user_stream ? h->user_stream : h->slot[0].stream;
+    // the two small host arrays are consumed by an async copy: make that copy complete before returning
+    rc = sweep_common(h, first_trial, B, n, noise_levels, L, P, hi_x, hi_y, d_corresp, st); if (rc) return rc;
+    TVF_CK(cudaStreamSynchronize(st));
+    return TVF_OK;
+}
+
+int tvf_generate_sweep(tvf_handle_t h, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
+                       const double* P, double hi_x, double hi_y, double* corresp) {
+    int rc = sweep_check(h, first_trial, B, n, noise_levels, L, P, corresp); if (rc) return rc;
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    Up u(h);
+    double* o = u.out<double>((size_t)6 * n * B);
+    if (u.rc) return u.rc;
+    rc = sweep_common(h, first_trial, B, n, noise_levels, L, P, hi_x, hi_y, o, u.st); if (rc) return rc;
+    u.back(corresp, o, (size_t)6 * n * B);
+    return u.finish();
+}
+
 int tvf_ang_error(tvf_handle_t h, const double* Rt_true, int true_batched, const double* Rt_est, int64_t B,
                   double* rot_err, double* t_err) {
     if (!h) return TVF_ERR_ARG;

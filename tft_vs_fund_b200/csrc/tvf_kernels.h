@@ -78,7 +78,14 @@ void launch_triangulate(const double* P, int M, int cams_batched, const double* 
                         double* X, cudaStream_t s);
 void launch_repr_error(const double* P, int M, int cams_batched, const double* corresp, int rows, int n, long long B,
                        const double* pts3d, int pts_rows, double* err, cudaStream_t s);
+void launch_project3d(const double* pts3d, const double* P, int M, int cams_batched, int n, long long B, double* out,
+                      cudaStream_t s);
 void launch_ang_error(const double* Rt_true, int true_batched, const double* Rt_est, long long B, double* rot,
                       double* tr, cudaStream_t s);
+
+// ---- synthetic sweep trials generated on the device (f1) -----------------------------------------------
+constexpr int SWEEP_MAX_N = 60;      // n + 100 points per scene must fit the per-thread scratch
+void launch_sweep_trials(long long first_trial, long long B, int n, const double* d_noise_levels, int L, const double* d_P,
+                         double hi_x, double hi_y, double* d_out, cudaStream_t stream);
 
 }  // namespace tvf

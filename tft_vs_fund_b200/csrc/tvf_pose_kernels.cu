@@ -506,6 +506,22 @@ repr_error_kernel(const double* __restrict__ P, int M, int cams_batched, const d
     }
 }
 
+// Corresp = project3Dpoints(Points3D, Pcam)   (auxiliar_functions/project3Dpoints.m:28-35)
+__global__ void project3d_kernel(const double* __restrict__ pts3d, const double* __restrict__ P, int M, int cams_batched,
+                                 int n, long long B, double* __restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * n) return;
+    const long long b = e / n;
+    const double* Pb = P + (cams_batched ? b * 12 * M : 0);
+    const double X[4] = {pts3d[e * 3], pts3d[e * 3 + 1], pts3d[e * 3 + 2], 1.0};
+    for (int v = 0; v < M; ++v) {
+        double x[3];
+        cam_apply(Pb + 12 * v, X, x);
+        out[(e * M + v) * 2] = x[0] / x[2];
+        out[(e * M + v) * 2 + 1] = x[1] / x[2];
+    }
+}
+
 __global__ void ang_error_kernel(const double* __restrict__ Rt_true, int true_batched, const double* __restrict__ Rt_est,
                                  long long B, double* __restrict__ rot, double* __restrict__ tr) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -592,6 +608,12 @@ void launch_repr_error(const double* P, int M, int cams_batched, const double* c
     const int ppb = PT_THREADS / tpp;
     repr_error_kernel<<<grid_for(B, ppb, 148LL * 32), PT_THREADS, 0, s>>>(P, M, cams_batched, corresp, rows, n, B, pts3d,
                                                                           pts_rows, err);
+}
+
+void launch_project3d(const double* pts3d, const double* P, int M, int cams_batched, int n, long long B, double* out,
+                      cudaStream_t s) {
+    if (B <= 0 || n <= 0) return;
+    project3d_kernel<<<grid_for(B * n, 128, 1LL << 30), 128, 0, s>>>(pts3d, P, M, cams_batched, n, B, out);
 }
 
 void launch_ang_error(const double* Rt_true, int true_batched, const double* Rt_est, long long B, double* rot,

@@ -188,3 +188,29 @@ def sweep_batch(B, n=20, first_trial=0, noise_levels=None, focalL=50, angle=0, w
             out = np.concatenate(pool.map(_sweep_range, jobs), axis=0)
     jj = np.arange(j0, j1)
     return dict(Corresp=out, CalM=np.tile(K, (3, 1)), R_t0=R_t0, noise=noise_levels[jj % L], seed=jj // L + 1)
+
+
+def sweep_batch_device(B, n=20, first_trial=0, noise_levels=None, focalL=50, angle=0, device=None, out_ptr=None):
+    """Same trials as sweep_batch, generated by the CUDA kernel behind tvf_generate_sweep (one thread per trial).
+    Returns the same dict (Corresp as a NumPy array) or, with `out_ptr` (a device pointer to 6*n*B doubles),
+    fills that buffer in place and returns the dict without "Corresp".  Integer work and the projections are
+    bit-exact with sweep_batch; noisy coordinates may differ in the last ulp (device log())."""
+    import ctypes as C
+    from . import _lib
+    if noise_levels is None:
+        noise_levels = np.arange(0.0, 3.0 + 1e-9, 0.25)
+    noise_levels = np.ascontiguousarray(noise_levels, dtype=np.float64)
+    L = noise_levels.size
+    K, Ps, R_t0 = scene_cameras(focalL, angle)
+    P = np.ascontiguousarray(np.stack(Ps), dtype=np.float64)            # (3,3,4) row-major
+    h = _lib.handle(device)
+    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
+    jj = np.arange(first_trial, first_trial + B)
+    d = dict(CalM=np.tile(K, (3, 1)), R_t0=R_t0, noise=noise_levels[jj % L], seed=jj // L + 1)
+    if out_ptr is not None:
+        h.call("tvf_generate_sweep_dev", first_trial, B, n, dp(noise_levels), L, dp(P), 36 * PIX, 24 * PIX, C.c_void_p(out_ptr))
+        return d
+    out = np.empty((B, n, 6))
+    h.call("tvf_generate_sweep", first_trial, B, n, dp(noise_levels), L, dp(P), 36 * PIX, 24 * PIX, dp(out))
+    d["Corresp"] = np.ascontiguousarray(out.transpose(0, 2, 1))
+    return d
