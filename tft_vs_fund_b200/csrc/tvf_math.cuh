@@ -26,6 +26,32 @@ TVF_HD double rsqrt_(double x) {
 #endif
 }
 
+// 1/x and sqrt(x) for normal positive/any-sign finite x.  Device: MUFU seed + Newton steps (full double
+// precision, not correctly rounded, no slow path) -- ~7 instructions instead of ~20 for the IEEE forms.
+// Host (test build): the exact operations.  Used where a last-ulp difference is immaterial (QR, Jacobi
+// rotations, normalisations); inv3/transform keep IEEE division.
+TVF_HD double rcp_(double x) {
+#if defined(__CUDA_ARCH__)
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+#else
+    return 1.0 / x;
+#endif
+}
+
+TVF_HD double sqrt_(double x) {        // x >= 0; sqrt(0) = 0
+#if defined(__CUDA_ARCH__)
+    const double r = rsqrt(x);
+    return (x > 0.0) ? x * r : 0.0;
+#else
+    return sqrt(x);
+#endif
+}
+
 TVF_HD double sign_(double x) {  // MATLAB sign(): sign(0)=0, sign(NaN)=NaN
     return (x > 0.0) ? 1.0 : ((x < 0.0) ? -1.0 : x);
 }
@@ -100,11 +126,11 @@ TVF_HD void jacobi_rot_(double* ap, double* aq, double* vp, double* vq, bool& ro
     const double alpha = ap[0] * ap[0] + ap[1] * ap[1] + ap[2] * ap[2];
     const double beta = aq[0] * aq[0] + aq[1] * aq[1] + aq[2] * aq[2];
     const double gamma = ap[0] * aq[0] + ap[1] * aq[1] + ap[2] * aq[2];
-    const double thr = 1.0e-15 * sqrt(alpha * beta);   // ~4.5 eps: below that a rotation only moves rounding noise
-    if (!(fabs(gamma) > thr) || fabs(gamma) < 1e-300) return;
+    // converged pair: |gamma| <= 1e-15*sqrt(alpha*beta) (~4.5 eps: below that a rotation only moves rounding noise)
+    if (!(gamma * gamma > 1.0e-30 * (alpha * beta)) || fabs(gamma) < 1e-300) return;
     rotated = true;
-    const double zeta = (beta - alpha) / (2.0 * gamma);
-    const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+    const double zeta = (beta - alpha) * rcp_(2.0 * gamma);
+    const double t = copysign(1.0, zeta) * rcp_(fabs(zeta) + sqrt_(1.0 + zeta * zeta));
     const double c = rsqrt_(1.0 + t * t);
     const double s = c * t;
 #pragma unroll
@@ -136,9 +162,9 @@ TVF_HD void jacobi_svd3(double* A, double* V, double* s, int* sweeps = nullptr) 
         if (sweeps) *sweeps = sweep + 1;
         if (!rotated) break;
     }
-    s[0] = sqrt(A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
-    s[1] = sqrt(A[3] * A[3] + A[4] * A[4] + A[5] * A[5]);
-    s[2] = sqrt(A[6] * A[6] + A[7] * A[7] + A[8] * A[8]);
+    s[0] = sqrt_(A[0] * A[0] + A[1] * A[1] + A[2] * A[2]);
+    s[1] = sqrt_(A[3] * A[3] + A[4] * A[4] + A[5] * A[5]);
+    s[2] = sqrt_(A[6] * A[6] + A[7] * A[7] + A[8] * A[8]);
     if (s[0] < s[1]) swap_cols_(A + 0, A + 3, V + 0, V + 3, s[0], s[1]);
     if (s[1] < s[2]) swap_cols_(A + 3, A + 6, V + 3, V + 6, s[1], s[2]);
     if (s[0] < s[1]) swap_cols_(A + 0, A + 3, V + 0, V + 3, s[0], s[1]);
@@ -169,7 +195,7 @@ TVF_HD void svd3_full(const double* M, double* U, double* s, double* V) {
 #pragma unroll
     for (int i = 0; i < 9; ++i) A[i] = M[i];
     jacobi_svd3(A, V, s);
-    const double i0 = 1.0 / s[0], i1 = 1.0 / s[1];
+    const double i0 = rcp_(s[0]), i1 = rcp_(s[1]);
 #pragma unroll
     for (int i = 0; i < 3; ++i) { U[i] = A[i] * i0; U[3 + i] = A[3 + i] * i1; }
     cross3(U, U + 3, U + 6);
@@ -286,11 +312,11 @@ TVF_HD void dlt_null(double (&a)[M][4], double* x, int* iters = nullptr) {
         double sig = 0.0;
 #pragma unroll
         for (int i = k; i < M; ++i) sig += a[i][k] * a[i][k];
-        const double nrm = sqrt(sig);
+        const double nrm = sqrt_(sig);
         const double x1 = a[k][k];
         const double alpha = -copysign(nrm, x1);
         const double den = sig - alpha * x1;          // = v'v / 2 >= 0
-        const double f = (den > 0.0) ? 1.0 / den : 0.0;
+        const double f = (den > 0.0) ? rcp_(den) : 0.0;
         const double vk = x1 - alpha;
 #pragma unroll
         for (int c = k + 1; c < 4; ++c) {
@@ -313,7 +339,7 @@ TVF_HD void dlt_null(double (&a)[M][4], double* x, int* iters = nullptr) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const double p = (fabs(r[k][k]) < tiny) ? copysign(tiny, r[k][k]) : r[k][k];
-        d[k] = 1.0 / p;
+        d[k] = rcp_(p);
     }
     // start vector: R x = e4
     double x0, x1, x2, x3;

@@ -140,7 +140,9 @@ TVF_HD void cheirality_point(const double* ra, const double* rb, const double* c
         dlt_rows(P, x2, y2, a[2], a[3]);
         double X[4];
         dlt_null<4>(a, X);
-        const double X0 = X[0] / X[3], X1 = X[1] / X[3], X2 = X[2] / X[3], X3 = X[3] / X[3];  // X1./X1(4)
+        // X1./X1(4): one reciprocal, same inf/NaN outcomes as the division (x*inf = +-inf, 0*inf = NaN)
+        const double iw = (X[3] != 0.0) ? rcp_(X[3]) : 1.0 / X[3];
+        const double X0 = X[0] * iw, X1 = X[1] * iw, X2 = X[2] * iw, X3 = X[3] * iw;
         const double z2 = r3[0] * X0 + r3[1] * X1 + r3[2] * X2 + tz * X3;                      // [R t]*X1
         if (X2 != X2 || z2 != z2) {
             *nanmask |= (1 << q);
@@ -186,7 +188,8 @@ TVF_HD void scale_point(const double* P1, const double* P2, const double* KR3, c
                         const double* p6, double* num, double* den) {
     double X[4];
     triangulate2(P1, P2, p6[0], p6[1], p6[2], p6[3], X);
-    const double Xc[3] = {X[0] / X[3], X[1] / X[3], X[2] / X[3]};
+    const double iw = 1.0 / X[3];
+    const double Xc[3] = {X[0] * iw, X[1] * iw, X[2] * iw};
     double X3[3];
     mat3_vec(KR3, Xc, X3);
     const double p3[3] = {p6[4], p6[5], 1.0};
@@ -202,7 +205,8 @@ TVF_HD void scale_point(const double* P1, const double* P2, const double* KR3, c
 TVF_HD double final_point(const double* P1, const double* P2, const double* P3, const double* p6, double* Xout) {
     double X[4];
     triangulate3(P1, P2, P3, p6, X);
-    const double Xe[4] = {X[0] / X[3], X[1] / X[3], X[2] / X[3], 1.0};
+    const double iw = 1.0 / X[3];
+    const double Xe[4] = {X[0] * iw, X[1] * iw, X[2] * iw, 1.0};
     Xout[0] = Xe[0]; Xout[1] = Xe[1]; Xout[2] = Xe[2];
     double sq = 0.0;
     const double* Ps[3] = {P1, P2, P3};
@@ -210,7 +214,8 @@ TVF_HD double final_point(const double* P1, const double* P2, const double* P3, 
     for (int v = 0; v < 3; ++v) {
         double x[3];
         cam_apply(Ps[v], Xe, x);
-        const double dx = x[0] / x[2] - p6[2 * v], dy = x[1] / x[2] - p6[2 * v + 1];
+        const double iz = 1.0 / x[2];
+        const double dx = x[0] * iz - p6[2 * v], dy = x[1] * iz - p6[2 * v + 1];
         sq += dx * dx + dy * dy;
     }
     return sq;

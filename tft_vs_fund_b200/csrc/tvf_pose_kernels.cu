@@ -287,7 +287,8 @@ pose_tail_fused_kernel(PoseTailArgs a) {
             // X of the selected pair-2 candidate: (R,t)->Xa, (R,-t)->(Xa, -w), (Rp,-t)->(Xb, -w), (Rp,t)->Xb
             const bool useA = (k2 == 0 || k2 == 1 || k2 == 15);
             const double w = ((k2 == 1 || k2 == 2) ? -1.0 : 1.0) * (useA ? Xa[3] : Xb[3]);
-            const double Xc[3] = {(useA ? Xa[0] : Xb[0]) / w, (useA ? Xa[1] : Xb[1]) / w, (useA ? Xa[2] : Xb[2]) / w};
+            const double iw = 1.0 / w;
+            const double Xc[3] = {(useA ? Xa[0] : Xb[0]) * iw, (useA ? Xa[1] : Xb[1]) * iw, (useA ? Xa[2] : Xb[2]) * iw};
             double X3[3], c1[3], c2[3];
             mat3_vec(Ps + 24, Xc, X3);
             const double p3[3] = {p6[4], p6[5], 1.0};
