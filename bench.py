@@ -153,6 +153,21 @@ class ClockSampler:
         return out
 
 
+def ncu_counters():
+    """Per-kernel hardware counters of the latest committed ncu capture (profiles/*_counters.json, written by
+    tools/ncu_summary.py from a separate profiled run of this same bench command)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_counters.json")))
+    for f in reversed(files):
+        try:
+            d = json.load(open(f))
+            d["file"] = os.path.relpath(f, ROOT)
+            return d
+        except Exception:
+            continue
+    return None
+
+
 def measured_peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -351,6 +366,27 @@ def run_gpu(args, rank, local_rank, world):
     for p in (p0, p1, p2, p3, p4, p5, p6):
         lib.tvf_host_free(C.c_void_p(p))
 
+    # 5b. the whole inner loop of experiments.m device-resident (generate + solve + per-level reduction; only a
+    #     13 x 5 table crosses the bus): tvf_sweep_run
+    K_, Ps_, Rt0_ = scene.scene_cameras(50, 0)
+    lv = np.ascontiguousarray(np.arange(0.0, 3.0 + 1e-9, 0.25)); Pm = np.ascontiguousarray(np.stack(Ps_))
+    g2 = np.ascontiguousarray(Rt0_[0].T); g3 = np.ascontiguousarray(Rt0_[1].T); table = np.zeros((lv.size, 5))
+
+    def step_sweep():
+        h.call("tvf_sweep_run", 1, rank * B, B, n, dp(lv), lv.size, dp(Pm), 1800.0, 1200.0, dp(h_calm), dp(g2), dp(g3), dp(table))
+
+    step_sweep()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(3):
+        step_sweep()
+    dt_sweep = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt_sweep], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt_sweep = float(t.item())
+    sweep_value = world * B * 3 / dt_sweep
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -374,8 +410,20 @@ def run_gpu(args, rank, local_rank, world):
     fp64_src = "measured on this device by tvf_fp64_peak_tflops (register-resident DFMA loop)"
     if not (fp64_peak and fp64_peak > 1.0):
         fp64_peak, fp64_src = 37.2, "nominal 148 SM x 64 FMA/clk x 1.965 GHz"
+    ncu = ncu_counters()
+    traffic = None
+    if ncu and dom in ncu["kernels"] and ncu["kernels"][dom].get("dram_bytes_per_launch"):
+        traffic = ncu["kernels"][dom]["dram_bytes_per_launch"] * units_per_launch / ncu["problems_per_launch"]
+        for name, c in ncu["kernels"].items():
+            if name in per_kernel:
+                per_kernel[name]["ncu"] = {"fp64_pipe_active_pct": c["fp64_pipe_active_pct"], "issue_active_pct": c["issue_active_pct"],
+                                           "dram_bytes_per_problem": c["dram_bytes_per_launch"] / ncu["problems_per_launch"],
+                                           "warp_instr_per_problem": c["warp_instructions"] / ncu["problems_per_launch"],
+                                           "registers": c["registers"], "from": ncu["file"]}
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp64_peak, "traffic": None,
+                "frac": achieved_tf / fp64_peak, "traffic": traffic,
+                "traffic_note": "dram__bytes_read+write of this kernel from the committed ncu --set full capture, scaled to this launch size",
+                "fp64_pipe_active_pct_ncu": (ncu["kernels"][dom]["fp64_pipe_active_pct"] if ncu and dom in ncu["kernels"] else None),
                 "peak_source": fp64_src,
                 "work_model": "reference-operation FLOP count of SURVEY.md App. B.1 attributed to this kernel "
                               "(%d flop/solve at n=%d) x %.0f solves per launch" % (kf[dom], n, units_per_launch)}
@@ -408,6 +456,9 @@ def run_gpu(args, rank, local_rank, world):
         "f_method": {"metric": "3-view linear F pose solves/sec (LinearFPoseEstimation + ReprError)", "value": f_value,
                      "unit": UNIT, "ms_per_step": ms_f / max(3, args.steps // 2),
                      "roofline_step_frac_fp64": f_flops(n) * B / (ms_f * 1e-3 / max(3, args.steps // 2)) / 1e12 / fp64_peak},
+        "device_resident_sweep": {"api": "tvf_sweep_run: trials generated, solved and reduced per noise level on the device",
+                                  "value": sweep_value, "unit": UNIT, "d2h_bytes_per_step": int(table.nbytes),
+                                  "mean_repr_err_px_by_level": (table[:, 0] / np.maximum(table[:, 3], 1)).round(4).tolist()},
         "flagged_problems": flagged,
         "input_generation": {"where": "device (tvf_generate_sweep_dev, TVF scene RNG v1)", "seconds": t_gen, "check": gen_check},
     }

@@ -150,6 +150,16 @@ int tvf_generate_sweep(tvf_handle_t h, int64_t first_trial, int64_t B, int n, co
 int tvf_generate_sweep_dev(tvf_handle_t h, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
                            const double* P, double hi_x, double hi_y, double* d_corresp);
 
+/* The inner loops of experiments.m:74-124 for one method (1 = LinearTFTPoseEstimation, 7 =
+ * LinearFPoseEstimation), entirely device-resident: trials [first_trial, first_trial+B) are generated
+ * (as tvf_generate_sweep), solved, and their ReprError / AngError (auxiliar_functions/AngError.m, mean of the
+ * two views as in :117-120) summed per noise level in a fixed order.  table: L x 5 row-major =
+ * [sum repr_err, sum rot_err, sum t_err, trials counted, trials skipped (no pose / non-finite)].
+ * calm 9x3; Rt0_2, Rt0_3: ground-truth 3x4 poses (column-major). */
+int tvf_sweep_run(tvf_handle_t h, int method, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
+                  const double* P, double hi_x, double hi_y, const double* calm, const double* Rt0_2, const double* Rt0_3,
+                  double* table);
+
 /* ---- device-pointer forms (inputs/outputs already in HBM; asynchronous on the handle's stream,
  *      return 0 without synchronising -- read `status` after tvf_synchronize) ----------------- */
 int tvf_linear_tft_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,

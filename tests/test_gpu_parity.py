@@ -338,3 +338,16 @@ def test_device_scene_generator(tvf):
     a = tvf.LinearTFTPoseEstimation(host["Corresp"][:500], host["CalM"])
     b = tvf.LinearTFTPoseEstimation(dev["Corresp"][:500], dev["CalM"])
     assert np.max(np.abs(a.repr_err - b.repr_err)) < 1e-7
+
+
+def test_device_resident_sweep_equals_host_driven_sweep(tvf):
+    """f3: tvf_sweep_run (generate + solve + per-level reduction on the device) == run_sweep (host-generated
+    inputs, results copied back, NumPy reduction)."""
+    from tft_vs_fund_b200 import experiments
+    host = experiments.run_sweep(13 * 40, 20, methods=(1, 7))
+    dev = experiments.run_sweep_device(13 * 40, 20, methods=(1, 7))
+    for m in (1, 7):
+        assert np.max(np.abs(host[m][:, 0] - dev[m][:, 0])) < 1e-7          # px (inputs agree to ~1e-13 px)
+        assert np.max(np.abs(host[m][:, 1:] - dev[m][:, 1:])) < 1e-5        # degrees
+    again = experiments.run_sweep_device(13 * 40, 20, methods=(1,))
+    assert np.array_equal(again[1], dev[1])                                  # fixed-order reduction: bit-stable

@@ -765,6 +765,48 @@ int tvf_generate_sweep(tvf_handle_t h, int64_t first_trial, int64_t B, int n, co
     return u.finish();
 }
 
+// experiments.m:74-124 for one method, device-resident: generate the trials of the sweep, solve them, and
+// reduce ReprError / AngError per noise level.  Only the L x 5 table crosses the bus.
+int tvf_sweep_run(tvf_handle_t h, int method, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
+                  const double* P, double hi_x, double hi_y, const double* calm, const double* Rt0_2, const double* Rt0_3,
+                  double* table) {
+    int rc = sweep_check(h, first_trial, B, n, noise_levels, L, P, table); if (rc) return rc;
+    if (!calm || !Rt0_2 || !Rt0_3 || (method != 1 && method != 7)) return fail(h, TVF_ERR_ARG, "method must be 1 (TFT) or 7 (F); calm/Rt0 required");
+    if (method == 7 && n < 8) return fail(h, TVF_ERR_TOO_FEW_POINTS, TVF_LINEARF_ERRMSG);
+    TVF_CK(cudaSetDevice(h->device));
+    Slot& s = h->slot[0];
+    cudaStream_t st = s.stream;
+    const int Q = 512;
+    const int64_t C = pick_chunk(h, n, B > 0 ? B : 1, true);
+    const size_t need = carve(nullptr, n, C, true, false, nullptr);
+    rc = ensure_arena(h, s, need); if (rc) return rc;
+    ChunkBufs b; carve(s.arena, n, C, true, false, &b);
+    void *pc, *pr, *pp, *pt;
+    rc = ensure_scratch(h, 0, 27 * sizeof(double), &pc); if (rc) return rc;
+    rc = ensure_scratch(h, NSCRATCH - 4, 24 * sizeof(double), &pr); if (rc) return rc;
+    rc = ensure_scratch(h, NSCRATCH - 5, (size_t)L * Q * 5 * sizeof(double), &pp); if (rc) return rc;
+    rc = ensure_scratch(h, NSCRATCH - 6, (size_t)L * 5 * sizeof(double), &pt); if (rc) return rc;
+    TVF_CK(cudaMemcpyAsync(pc, calm, 27 * sizeof(double), cudaMemcpyHostToDevice, st));
+    TVF_CK(cudaMemcpyAsync(pr, Rt0_2, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    TVF_CK(cudaMemcpyAsync((double*)pr + 12, Rt0_3, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
+    TVF_CK(cudaMemsetAsync(pp, 0, (size_t)L * Q * 5 * sizeof(double), st));
+    for (int64_t done = 0; done < B; done += C) {
+        const int64_t Bc = (B - done < C) ? (B - done) : C;
+        rc = sweep_common(h, first_trial + done, Bc, n, noise_levels, L, P, hi_x, hi_y, b.in, st); if (rc) return rc;
+        rc = run_pose_chunk(h, st, method == 1 ? METHOD_TFT : METHOD_F, b.in, (const double*)pc, 0, n, Bc, b.T, b.F, b.core, b.cand,
+                            b.votes, b.scale, b.Rt2, b.Rt3, b.reconst, b.repr, b.status);
+        if (rc) return rc;
+        launch_sweep_eval_accumulate(b.Rt2, b.Rt3, b.repr, b.status, first_trial + done, Bc, L, Q, (const double*)pr, (double*)pp, st);
+        h->launches += 1;
+    }
+    launch_sweep_eval_finish((const double*)pp, L, Q, (double*)pt, st);
+    h->launches += 1;
+    TVF_CK(cudaGetLastError());
+    TVF_CK(cudaMemcpyAsync(table, pt, (size_t)L * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TVF_CK(cudaStreamSynchronize(st));
+    return TVF_OK;
+}
+
 int tvf_ang_error(tvf_handle_t h, const double* Rt_true, int true_batched, const double* Rt_est, int64_t B,
                   double* rot_err, double* t_err) {
     if (!h) return TVF_ERR_ARG;

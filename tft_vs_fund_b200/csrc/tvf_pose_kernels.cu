@@ -535,6 +535,56 @@ __global__ void ang_error_kernel(const double* __restrict__ Rt_true, int true_ba
     rot[b] = r; tr[b] = t;
 }
 
+// ------------------------------------------------------- sweep evaluation (experiments.m:112-124)
+// Per-trial ReprError / AngError accumulated per noise level.  Thread g owns level g % L and a fixed,
+// strided subset of that level's trials, so its four partial sums are updated by one thread in a fixed
+// order (chunk after chunk); sweep_eval_finish adds the per-thread partials in index order.  Bit-stable.
+__global__ void __launch_bounds__(256)
+sweep_eval_accumulate_kernel(const double* __restrict__ Rt2, const double* __restrict__ Rt3, const double* __restrict__ repr,
+                             const int* __restrict__ status, long long first_trial, long long B, int L, int Q,
+                             const double* __restrict__ Rt0, double* __restrict__ partial) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= L * Q) return;
+    const int level = g % L, q = g / L;
+    const int r = (int)(((level - first_trial % L) % L + L) % L);
+    double gt2[12], gt3[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { gt2[i] = Rt0[i]; gt3[i] = Rt0[12 + i]; }
+    double s_rep = 0.0, s_rot = 0.0, s_t = 0.0, cnt = 0.0, bad = 0.0;
+    for (long long b = r + (long long)L * q; b < B; b += (long long)L * Q) {
+        if (status != nullptr && (status[b] & (ST_NO_POSE_2 | ST_NO_POSE_3 | ST_NONFINITE))) { bad += 1.0; continue; }
+        double e2[12], e3[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { e2[i] = Rt2[b * 12 + i]; e3[i] = Rt3[b * 12 + i]; }
+        double r2, t2, r3, t3;
+        ang_error(gt2, e2, &r2, &t2);                                   // experiments.m:117-118
+        ang_error(gt3, e3, &r3, &t3);
+        s_rep += repr[b]; s_rot += (r2 + r3) * 0.5; s_t += (t2 + t3) * 0.5; cnt += 1.0;   // :112-120
+    }
+    double* p = partial + (size_t)g * 5;
+    p[0] += s_rep; p[1] += s_rot; p[2] += s_t; p[3] += cnt; p[4] += bad;
+}
+
+__global__ void sweep_eval_finish_kernel(const double* __restrict__ partial, int L, int Q, double* __restrict__ table) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= L * 5) return;
+    const int level = e / 5, c = e % 5;
+    double a = 0.0;
+    for (int q = 0; q < Q; ++q) a += partial[((size_t)q * L + level) * 5 + c];
+    table[e] = a;
+}
+
+void launch_sweep_eval_accumulate(const double* Rt2, const double* Rt3, const double* repr, const int* status,
+                                  long long first_trial, long long B, int L, int Q, const double* d_Rt0, double* d_partial,
+                                  cudaStream_t s) {
+    if (B <= 0) return;
+    sweep_eval_accumulate_kernel<<<(L * Q + 255) / 256, 256, 0, s>>>(Rt2, Rt3, repr, status, first_trial, B, L, Q, d_Rt0, d_partial);
+}
+
+void launch_sweep_eval_finish(const double* d_partial, int L, int Q, double* d_table, cudaStream_t s) {
+    sweep_eval_finish_kernel<<<(L * 5 + 63) / 64, 64, 0, s>>>(d_partial, L, Q, d_table);
+}
+
 // ------------------------------------------------------------------- launchers
 static inline unsigned grid_for(long long work, int per_block, long long cap) {
     long long g = (work + per_block - 1) / per_block;

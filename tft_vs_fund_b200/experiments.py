@@ -52,3 +52,28 @@ def run_sweep(total_trials, n=20, methods=(1, 7), noise_levels=NOISE_LEVELS, foc
         if total is not None:
             out[m] = total[:, :3] / total[:, 3:4]
     return out if rank == 0 else None
+
+
+def run_sweep_device(total_trials, n=20, methods=(1, 7), noise_levels=NOISE_LEVELS, focalL=50, angle=0, device=None):
+    """run_sweep with everything on the device (tvf_sweep_run): trials are generated, solved and reduced per
+    noise level in HBM; each rank moves one L x 5 table.  Per-rank sums are added in rank order on rank 0."""
+    from . import _lib
+    rank, size = sharding.world()
+    lo, hi = sharding.shard_range(total_trials, rank, size)
+    noise_levels = np.ascontiguousarray(noise_levels, dtype=np.float64)
+    L = noise_levels.size
+    K, Ps, R_t0 = scene.scene_cameras(focalL, angle)
+    P = np.ascontiguousarray(np.stack(Ps), dtype=np.float64)
+    calm = np.ascontiguousarray(np.tile(K, (3, 1)).T)
+    g2 = np.ascontiguousarray(R_t0[0].T); g3 = np.ascontiguousarray(R_t0[1].T)
+    h = _lib.handle(device)
+    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
+    out = {}
+    for m in methods:
+        table = np.zeros((L, 5))
+        h.call("tvf_sweep_run", int(m), lo, hi - lo, n, dp(noise_levels), L, dp(P), 36 * scene.PIX, 24 * scene.PIX,
+               dp(calm), dp(g2), dp(g3), dp(table))
+        total = sharding.sum_in_rank_order(table)
+        if total is not None:
+            out[m] = total[:, :3] / total[:, 3:4]
+    return out if rank == 0 else None

@@ -78,11 +78,42 @@ def kernels(rep, out):
             f.write("\n")
 
 
+def counters_json(rep, out, problems_per_launch):
+    """Machine-readable per-kernel counters (first captured launch of each kernel) for bench.py's `traffic`."""
+    import json
+    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    H, U = rows[0], rows[1]
+    ix = {h: i for i, h in enumerate(H)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+    def num(r, name):
+        return float(r[ix[name]].replace(",", "")) if name in ix and r[ix[name]] not in ("", "n/a") else None
+
+    out_d = {"source": rep, "problems_per_launch": problems_per_launch, "kernels": {}}
+    for r in rows[2:]:
+        name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
+        if name in out_d["kernels"]:
+            continue
+        rd = num(r, "dram__bytes_read.sum"); wr = num(r, "dram__bytes_write.sum")
+        out_d["kernels"][name] = {
+            "dram_bytes_per_launch": (rd * scale.get(U[ix["dram__bytes_read.sum"]], 1.0) + wr * scale.get(U[ix["dram__bytes_write.sum"]], 1.0)) if rd is not None else None,
+            "duration_us": num(r, "gpu__time_duration.sum"),
+            "fp64_pipe_active_pct": num(r, "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+            "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "warp_instructions": num(r, "smsp__inst_executed.sum"),
+            "registers": num(r, "launch__registers_per_thread"),
+        }
+    json.dump(out_d, open(out, "w"), indent=1)
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--launches"); ap.add_argument("--rep"); ap.add_argument("--out", required=True)
+    ap.add_argument("--problems-per-launch", type=int, default=65536)
     a = ap.parse_args()
     if a.launches:
         launches(a.launches, a.out + "_launches.md")
     if a.rep:
         kernels(a.rep, a.out + "_kernels.md")
+        counters_json(a.rep, a.out + "_counters.json", a.problems_per_launch)
