@@ -103,8 +103,26 @@ def epfl(ntrip=6):
     np.savez_compressed(os.path.join(HERE, "epfl_triplets.npz"), **pack(cases))
 
 
+def large_n(n=10000, seeds=(1, 2)):
+    """BASELINE config 5 shape: n = 10 000 correspondences per scene, 1 px noise.  The oracle needs ~90 s per
+    scene, so its outputs are stored; the inputs are regenerated from the seed by the test (the first points are
+    stored as a generator check) and Reconst is stored for every 50th point only."""
+    d = {k: [] for k in ("seed", "Corresp_head", "CalM", "Rt2", "Rt3", "T", "repr", "Reconst_sub")}
+    for seed in seeds:
+        CalM, R_t0, C, _ = o.generateSyntheticScene(n, 1.0, seed, 50, 0)
+        K = CalM[:3]
+        R2, R3, Rec, T, _ = o.LinearTFTPoseEstimation(C, CalM)
+        rep = o.ReprError([K @ np.eye(3, 4), K @ R2, K @ R3], C, Rec)
+        for k, v in (("seed", seed), ("Corresp_head", C[:, :8]), ("CalM", CalM), ("Rt2", R2), ("Rt3", R3), ("T", T),
+                     ("repr", rep), ("Reconst_sub", Rec[:, ::50])):
+            d[k].append(np.asarray(v))
+    np.savez_compressed(os.path.join(HERE, "large_n10000.npz"), **{k: np.stack(v) for k, v in d.items()})
+
+
 if __name__ == "__main__":
-    sweep(); example()
+    if len(sys.argv) > 1 and sys.argv[1] == "large":
+        large_n(); sys.exit(0)
+    sweep(); example(); large_n()
     if os.path.isdir(REFERENCE):
         epfl()
     print("golden vectors written to", HERE)

@@ -304,6 +304,24 @@ def test_large_n_cluster_tma_path(tvf, n):
     assert np.array_equal(one[3], res[3][0])
 
 
+def test_large_n_config5_golden(tvf):
+    """BASELINE config 5 shape (n = 10 000): CUDA path vs the oracle outputs stored in tests/golden/large_n10000.npz
+    (the oracle needs ~90 s per scene at this size; inputs are regenerated from the seed)."""
+    g = _golden("large_n10000.npz")
+    Cs = []
+    for k, seed in enumerate(g["seed"]):
+        CalM, _, C, _ = o.generateSyntheticScene(10000, 1.0, int(seed), 50, 0)
+        assert np.array_equal(C[:, :8], g["Corresp_head"][k]) and np.array_equal(CalM, g["CalM"][k])
+        Cs.append(C)
+    Cs = np.stack(Cs)
+    res = tvf.LinearTFTPoseEstimation(Cs, CalM)
+    assert np.all(res.status == 0)
+    for k in range(len(Cs)):
+        ref = (g["Rt2"][k], g["Rt3"][k], g["Reconst_sub"][k], g["T"][k], float(g["repr"][k]))
+        got = (res[0][k], res[1][k], res[2][k][:, ::50], res[3][k], res.repr_err[k])
+        assert_pose_close(ref, got, "large n=10000 seed %d" % int(g["seed"][k]))
+
+
 def test_epfl_prefilter_pipeline(tvf):
     """f2: experiments_real.m:94-101 on the GPU for the full match list of fountain-P11 triplet (5,6,7):
     1400 matches -> 1360 inliers at 1 px, ground-truth reprojection RMS 0.2586 px."""
