@@ -154,18 +154,20 @@ class ClockSampler:
 
 
 def ncu_counters():
-    """Per-kernel hardware counters of the latest committed ncu capture (profiles/*_counters.json, written by
-    tools/ncu_summary.py from a separate profiled run of this same bench command)."""
+    """Per-kernel hardware counters of the committed ncu captures (profiles/*_counters.json, written by
+    tools/ncu_summary.py from separate profiled runs of this same bench command): kernel name ->
+    counters + the number of problems its captured launch processed."""
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_counters.json")))
-    for f in reversed(files):
+    out = {}
+    for f in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_counters.json"))):
         try:
             d = json.load(open(f))
-            d["file"] = os.path.relpath(f, ROOT)
-            return d
         except Exception:
             continue
-    return None
+        for name, c in d.get("kernels", {}).items():
+            c = dict(c); c["problems_per_launch"] = d["problems_per_launch"]; c["file"] = os.path.relpath(f, ROOT)
+            out[name] = c
+    return out
 
 
 def measured_peaks():
@@ -412,18 +414,18 @@ def run_gpu(args, rank, local_rank, world):
         fp64_peak, fp64_src = 37.2, "nominal 148 SM x 64 FMA/clk x 1.965 GHz"
     ncu = ncu_counters()
     traffic = None
-    if ncu and dom in ncu["kernels"] and ncu["kernels"][dom].get("dram_bytes_per_launch"):
-        traffic = ncu["kernels"][dom]["dram_bytes_per_launch"] * units_per_launch / ncu["problems_per_launch"]
-        for name, c in ncu["kernels"].items():
-            if name in per_kernel:
-                per_kernel[name]["ncu"] = {"fp64_pipe_active_pct": c["fp64_pipe_active_pct"], "issue_active_pct": c["issue_active_pct"],
-                                           "dram_bytes_per_problem": c["dram_bytes_per_launch"] / ncu["problems_per_launch"],
-                                           "warp_instr_per_problem": c["warp_instructions"] / ncu["problems_per_launch"],
-                                           "registers": c["registers"], "from": ncu["file"]}
+    if dom in ncu and ncu[dom].get("dram_bytes_per_launch"):
+        traffic = ncu[dom]["dram_bytes_per_launch"] * units_per_launch / ncu[dom]["problems_per_launch"]
+    for name, c in ncu.items():
+        if name in per_kernel and c.get("dram_bytes_per_launch") is not None:
+            per_kernel[name]["ncu"] = {"fp64_pipe_active_pct": c["fp64_pipe_active_pct"], "issue_active_pct": c["issue_active_pct"],
+                                       "dram_bytes_per_problem": c["dram_bytes_per_launch"] / c["problems_per_launch"],
+                                       "warp_instr_per_problem": c["warp_instructions"] / c["problems_per_launch"],
+                                       "registers": c["registers"], "from": c["file"]}
     roofline = {"bound": "fp64", "kernel": dom, "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
                 "frac": achieved_tf / fp64_peak, "traffic": traffic,
                 "traffic_note": "dram__bytes_read+write of this kernel from the committed ncu --set full capture, scaled to this launch size",
-                "fp64_pipe_active_pct_ncu": (ncu["kernels"][dom]["fp64_pipe_active_pct"] if ncu and dom in ncu["kernels"] else None),
+                "fp64_pipe_active_pct_ncu": (ncu[dom]["fp64_pipe_active_pct"] if dom in ncu else None),
                 "peak_source": fp64_src,
                 "work_model": "reference-operation FLOP count of SURVEY.md App. B.1 attributed to this kernel "
                               "(%d flop/solve at n=%d) x %.0f solves per launch" % (kf[dom], n, units_per_launch)}
@@ -530,6 +532,9 @@ def run_large_n(args, local_rank):
     gram_s = gram_ms * 1e-3 / max(1, gram_n)                       # one launch = all B scenes of the step (or a chunk)
     scenes_per_launch = B * steps / max(1, gram_n)
     gram_bytes = (48 * n + 216) * scenes_per_launch
+    c5 = ncu_counters().get("tft_moments_large_kernel")
+    gram_traffic = (c5["dram_bytes_per_launch"] * scenes_per_launch / c5["problems_per_launch"]
+                    if c5 and c5.get("dram_bytes_per_launch") and n == 10000 else None)
     line = {
         "metric": "large-n linearTFT Gram formation (normalisation + 96 moments), scenes/s", "unit": "scenes/s",
         "value": scenes_per_launch / gram_s, "n_gpus": 1, "steps": steps, "warmup": max(1, args.warmup),
@@ -538,7 +543,9 @@ def run_large_n(args, local_rank):
         "config": {"workload": "large-n triplets: %d correspondences per scene x %d scenes (BASELINE config 5)" % (n, B),
                    "n_points": n, "scenes": B, "cache": "%.1f GB of input per step, far beyond L2" % (B * n * 48 / 1e9)},
         "roofline": {"bound": "hbm", "kernel": "tft_moments_large_kernel", "achieved": gram_bytes / gram_s / 1e9,
-                     "peak": hbm_peak, "unit": "GB/s", "frac": gram_bytes / gram_s / 1e9 / hbm_peak, "traffic": None,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": gram_bytes / gram_s / 1e9 / hbm_peak, "traffic": gram_traffic,
+                     "traffic_note": "dram__bytes_read+write of this kernel from the committed ncu --set full capture (n = 10000), scaled to this launch size",
+                     "fp64_pipe_active_pct_ncu": (c5["fp64_pipe_active_pct"] if c5 else None),
                      "work_model": "48*n+216 algorithmic bytes per scene (SURVEY.md 8d)"},
         "roofline_fp64": {"bound": "fp64", "achieved": 624.0 * n * scenes_per_launch / gram_s / 1e12, "peak": fp64_peak,
                           "unit": "TFLOP/s", "frac": 624.0 * n * scenes_per_launch / gram_s / 1e12 / fp64_peak,
