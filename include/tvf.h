@@ -88,6 +88,22 @@ int tvf_linear_f_pose(tvf_handle_t h, const double* corresp, const double* calm,
                       int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
                       double* F21, double* F31, int32_t* status);
 
+/* [R_t_2,R_t_3,Reconst,T,iter] = OptimFPoseEstimation(Corresp,CalM)
+ * F_methods/OptimFPoseEstimation.m:1,43-72: both fundamental matrices refined by optimF (Gauss-Helmert
+ * minimisation of the reprojection error, Optimization/Gauss_Helmert.m:38-83), then the pose tail of the F method.
+ * Same arguments as tvf_linear_f_pose plus iter (B, may be NULL) = it1 + it2 of :49.  F21, F31: the refined
+ * matrices of :47-48.  n < 8 -> TVF_ERR_TOO_FEW_POINTS; n > tvf_optim_f_max_n() -> TVF_ERR_ARG (the reference
+ * itself forms dense 4N x 4N matrices there). */
+int tvf_optim_f_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,
+                     int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
+                     double* F21, double* F31, int32_t* iter, int32_t* status);
+int tvf_optim_f_max_n(void);
+
+/* [F,iter] = optimF(p1,p2)   F_methods/optimF.m:1,34-78.  p1,p2 rows x n x B (rows = 2 or 3); F 3x3xB;
+ * iter B (may be NULL).  n < 8 -> TVF_ERR_TOO_FEW_POINTS. */
+int tvf_optim_f(tvf_handle_t h, const double* p1, const double* p2, int rows, int n, int64_t B, double* F,
+                int32_t* iter, int32_t* status);
+
 /* [T,P1,P2,P3] = linearTFT(p1,p2,p3)   TFT_methods/linearTFT.m:1,36-91.
  * p1,p2,p3: rows x n x B with rows = 2, or 3 for homogeneous points (:39-43).
  * T 3x3x3xB; P2,P3 3x4xB (may be NULL); P1 is eye(3,4) (:88) and is left to the caller. */
@@ -143,8 +159,9 @@ int tvf_ang_error(tvf_handle_t h, const double* Rt_true, int true_batched, const
  * Trials [first_trial, first_trial+B) of experiments.m's sweep: trial j uses noise_levels[j mod L] and
  * seed j div L + 1; each is generateSyntheticScene(n+100, noise, seed, ...) followed by the column
  * sub-sampling of experiments.m:94-95 (auxiliar_functions/generateSyntheticScene.m:75-111).  P: the three
- * scaled 3x4 cameras, ROW-major (36 doubles); (hi_x, hi_y): image size in pixels.  RNG = "TVF scene RNG v1"
- * (MT19937 genrand_res53 + NumPy's legacy polar Gaussian and shuffle); n <= 60.  corresp: 6 x n x B. */
+ * scaled 3x4 cameras, ROW-major (36 doubles); (hi_x, hi_y): image size in pixels.  RNG = "TVF scene RNG v2"
+ * (MT19937 genrand_res53, polar Gaussian with a reproducible logarithm, NumPy's legacy shuffle): bit-identical
+ * to the host generator tft_vs_fund_b200/scene.py; n <= 60.  corresp: 6 x n x B. */
 int tvf_generate_sweep(tvf_handle_t h, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
                        const double* P, double hi_x, double hi_y, double* corresp);
 int tvf_generate_sweep_dev(tvf_handle_t h, int64_t first_trial, int64_t B, int n, const double* noise_levels, int L,
@@ -168,6 +185,9 @@ int tvf_linear_tft_pose_dev(tvf_handle_t h, const double* corresp, const double*
 int tvf_linear_f_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,
                           int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
                           double* F21, double* F31, int32_t* status);
+int tvf_optim_f_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,
+                         int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
+                         double* F21, double* F31, int32_t* iter, int32_t* status);
 
 /* ---- measurement support ------------------------------------------------------------------ */
 /* number of kernel launches issued through this handle since creation */
@@ -188,7 +208,8 @@ int64_t tvf_launch_count(tvf_handle_t h);
 #define TVF_K_TAIL_FUSED 10
 #define TVF_K_TFT_MOMENTS_LARGE 11
 #define TVF_K_TFT_STAGE1_SOLVE 12
-#define TVF_NUM_KERNELS 13
+#define TVF_K_OPTIMF_GH 13
+#define TVF_NUM_KERNELS 14
 int tvf_profile_enable(tvf_handle_t h, int on);
 int tvf_profile_reset(tvf_handle_t h);
 int tvf_profile_read(tvf_handle_t h, double* total_ms, int64_t* launches);

@@ -35,5 +35,6 @@ from .reference_port import (  # noqa: F401
     linearF, LinearFPoseEstimation, TFT_from_P, crossM, AngError,
     project3Dpoints, matlab_svd, matlab_rank, LinearFError,
 )
+from .gauss_helmert_port import Gauss_Helmert, optimF, OptimFPoseEstimation, matlab_pinv, constraintsGH_F  # noqa: F401
 from .scene import generateSyntheticScene, SceneRNG, experiments_subsample  # noqa: F401
 from .epfl import readCalibrationOrientation_EPFL, load_corresp_triplets, epfl_triplet  # noqa: F401

@@ -32,8 +32,9 @@ class Cell(list):
 
 
 class FuncHandle:
-    def __init__(self, name):
+    def __init__(self, name, scope=None):
         self.name = name
+        self.scope = scope       # local functions of the file that created the handle (MATLAB keeps them reachable)
 
 
 # ============================================================================ tokenizer
@@ -667,7 +668,7 @@ class Interpreter:
         if kind == "paren":
             return [self.eval(e[1], env)]
         if kind == "handle":
-            return [FuncHandle(e[1])]
+            return [FuncHandle(e[1], env.get("__locals__"))]
         if kind == "id":
             name = e[1]
             if name in env:
@@ -723,7 +724,7 @@ class Interpreter:
             A = self.eval(base, env)
             if isinstance(A, FuncHandle):
                 args = [self.eval(a, env) for a in e[2]]
-                return self.call(A.name, args, nargout, env.get("__locals__"))
+                return self.call(A.name, args, nargout, A.scope if A.scope is not None else env.get("__locals__"))
             if isinstance(A, Cell):
                 subs = [self.eval_index_arg(a, env, A, k, len(e[2])) for k, a in enumerate(e[2])]
                 if len(subs) == 1:
@@ -972,6 +973,28 @@ class Interpreter:
 
     def bi_inv(self, a, n):
         return np.linalg.inv(_num(a[0]))
+
+    def bi_pinv(self, a, n):
+        """MATLAB pinv: SVD with tolerance max(size(A)) * eps(norm(A)); singular values <= tol are dropped."""
+        v = _num(a[0])
+        if v.size == 0:
+            return np.zeros((v.shape[1], v.shape[0]))
+        U, s, Vh = np.linalg.svd(v, full_matrices=False)
+        tol = max(v.shape) * np.spacing(s.max()) if len(a) < 2 else _scalar(a[1])
+        r = int(np.sum(s > tol))
+        return (Vh[:r].T / s[:r]) @ U[:, :r].T
+
+    def bi_any(self, a, n):
+        v = _num(a[0])
+        if v.ndim == 2 and 1 not in v.shape and v.size:
+            return np.any(v != 0, axis=0, keepdims=True).astype(np.float64)
+        return np.array([[float(np.any(v != 0))]])
+
+    def bi_isnan(self, a, n):
+        return np.isnan(_num(a[0])).astype(np.float64)
+
+    def bi_isinf(self, a, n):
+        return np.isinf(_num(a[0])).astype(np.float64)
 
     def bi_kron(self, a, n):
         return np.kron(_num(a[0]), _num(a[1]))

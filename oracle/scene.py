@@ -3,14 +3,17 @@
 Follows auxiliar_functions/generateSyntheticScene.m:45-135 and the trial
 sub-sampling of experiments.m:93-95 line by line.
 
-RNG ("TVF scene RNG v1", documented substitute for MATLAB's generators):
+RNG ("TVF scene RNG v2", documented substitute for MATLAB's generators):
   * ``rng(seed)`` + ``rand(r,c)``  -> ``numpy.random.RandomState(seed)``
     ``.random_sample``, filled column-major.  This is MT19937 ``genrand_res53``,
     the generator behind MATLAB's default ``rng(seed)``/``rand`` (widely
     documented equivalence; unverifiable here without MATLAB).
-  * ``randn(r,c)`` -> ``RandomState.standard_normal`` filled column-major
-    (NumPy's frozen legacy polar method).  MATLAB's ziggurat ``randn`` is
-    proprietary and NOT reproduced.
+  * ``randn(r,c)`` -> the polar (Marsaglia) method on the same stream, filled
+    column-major in NumPy-legacy order (second value of a pair first, the other
+    cached), with the logarithm taken by ``tvf_log``: a fixed sequence of IEEE
+    operations, so host and CUDA generators agree bit for bit (libm ``log``
+    differs between glibc and CUDA in the last ulp).  MATLAB's ziggurat
+    ``randn`` is proprietary and NOT reproduced.
   * ``randsample(n,k)`` -> first k entries of ``RandomState.permutation(n)``
     (MATLAB's Statistics-Toolbox ``randsample`` is NOT reproduced).
 Parity between oracle, product generator and GPU is therefore defined on
@@ -24,17 +27,83 @@ import numpy as np
 from .reference_port import crossM
 
 
+# ---- randn of "TVF scene RNG v2": polar method on the MT19937 stream with a reproducible logarithm ----------
+_LN2_HI = 6.93147180369123816490e-01
+_LN2_LO = 1.90821492927058770002e-10
+_SQRT2_BITS = 0x3ff6a09e667f3bcd
+_LOG_Q = [1.0 / k for k in (3.0, 5.0, 7.0, 9.0, 11.0, 13.0, 15.0, 17.0, 19.0, 21.0, 23.0)]
+
+
+def tvf_log(x):
+    """log(x) for positive normal doubles as a fixed sequence of IEEE operations -- the NumPy twin of
+    tvf_log in tft_vs_fund_b200/csrc/tvf_scene.cuh (same operations in the same order, no FMA)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    bits = x.view(np.int64)
+    e = ((bits >> 52) & 0x7ff) - 1023
+    mb = (bits & 0x000fffffffffffff) | (1023 << 52)
+    big = mb > _SQRT2_BITS
+    mb = np.where(big, mb - (1 << 52), mb)
+    e = e + big
+    m = mb.view(np.float64)
+    f = m + (-1.0)
+    s = f / (2.0 + f)
+    z = s * s
+    q = np.full_like(z, _LOG_Q[10])
+    for k in range(9, -1, -1):
+        q = q * z + _LOG_Q[k]
+    t = 2.0 * s
+    lg = t + (t * z) * q
+    ed = e.astype(np.float64)
+    return ed * _LN2_HI + (lg + ed * _LN2_LO)
+
+
+def polar_pairs(rs, m):
+    """The next m accepted pairs of the polar method on RandomState `rs`, shape (m, 2) = [f*x2, f*x1] per pair
+    (the order NumPy's legacy gauss returns them); consumes exactly the uniforms a sequential loop would."""
+    if m <= 0:
+        return np.empty((0, 2))
+    st = rs.get_state()
+    xs, oks = [], []
+    have = 0
+    while have < m:
+        draw = int((m - have) * 1.4) + 16
+        u = rs.random_sample(2 * draw).reshape(draw, 2)
+        x = 2.0 * u + (-1.0)
+        r2 = x[:, 0] * x[:, 0] + x[:, 1] * x[:, 1]
+        ok = (r2 < 1.0) & (r2 != 0.0)
+        xs.append((x, r2)); oks.append(ok)
+        have += int(ok.sum())
+    x = np.concatenate([a for a, _ in xs]); r2 = np.concatenate([b for _, b in xs]); ok = np.concatenate(oks)
+    idx = np.flatnonzero(ok)[:m]
+    rs.set_state(st)
+    rs.random_sample(2 * (int(idx[-1]) + 1))                      # leave the stream where the m-th acceptance left it
+    x = x[idx]; r2 = r2[idx]
+    f = np.sqrt((-2.0 * tvf_log(r2)) / r2)
+    return np.stack([f * x[:, 1], f * x[:, 0]], axis=1)
+
+
+
 class SceneRNG:
     """rng(seed) / rand / randn / randsample stand-ins (see module docstring)."""
 
     def __init__(self, seed):
         self.rs = np.random.RandomState(int(seed))
+        self._cached = None                      # second value of the last pair when an odd count was drawn
 
     def rand(self, r, c):
         return self.rs.random_sample((c, r)).T.copy()
 
     def randn(self, r, c):
-        return self.rs.standard_normal((c, r)).T.copy()
+        count = r * c
+        out = np.empty(count)
+        k = 0
+        if self._cached is not None and count > 0:
+            out[0] = self._cached; self._cached = None; k = 1
+        pairs = polar_pairs(self.rs, (count - k + 1) // 2).ravel()
+        out[k:] = pairs[:count - k]
+        if (count - k) % 2:
+            self._cached = pairs[-1]
+        return np.ascontiguousarray(out.reshape(c, r).T)
 
     def randsample(self, n, k):
         """0-based indices, k distinct values out of range(n)."""

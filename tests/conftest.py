@@ -33,7 +33,7 @@ def hostcheck():
     os.makedirs(out_dir, exist_ok=True)
     so = os.path.join(out_dir, "libhostcheck.so")
     inc = os.path.join(ROOT, "tft_vs_fund_b200", "csrc")
-    deps = [src] + [os.path.join(inc, f) for f in ("tvf_math.cuh", "tvf_pose.cuh")]
+    deps = [src] + [os.path.join(inc, f) for f in ("tvf_math.cuh", "tvf_pose.cuh", "tvf_scene.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-ffp-contract=off", "-I", inc,
                                "-x", "c++", src, "-o", so])

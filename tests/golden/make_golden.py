@@ -103,6 +103,39 @@ def epfl(ntrip=6):
     np.savez_compressed(os.path.join(HERE, "epfl_triplets.npz"), **pack(cases))
 
 
+def optimf():
+    """OptimFPoseEstimation / optimF (Gauss-Helmert refinement of F) on the first 13 x 8 trials of the
+    sweep (n = 20) and on N = 12 points (experiments.m's default N).  optf_* from the oracle port
+    (oracle/gauss_helmert_port.py), ref_optf_* from the reference's unmodified .m files run by mini_matlab."""
+    have_ref = os.path.isdir(REFERENCE)
+    if have_ref:
+        from oracle.mini_matlab import reference_interpreter
+        interp = reference_interpreter(REFERENCE, rng_factory=o.SceneRNG)
+    for name, n, ntr in (("optimf_n20.npz", 20, 13 * 8), ("optimf_n12.npz", 12, 13 * 3)):
+        d = {}
+        def put(k, v):
+            d.setdefault(k, []).append(np.asarray(v))
+        for j in range(ntr):
+            noise, seed = 0.25 * (j % 13), j // 13 + 1
+            CalM, R_t0, C, _ = o.experiments_subsample(n, noise, seed)
+            K = CalM[:3]
+            R2, R3, Rec, T, it, F21, F31 = o.OptimFPoseEstimation(C, CalM, return_F=True)
+            rep = o.ReprError([K @ np.eye(3, 4), K @ R2, K @ R3], C, Rec)
+            F, it1 = o.optimF(C[0:2], C[2:4])
+            for k, v in (("Corresp", C), ("CalM", CalM), ("noise", noise), ("seed", seed), ("optf_Rt2", R2), ("optf_Rt3", R3),
+                         ("optf_Reconst", Rec), ("optf_T", T), ("optf_iter", it), ("optf_F21", F21), ("optf_F31", F31),
+                         ("optf_repr", rep), ("optf_F_single", F), ("optf_iter_single", it1)):
+                put(k, v)
+            if have_ref:
+                r = interp.call("OptimFPoseEstimation", [C.copy(), CalM.copy()], 5)
+                rF, rit = interp.call("optimF", [C[0:2].copy(), C[2:4].copy()], 2)
+                for k, v in (("ref_optf_Rt2", r[0]), ("ref_optf_Rt3", r[1]), ("ref_optf_Reconst", r[2]), ("ref_optf_T", r[3]),
+                             ("ref_optf_iter", float(np.asarray(r[4]).item())), ("ref_optf_F_single", rF),
+                             ("ref_optf_iter_single", float(np.asarray(rit).item()))):
+                    put(k, v)
+        np.savez_compressed(os.path.join(HERE, name), **{k: np.stack(v) for k, v in d.items()})
+
+
 def large_n(n=10000, seeds=(1, 2)):
     """BASELINE config 5 shape: n = 10 000 correspondences per scene, 1 px noise.  The oracle needs ~90 s per
     scene, so its outputs are stored; the inputs are regenerated from the seed by the test (the first points are
@@ -122,7 +155,9 @@ def large_n(n=10000, seeds=(1, 2)):
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "large":
         large_n(); sys.exit(0)
-    sweep(); example(); large_n()
+    if len(sys.argv) > 1 and sys.argv[1] == "optimf":
+        optimf(); sys.exit(0)
+    sweep(); example(); large_n(); optimf()
     if os.path.isdir(REFERENCE):
         epfl()
     print("golden vectors written to", HERE)

@@ -62,3 +62,7 @@ def test_linearF_error_before_any_device_work():
         pkg.linearF(p, p)
     with pytest.raises(ValueError):
         pkg.linearF(np.zeros((2, 9)), np.zeros((2, 8)))
+    with pytest.raises(ValueError, match="At least 8 correspondences are necessary"):   # optimF.m:36-38
+        pkg.optimF(p, p)
+    with pytest.raises(ValueError, match="At least 8 correspondences are necessary"):
+        pkg.OptimFPoseEstimation(np.zeros((6, 7)), np.zeros((9, 3)))

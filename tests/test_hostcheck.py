@@ -85,14 +85,17 @@ def test_pose_tail_matches_oracle(hostcheck, mode, n, noise):
 
 
 def test_scene_generator_code_is_bit_exact_with_host_generator(hostcheck):
-    """csrc/tvf_scene.cuh (MT19937 genrand_res53, legacy polar Gaussian, legacy shuffle, fixed-order projection,
-    rejection loop, compaction, sub-sampling) compiled for the host == tft_vs_fund_b200.scene, bit for bit."""
+    """csrc/tvf_scene.cuh (MT19937 genrand_res53, polar Gaussian with the reproducible tvf_log, legacy shuffle,
+    fixed-order projection, rejection loop, compaction, sub-sampling) compiled for the host ==
+    tft_vs_fund_b200.scene, bit for bit -- noisy coordinates included."""
     from tft_vs_fund_b200 import scene
     n = 2000
     u = np.zeros(n); z = np.zeros(n); k = np.zeros(n, dtype=np.uint32)
     hostcheck.hc_mt_streams(C.c_uint(987654321), n, dp(u), dp(z), k.ctypes.data_as(C.POINTER(C.c_uint)), C.c_uint(119))
-    rs = np.random.RandomState(987654321)
-    assert np.array_equal(u, rs.random_sample(n)) and np.array_equal(z, rs.standard_normal(n))
+    rng = scene.SceneRNG(987654321)
+    assert np.array_equal(u, rng.rs.random_sample(n)) and np.array_equal(z, rng.randn(1, n).ravel())
+    rs = np.random.RandomState(987654321); rs.random_sample(n)
+    assert np.abs(z - rs.standard_normal(n)).max() < 1e-14          # same stream as NumPy's legacy gauss up to log()'s last ulp
     assert k.max() <= 119
     K, Ps, _ = scene.scene_cameras(50, 0)
     P = np.ascontiguousarray(np.stack(Ps))

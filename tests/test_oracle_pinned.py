@@ -39,6 +39,39 @@ def test_oracle_reproduces_reference_source_outputs(name, stride, method):
         assert rel_frob_up_to_sign(g["%s_T" % method][b], g["ref_%s_T" % method][b]) < 1e-12
 
 
+@pytest.mark.parametrize("name,stride", [("optimf_n20.npz", 9), ("optimf_n12.npz", 5)])
+def test_gauss_helmert_port_reproduces_reference_source_outputs(name, stride):
+    """oracle/gauss_helmert_port.py (Gauss_Helmert.m, optimF.m, OptimFPoseEstimation.m) against the
+    outputs of the reference's unmodified .m files (ref_optf_*), iteration counts included."""
+    g = np.load(os.path.join(GOLDEN, name))
+    assert "ref_optf_T" in g.files, "golden file lacks interpreter outputs: regenerate with make_golden.py optimf"
+    for b in range(0, g["Corresp"].shape[0], stride):
+        C, CalM = g["Corresp"][b], g["CalM"][b]
+        R2, R3, Rec, T, it = o.OptimFPoseEstimation(C, CalM)
+        assert it == int(g["ref_optf_iter"][b])
+        for got, key in ((R2, "Rt2"), (R3, "Rt3"), (Rec, "Reconst"), (T, "T")):
+            ref = g["ref_optf_" + key][b]
+            assert np.max(np.abs(got - ref)) <= 1e-9 * max(1.0, float(np.max(np.abs(ref)))), (name, b, key)
+        F, it1 = o.optimF(C[0:2], C[2:4])
+        assert it1 == int(g["ref_optf_iter_single"][b])
+        assert rel_frob_up_to_sign(F, g["ref_optf_F_single"][b]) < 1e-11
+    # all stored oracle outputs agree with the interpreter's
+    assert np.array_equal(g["optf_iter"], g["ref_optf_iter"].astype(g["optf_iter"].dtype))
+    for b in range(g["Corresp"].shape[0]):
+        assert rel_frob_up_to_sign(g["optf_T"][b], g["ref_optf_T"][b]) < 1e-10
+
+
+def test_matlab_pinv_definition():
+    rs = np.random.RandomState(0)
+    A = rs.standard_normal((7, 4)); A[:, 3] = A[:, 0] + A[:, 1]             # rank 3
+    P = o.matlab_pinv(A)
+    assert np.allclose(A @ P @ A, A, atol=1e-12) and np.allclose(P @ A @ P, P, atol=1e-12)
+    assert np.linalg.matrix_rank(P) == 3
+    D = np.diag([4.0, 1e-18, 2.0])
+    assert np.array_equal(o.matlab_pinv(D), np.diag([0.25, 0.0, 0.5]))     # entries below max(size)*eps(norm) vanish
+    assert o.matlab_pinv(np.zeros((0, 3))).shape == (3, 0)
+
+
 @pytest.mark.skipif(not HAVE_REF, reason="reference sources not present on this box")
 def test_interpreter_live_small_functions():
     from oracle.mini_matlab import reference_interpreter, Cell, MatlabError

@@ -6,7 +6,7 @@ CUDA (sm_100a) behind the C ABI of ``include/tvf.h`` (``libtvf.so``).  There is
 no CPU fallback; importing is cheap, the library is loaded on first use.
 """
 from .api import (  # noqa: F401
-    LinearTFTPoseEstimation, LinearFPoseEstimation, linearTFT, linearF,
+    LinearTFTPoseEstimation, LinearFPoseEstimation, OptimFPoseEstimation, linearTFT, linearF, optimF,
     Normalize2Ddata, transform_TFT, R_t_from_TFT, TFT_from_P, triangulation3D,
     ReprError, AngError, crossM, project3Dpoints, PoseResult,
 )
@@ -15,7 +15,7 @@ from .scene import generateSyntheticScene, sweep_batch, SceneRNG  # noqa: F401
 from . import experiments, sharding, epfl  # noqa: F401
 
 __all__ = [
-    "LinearTFTPoseEstimation", "LinearFPoseEstimation", "linearTFT", "linearF",
+    "LinearTFTPoseEstimation", "LinearFPoseEstimation", "OptimFPoseEstimation", "linearTFT", "linearF", "optimF",
     "Normalize2Ddata", "transform_TFT", "R_t_from_TFT", "TFT_from_P",
     "triangulation3D", "ReprError", "AngError", "crossM", "project3Dpoints",
     "generateSyntheticScene", "sweep_batch", "Handle", "handle", "TvfError",

@@ -49,6 +49,10 @@ SIGNATURES = {
     "tvf_host_free": (None, [C.c_void_p]),
     "tvf_linear_tft_pose": (_I, [_H, _D, _D, _I, _I, _L, _D, _D, _D, _D, _D, _S]),
     "tvf_linear_f_pose": (_I, [_H, _D, _D, _I, _I, _L, _D, _D, _D, _D, _D, _D, _D, _S]),
+    "tvf_optim_f_pose": (_I, [_H, _D, _D, _I, _I, _L, _D, _D, _D, _D, _D, _D, _D, _S, _S]),
+    "tvf_optim_f_pose_dev": (_I, [_H, C.c_void_p, C.c_void_p, _I, _I, _L] + [C.c_void_p] * 9),
+    "tvf_optim_f_max_n": (_I, []),
+    "tvf_optim_f": (_I, [_H, _D, _D, _I, _I, _L, _D, _S, _S]),
     "tvf_linear_tft": (_I, [_H, _D, _D, _D, _I, _I, _L, _D, _D, _D, _S]),
     "tvf_linear_f": (_I, [_H, _D, _D, _I, _I, _L, _D, _S]),
     "tvf_normalize2d": (_I, [_H, _D, _I, _L, _D, _D]),
@@ -71,7 +75,7 @@ SIGNATURES = {
     "tvf_kernel_name": (C.c_char_p, [_I]),
     "tvf_fp64_peak_tflops": (C.c_double, [_H]),
 }
-NUM_KERNELS = 13
+NUM_KERNELS = 14
 
 _lib = None
 _lock = threading.Lock()

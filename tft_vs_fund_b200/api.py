@@ -83,11 +83,17 @@ def _pose(method, Corresp, CalM, device):
     if method == "tft":
         h.call("tvf_linear_tft_pose", _p(c), _p(calm), cb, n, B, _p(Rt2), _p(Rt3), _p(Rec), _p(T), _p(rep),
                st.ctypes.data_as(_ip))
-    else:
+    elif method == "f":
         F21 = np.empty((B, 9)); F31 = np.empty((B, 9))
         h.call("tvf_linear_f_pose", _p(c), _p(calm), cb, n, B, _p(Rt2), _p(Rt3), _p(Rec), _p(T), _p(rep),
                _p(F21), _p(F31), st.ctypes.data_as(_ip))
+    else:
+        F21 = np.empty((B, 9)); F31 = np.empty((B, 9)); its = np.zeros(B, dtype=np.int32)
+        h.call("tvf_optim_f_pose", _p(c), _p(calm), cb, n, B, _p(Rt2), _p(Rt3), _p(Rec), _p(T), _p(rep),
+               _p(F21), _p(F31), its.ctypes.data_as(_ip), st.ctypes.data_as(_ip))
     it = np.zeros(B) if batched else 0                      # iter=0  (LinearTFTPoseEstimation.m:62)
+    if method == "optf":
+        it = its.astype(np.float64) if batched else int(its[0])      # iter=it1+it2 (OptimFPoseEstimation.m:49)
     out = PoseResult((_from_cm(Rt2, B, (3, 4), batched), _from_cm(Rt3, B, (3, 4), batched),
                       _from_cm(Rec, B, (3, n), batched), _from_cm(T, B, (3, 3, 3), batched), it))
     out.repr_err = rep if batched else float(rep[0])
@@ -110,6 +116,29 @@ def LinearFPoseEstimation(Corresp, CalM, device=None):
     """[R_t_2,R_t_3,Reconst,T,iter]=LinearFPoseEstimation(Corresp,CalM)
     (F_methods/LinearFPoseEstimation.m:1,42-78).  Raises ValueError with linearF's message for N<8."""
     return _pose("f", Corresp, CalM, device)
+
+
+def OptimFPoseEstimation(Corresp, CalM, device=None):
+    """[R_t_2,R_t_3,Reconst,T,iter]=OptimFPoseEstimation(Corresp,CalM)
+    (F_methods/OptimFPoseEstimation.m:1,43-72): both F refined by optimF's Gauss-Helmert iteration."""
+    c = np.asarray(Corresp)
+    if c.shape[-1] < 8:
+        raise ValueError(_lib.LINEARF_ERRMSG)                          # optimF.m:36-38
+    return _pose("optf", Corresp, CalM, device)
+
+
+def optimF(p1, p2, device=None):
+    """[F,iter]=optimF(p1,p2) (F_methods/optimF.m:1,34-78).  ValueError (optimF.m:37 text) if N<8 or N differs."""
+    a, batched, B = _cm(p1, 2); b, _, _ = _cm(p2, 2)
+    if a.shape[1] != b.shape[1] or a.shape[1] < 8:                    # optimF.m:36-38
+        raise ValueError(_lib.LINEARF_ERRMSG)
+    h = _lib.handle(device)
+    rows, n = a.shape[2], a.shape[1]
+    if b.shape != a.shape or rows not in (2, 3):
+        raise ValueError("p1,p2 must both be 2xN or 3xN")
+    F = np.empty((B, 9)); its = np.zeros(B, dtype=np.int32)
+    h.call("tvf_optim_f", _p(a), _p(b), rows, n, B, _p(F), its.ctypes.data_as(_ip), None)
+    return _from_cm(F, B, (3, 3), batched), (its.astype(np.float64) if batched else int(its[0]))
 
 
 def linearTFT(p1, p2, p3, device=None):

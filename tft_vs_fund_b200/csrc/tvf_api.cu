@@ -101,7 +101,7 @@ struct Carver {
 
 struct ChunkBufs {
     double* in; double* calm; double* T; double* F; double* core; double* cand; int* votes; double* scale;
-    double* Rt2; double* Rt3; double* reconst; double* repr; int* status;
+    double* Rt2; double* Rt3; double* reconst; double* repr; int* status; int* iters; int* iter_sum;
 };
 
 size_t carve(char* base, int n, int64_t C, bool host_io, bool calm_batched, ChunkBufs* out) {
@@ -114,6 +114,8 @@ size_t carve(char* base, int n, int64_t C, bool host_io, bool calm_batched, Chun
     b.votes = c.take<int>(10 * C);
     b.scale = c.take<double>(2 * C);
     b.status = c.take<int>(C);
+    b.iters = c.take<int>(2 * C);
+    b.iter_sum = c.take<int>(C);
     if (host_io) {
         b.in = c.take<double>((size_t)6 * n * C);
         b.calm = calm_batched ? c.take<double>(27 * C) : nullptr;
@@ -129,7 +131,7 @@ size_t carve(char* base, int n, int64_t C, bool host_io, bool calm_batched, Chun
 int64_t pick_chunk(tvf_handle_t h, int n, int64_t B, bool host_io) {
     int64_t c = h->chunk_user > 0 ? h->chunk_user : DEFAULT_CHUNK;
     if (h->chunk_user <= 0) {   // automatic: keep one slot's work space near ARENA_BUDGET
-        size_t payload = (27 + 18 + CORE_WS_TFT + CAND_SIZE + 2) * 8 + 11 * 4;
+        size_t payload = (27 + 18 + CORE_WS_TFT + CAND_SIZE + 2) * 8 + 14 * 4;
         if (host_io) payload += (size_t)(6 * n + 27 + 24 + 3 * n + 1) * 8;
         const int64_t fit = (int64_t)(ARENA_BUDGET / payload);
         if (c > fit) c = fit;
@@ -139,7 +141,7 @@ int64_t pick_chunk(tvf_handle_t h, int n, int64_t B, bool host_io) {
     return c;
 }
 
-enum Method { METHOD_TFT = 0, METHOD_F = 1 };
+enum Method { METHOD_TFT = 0, METHOD_F = 1, METHOD_OPTF = 2 };
 
 cudaEvent_t get_event(tvf_handle_t h) {
     if (!h->free_events.empty()) { cudaEvent_t e = h->free_events.back(); h->free_events.pop_back(); return e; }
@@ -175,7 +177,8 @@ int drain_events(tvf_handle_t h) {
 // kernels of one chunk; all pointers are device pointers
 int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double* d_corresp, const double* d_calm,
                    int calm_batched, int n, int64_t Bc, double* d_T, double* d_F, double* d_core, double* d_cand, int* d_votes,
-                   double* d_scale, double* d_Rt2, double* d_Rt3, double* d_reconst, double* d_repr, int* d_status) {
+                   double* d_scale, double* d_Rt2, double* d_Rt3, double* d_reconst, double* d_repr, int* d_status,
+                   int* d_iters = nullptr, int* d_iter_sum = nullptr) {
     CoreInput in{};
     in.p1 = d_corresp; in.p2 = nullptr; in.p3 = nullptr; in.packed = 1; in.rows = 2; in.n = n; in.B = Bc; in.normalize = 1;
     PoseTailArgs a{};
@@ -197,9 +200,16 @@ int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double*
         timed_launch(h, TVF_K_TFT_EPIPOLES, st, [&] { launch_tft_epipoles(d_core, Bc, st); });
         timed_launch(h, TVF_K_TFT_STAGE2, st, [&] { launch_tft_stage2(in, d_core, d_T, nullptr, nullptr, d_status, sm, st); });
         timed_launch(h, TVF_K_CANDIDATES, st, [&] { launch_candidates(0, d_T, a, st); });
-    } else {
+    } else if (method == METHOD_F) {
         timed_launch(h, TVF_K_F_STAGE1, st, [&] { launch_f_stage1(in, d_core, d_status, sm, st); });
         timed_launch(h, TVF_K_F_FINISH, st, [&] { launch_f_finish(d_core, 1, Bc, d_F, st); });
+        timed_launch(h, TVF_K_CANDIDATES, st, [&] { launch_candidates(1, d_F, a, st); });
+    } else {    // OptimFPoseEstimation.m:47-53: linearF start, Gauss-Helmert refinement, then the F pose tail
+        timed_launch(h, TVF_K_F_STAGE1, st, [&] { launch_f_stage1(in, d_core, d_status, sm, st); });
+        int ok = 1;
+        timed_launch(h, TVF_K_OPTIMF_GH, st, [&] { ok = launch_optimf_gh(d_corresp, n, Bc, d_core, d_F, d_iters, d_status, sm, st); });
+        if (!ok) return fail(h, TVF_ERR_ARG, "optimF: too many correspondences for the Gauss-Helmert kernel (see tvf_optim_f_max_n)");
+        if (d_iter_sum) launch_sum_pairs(d_iters, Bc, d_iter_sum, st);
         timed_launch(h, TVF_K_CANDIDATES, st, [&] { launch_candidates(1, d_F, a, st); });
     }
     if (n >= TAIL_FUSED_MIN_N && n <= TAIL_FUSED_MAX_N) {
@@ -209,7 +219,7 @@ int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double*
         timed_launch(h, TVF_K_SCALE, st, [&] { launch_scale(a, sm, st); });
         timed_launch(h, TVF_K_FINAL, st, [&] { launch_final(a, sm, st); });
     }
-    if (method == METHOD_F && d_T != nullptr)
+    if (method != METHOD_TFT && d_T != nullptr)
         timed_launch(h, TVF_K_TFT_FROM_POSE, st, [&] { launch_tft_from_pose(d_calm, calm_batched, d_Rt2, d_Rt3, Bc, d_T, st); });
     TVF_CK(cudaGetLastError());
     return TVF_OK;
@@ -219,7 +229,8 @@ int check_pose_args(tvf_handle_t h, const void* corresp, const void* calm, int n
     if (!h) return TVF_ERR_ARG;
     if (!corresp || !calm) return fail(h, TVF_ERR_ARG, "corresp/calm must not be NULL");
     if (B < 0 || n < 1) return fail(h, TVF_ERR_ARG, "need n >= 1 and B >= 0");
-    if (m == METHOD_F && n < 8) return fail(h, TVF_ERR_TOO_FEW_POINTS, TVF_LINEARF_ERRMSG);
+    if (m != METHOD_TFT && n < 8) return fail(h, TVF_ERR_TOO_FEW_POINTS, TVF_LINEARF_ERRMSG);
+    if (m == METHOD_OPTF && n > optimf_max_n()) return fail(h, TVF_ERR_ARG, "optimF: too many correspondences for the Gauss-Helmert kernel (see tvf_optim_f_max_n)");
     return TVF_OK;
 }
 
@@ -231,7 +242,7 @@ int count_flagged(const int32_t* st, int64_t B) {
 
 int pose_host(tvf_handle_t h, Method method, const double* corresp, const double* calm, int calm_batched, int n,
               int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21,
-              double* F31, int32_t* status) {
+              double* F31, int32_t* status, int32_t* iter = nullptr) {
     int rc = check_pose_args(h, corresp, calm, n, B, method);
     if (rc != TVF_OK) return rc;
     if (B == 0) return TVF_OK;
@@ -263,16 +274,18 @@ int pose_host(tvf_handle_t h, Method method, const double* corresp, const double
         }
         rc = run_pose_chunk(h, s.stream, method, b.in, d_calm, calm_batched, n, Bc,
                             (method == METHOD_TFT || T) ? b.T : nullptr, b.F, b.core, b.cand, b.votes, b.scale, b.Rt2, b.Rt3,
-                            b.reconst, b.repr, b.status);
+                            b.reconst, b.repr, b.status, b.iters, b.iter_sum);
         if (rc) return rc;
+        if (iter && method == METHOD_OPTF)
+            TVF_CK(cudaMemcpyAsync(iter + done, b.iter_sum, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         if (Rt2) TVF_CK(cudaMemcpyAsync(Rt2 + done * 12, b.Rt2, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         if (Rt3) TVF_CK(cudaMemcpyAsync(Rt3 + done * 12, b.Rt3, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         if (reconst) TVF_CK(cudaMemcpyAsync(reconst + done * 3 * n, b.reconst, (size_t)Bc * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         if (T) TVF_CK(cudaMemcpyAsync(T + done * 27, b.T, (size_t)Bc * 27 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
         if (repr_err) TVF_CK(cudaMemcpyAsync(repr_err + done, b.repr, (size_t)Bc * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (method == METHOD_F && F21)
+        if (method != METHOD_TFT && F21)
             TVF_CK(cudaMemcpy2DAsync(F21 + done * 9, 72, b.F, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
-        if (method == METHOD_F && F31)
+        if (method != METHOD_TFT && F31)
             TVF_CK(cudaMemcpy2DAsync(F31 + done * 9, 72, b.F + 9, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
         TVF_CK(cudaMemcpyAsync(st_host + done, b.status, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         done += Bc; ++ci;
@@ -283,7 +296,7 @@ int pose_host(tvf_handle_t h, Method method, const double* corresp, const double
 
 int pose_dev(tvf_handle_t h, Method method, const double* corresp, const double* calm, int calm_batched, int n,
              int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21,
-             double* F31, int32_t* status) {
+             double* F31, int32_t* status, int32_t* iter = nullptr) {
     int rc = check_pose_args(h, corresp, calm, n, B, method);
     if (rc != TVF_OK) return rc;
     if (B == 0) return TVF_OK;
@@ -304,11 +317,12 @@ int pose_dev(tvf_handle_t h, Method method, const double* corresp, const double*
         double* dRt3 = Rt3 ? Rt3 + done * 12 : tmpRt3;
         rc = run_pose_chunk(h, st, method, corresp + done * 6 * n, calm + (calm_batched ? done * 27 : 0), calm_batched, n,
                             Bc, dT, b.F, b.core, b.cand, b.votes, b.scale, dRt2, dRt3, reconst ? reconst + done * 3 * n : nullptr,
-                            repr_err ? repr_err + done : nullptr, status ? status + done : b.status);
+                            repr_err ? repr_err + done : nullptr, status ? status + done : b.status, b.iters,
+                            iter ? iter + done : nullptr);
         if (rc) return rc;
-        if (method == METHOD_F && F21)
+        if (method != METHOD_TFT && F21)
             TVF_CK(cudaMemcpy2DAsync(F21 + done * 9, 72, b.F, 144, 72, (size_t)Bc, cudaMemcpyDeviceToDevice, st));
-        if (method == METHOD_F && F31)
+        if (method != METHOD_TFT && F31)
             TVF_CK(cudaMemcpy2DAsync(F31 + done * 9, 72, b.F + 9, 144, 72, (size_t)Bc, cudaMemcpyDeviceToDevice, st));
     }
     return TVF_OK;
@@ -497,7 +511,7 @@ const char* tvf_kernel_name(int id) {
                                                  "f_stage1_kernel", "f_finish_kernel", "candidates_kernel",
                                                  "votes_kernel", "scale_kernel", "final_kernel", "tft_from_pose_kernel",
                                                  "pose_tail_fused_kernel", "tft_moments_large_kernel",
-                                                 "tft_stage1_solve_kernel"};
+                                                 "tft_stage1_solve_kernel", "optimf_gh_kernel"};
     return (id >= 0 && id < TVF_NUM_KERNELS) ? names[id] : "";
 }
 
@@ -511,6 +525,20 @@ int tvf_linear_f_pose(tvf_handle_t h, const double* corresp, const double* calm,
                       int32_t* status) {
     return pose_host(h, METHOD_F, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, F21, F31, status);
 }
+
+int tvf_optim_f_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
+                     double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21, double* F31,
+                     int32_t* iter, int32_t* status) {
+    return pose_host(h, METHOD_OPTF, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, F21, F31, status, iter);
+}
+
+int tvf_optim_f_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
+                         double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21, double* F31,
+                         int32_t* iter, int32_t* status) {
+    return pose_dev(h, METHOD_OPTF, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, F21, F31, status, iter);
+}
+
+int tvf_optim_f_max_n(void) { return optimf_max_n(); }
 
 int tvf_linear_tft_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
                             double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, int32_t* status) {
@@ -579,6 +607,49 @@ int tvf_linear_f(tvf_handle_t h, const double* p1, const double* p2, int rows, i
     u.back(sth, (const int32_t*)dst, (size_t)B);
     int rc = u.finish();
     return rc ? rc : count_flagged(sth, B);
+}
+
+int tvf_optim_f(tvf_handle_t h, const double* p1, const double* p2, int rows, int n, int64_t B, double* F, int32_t* iter,
+                int32_t* status) {
+    if (!h) return TVF_ERR_ARG;
+    if (!p1 || !p2 || !F || (rows != 2 && rows != 3) || B < 0) return fail(h, TVF_ERR_ARG, "optimF: bad argument");
+    if (n < 8) return fail(h, TVF_ERR_TOO_FEW_POINTS, TVF_LINEARF_ERRMSG);                 // optimF.m:36-38
+    if (n > optimf_max_n()) return fail(h, TVF_ERR_ARG, "optimF: too many correspondences for the Gauss-Helmert kernel (see tvf_optim_f_max_n)");
+    if (B == 0) return TVF_OK;
+    TVF_CK(cudaSetDevice(h->device));
+    // the kernels work on packed 6 x n records; the pair (p1, p2) is stored as views 1 and 2 (and again as view 3)
+    std::vector<double> packed((size_t)6 * n * B);
+    for (size_t i = 0; i < (size_t)n * B; ++i) {
+        double a0 = p1[i * rows], a1 = p1[i * rows + 1], b0 = p2[i * rows], b1 = p2[i * rows + 1];
+        if (rows == 3) { a0 /= p1[i * 3 + 2]; a1 /= p1[i * 3 + 2]; b0 /= p2[i * 3 + 2]; b1 /= p2[i * 3 + 2]; }   // optimF.m:40-43
+        double* q = &packed[6 * i];
+        q[0] = a0; q[1] = a1; q[2] = b0; q[3] = b1; q[4] = b0; q[5] = b1;
+    }
+    Up u(h);
+    CoreInput in{};
+    in.p1 = u.in(packed.data(), packed.size()); in.packed = 1; in.rows = 2; in.n = n; in.B = B; in.normalize = 1;
+    double* dF = u.out<double>(18 * (size_t)B);
+    int* dst = u.out<int>((size_t)B);
+    int* dit = u.out<int>(2 * (size_t)B);
+    double* dws = u.out<double>((size_t)CORE_WS_F * B);
+    if (u.rc) return u.rc;
+    launch_f_stage1(in, dws, dst, h->sm_count, u.st);
+    if (!launch_optimf_gh(in.p1, n, B, dws, dF, dit, dst, h->sm_count, u.st)) return fail(h, TVF_ERR_ARG, "optimF: n too large");
+    h->launches += 3;
+    std::vector<double> Fh(18 * (size_t)B);
+    std::vector<int32_t> ith(2 * (size_t)B), tmp;
+    int32_t* sth = status;
+    if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }
+    u.back(Fh.data(), dF, 18 * (size_t)B);
+    u.back(ith.data(), (const int32_t*)dit, 2 * (size_t)B);
+    u.back(sth, (const int32_t*)dst, (size_t)B);
+    int rc = u.finish();
+    if (rc) return rc;
+    for (int64_t b = 0; b < B; ++b) {
+        for (int q = 0; q < 9; ++q) F[9 * b + q] = Fh[18 * b + q];
+        if (iter) iter[b] = ith[2 * b];
+    }
+    return count_flagged(sth, B);
 }
 
 int tvf_normalize2d(tvf_handle_t h, const double* points, int n, int64_t B, double* new_points, double* N_matrix) {

@@ -37,6 +37,13 @@ void launch_f_stage1(const CoreInput& in, double* ws, int* status, int sm_count,
 // normalize != 0: two pairs per problem (F21, F31 -> F[18*b]); else one (F[9*b])
 void launch_f_finish(const double* ws, int normalize, long long B, double* F, cudaStream_t stream);
 
+// ---- Gauss-Helmert refinement of F (optimF.m; tvf_gh_kernels.cu).  ws: f_stage1 records of the pose path
+// (two pairs per problem); Fio: 18 x B, receives [F21 F31]; iters: 2 x B.  Returns 0 if n is too large.
+int optimf_max_n();
+int launch_optimf_gh(const double* corresp, int n, long long B, const double* ws, double* Fio, int* iters, int* status,
+                     int sm_count, cudaStream_t stream);
+void launch_sum_pairs(const int* in2, long long B, int* out, cudaStream_t stream);
+
 // ---- pose tail -----------------------------------------------------------------------------
 struct PoseTailArgs {
     const double* corresp;     // 6 x n x B

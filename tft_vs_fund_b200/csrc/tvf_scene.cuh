@@ -2,15 +2,17 @@
 // auxiliar_functions/generateSyntheticScene.m:75-111 (N+100 points, projection, Gaussian noise,
 // inside-image rejection loop) followed by the column sub-sampling of experiments.m:94-95.
 //
-// RNG = "TVF scene RNG v1" (tft_vs_fund_b200/scene.py): rng(seed)/rand is MT19937 genrand_res53;
-// randn is NumPy's legacy polar method on the same stream; randsample(n,k) is the first k entries of
-// NumPy's legacy shuffle of 0..n-1 on a freshly seeded stream.  Integer work (MT19937, rejection masks,
-// compaction order, permutation) and the projection arithmetic (fixed order, no FMA contraction, IEEE
-// division) are bit-exact with the host generator; the Gaussian uses log(), whose device implementation
-// may differ from glibc in the last ulp, so noisy coordinates agree to ~1e-12 px, not bit for bit.
+// RNG = "TVF scene RNG v2" (tft_vs_fund_b200/scene.py): rng(seed)/rand is MT19937 genrand_res53;
+// randn is the polar (Marsaglia) method on the same stream in NumPy-legacy order (second value of a pair
+// first, the other cached) with the logarithm taken by tvf_log below -- a fixed sequence of IEEE
+// operations, so that host and device produce the same bits (libm's log differs between glibc and CUDA in
+// the last ulp); randsample(n,k) is the first k entries of NumPy's legacy shuffle of 0..n-1 on a freshly
+// seeded stream.  Everything -- MT19937, rejection masks, compaction order, permutation, projections (fixed
+// order, no FMA contraction, IEEE division) and the noisy coordinates -- is bit-exact with the host generator.
 // Host/device code: tests/hostcheck compiles it for the CPU and compares with NumPy.
 #pragma once
 #include <stdint.h>
+#include <string.h>
 
 #include "tvf_math.cuh"
 
@@ -27,6 +29,46 @@ namespace tvf {
 #define TVF_DIV(a, b) ((a) / (b))
 #define TVF_SQRT(a) sqrt((a))
 #endif
+
+// Natural logarithm of a positive, normal double as a fixed sequence of correctly rounded IEEE operations
+// (no FMA, no libm): x = m * 2^e with m in (sqrt(1/2), sqrt(2)], s = (m-1)/(m+1), z = s^2,
+// log m = 2s + 2s*z*(1/3 + z/5 + ... + z^10/23) (next term < 6e-19 relative), log x = e*ln2_hi + (log m + e*ln2_lo).
+// Accurate to ~2 ulp; its point is reproducibility: scene.py / oracle/scene.py restate it in NumPy.
+TVF_HD double tvf_log(double x) {
+    long long bits;
+#if defined(__CUDA_ARCH__)
+    bits = __double_as_longlong(x);
+#else
+    memcpy(&bits, &x, 8);
+#endif
+    long long e = ((bits >> 52) & 0x7ff) - 1023;
+    long long mb = (bits & 0x000fffffffffffffLL) | (1023LL << 52);
+    if (mb > 0x3ff6a09e667f3bcdLL) { mb -= (1LL << 52); e += 1; }        // m > sqrt(2): halve
+    double m;
+#if defined(__CUDA_ARCH__)
+    m = __longlong_as_double(mb);
+#else
+    memcpy(&m, &mb, 8);
+#endif
+    const double f = TVF_ADD(m, -1.0);
+    const double s = TVF_DIV(f, TVF_ADD(2.0, f));
+    const double z = TVF_MUL(s, s);
+    double q = 1.0 / 23.0;
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 21.0);
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 19.0);
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 17.0);
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 15.0);
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 13.0);
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 11.0);
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 9.0);
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 7.0);
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 5.0);
+    q = TVF_ADD(TVF_MUL(q, z), 1.0 / 3.0);
+    const double t = TVF_MUL(2.0, s);
+    const double lg = TVF_ADD(t, TVF_MUL(TVF_MUL(t, z), q));
+    const double ed = (double)e;
+    return TVF_ADD(TVF_MUL(ed, 6.93147180369123816490e-01), TVF_ADD(lg, TVF_MUL(ed, 1.90821492927058770002e-10)));
+}
 
 constexpr int SCENE_MAX_POINTS = 160;       // N + 100 <= 160, i.e. n <= 60 per problem on this path
 
@@ -79,7 +121,7 @@ struct MT19937 {
             x2 = TVF_ADD(TVF_MUL(2.0, res53()), -1.0);
             r2 = TVF_ADD(TVF_MUL(x1, x1), TVF_MUL(x2, x2));
         } while (r2 >= 1.0 || r2 == 0.0);
-        const double f = TVF_SQRT(TVF_DIV(TVF_MUL(-2.0, log(r2)), r2));
+        const double f = TVF_SQRT(TVF_DIV(TVF_MUL(-2.0, tvf_log(r2)), r2));
         gauss = TVF_MUL(f, x1); has_gauss = 1;
         return TVF_MUL(f, x2);
     }

@@ -10,7 +10,8 @@ import numpy as np
 from . import api, scene, sharding
 
 NOISE_LEVELS = np.arange(0.0, 3.0 + 1e-9, 0.25)          # experiments.m:40  interval=0:0.25:3
-METHODS = {1: ("Linear TFT", api.LinearTFTPoseEstimation), 7: ("Linear F", api.LinearFPoseEstimation)}
+METHODS = {1: ("Linear TFT", api.LinearTFTPoseEstimation), 7: ("Linear F", api.LinearFPoseEstimation),
+           8: ("Optimal F", api.OptimFPoseEstimation)}          # numbering of experiments.m:51-59
 
 
 def evaluate(res, R_t0, device=None):

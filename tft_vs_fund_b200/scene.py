@@ -6,10 +6,13 @@ of experiments.m:93-95, vectorised over points and batched over trials.  It is
 independent of ``oracle/`` (which restates the same script line by line); the
 tests require the two to agree bit for bit.
 
-RNG ("TVF scene RNG v1"): ``rng(seed)``/``rand`` -> MT19937 ``genrand_res53``
+RNG ("TVF scene RNG v2"): ``rng(seed)``/``rand`` -> MT19937 ``genrand_res53``
 via ``numpy.random.RandomState(seed).random_sample`` (column-major fill, the
-stream MATLAB's default generator produces); ``randn`` -> RandomState's frozen
-``standard_normal``; ``randsample(n,k)`` -> ``RandomState.permutation(n)[:k]``.
+stream MATLAB's default generator produces); ``randn`` -> the polar method on
+the same stream in NumPy-legacy order, with the logarithm taken by ``tvf_log``
+(a fixed sequence of IEEE operations, so the CUDA generator reproduces every
+noisy coordinate bit for bit; libm's ``log`` differs between glibc and CUDA in
+the last ulp); ``randsample(n,k)`` -> ``RandomState.permutation(n)[:k]``.
 MATLAB's own ``randn``/``randsample`` streams are proprietary and are not
 reproduced.  Projection arithmetic is fixed and unfused:
 ``x_r = ((P[r,0]*X + P[r,1]*Y) + P[r,2]*Z) + P[r,3]`` followed by ``x_r/x_3``.
@@ -19,15 +22,81 @@ import numpy as np
 PIX = 50.0   # pixels per mm (generateSyntheticScene.m:54)
 
 
+# ---- randn of "TVF scene RNG v2": polar method on the MT19937 stream with a reproducible logarithm ----------
+_LN2_HI = 6.93147180369123816490e-01
+_LN2_LO = 1.90821492927058770002e-10
+_SQRT2_BITS = 0x3ff6a09e667f3bcd
+_LOG_Q = [1.0 / k for k in (3.0, 5.0, 7.0, 9.0, 11.0, 13.0, 15.0, 17.0, 19.0, 21.0, 23.0)]
+
+
+def tvf_log(x):
+    """log(x) for positive normal doubles as a fixed sequence of IEEE operations -- the NumPy twin of
+    tvf_log in tft_vs_fund_b200/csrc/tvf_scene.cuh (same operations in the same order, no FMA)."""
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    bits = x.view(np.int64)
+    e = ((bits >> 52) & 0x7ff) - 1023
+    mb = (bits & 0x000fffffffffffff) | (1023 << 52)
+    big = mb > _SQRT2_BITS
+    mb = np.where(big, mb - (1 << 52), mb)
+    e = e + big
+    m = mb.view(np.float64)
+    f = m + (-1.0)
+    s = f / (2.0 + f)
+    z = s * s
+    q = np.full_like(z, _LOG_Q[10])
+    for k in range(9, -1, -1):
+        q = q * z + _LOG_Q[k]
+    t = 2.0 * s
+    lg = t + (t * z) * q
+    ed = e.astype(np.float64)
+    return ed * _LN2_HI + (lg + ed * _LN2_LO)
+
+
+def polar_pairs(rs, m):
+    """The next m accepted pairs of the polar method on RandomState `rs`, shape (m, 2) = [f*x2, f*x1] per pair
+    (the order NumPy's legacy gauss returns them); consumes exactly the uniforms a sequential loop would."""
+    if m <= 0:
+        return np.empty((0, 2))
+    st = rs.get_state()
+    xs, oks = [], []
+    have = 0
+    while have < m:
+        draw = int((m - have) * 1.4) + 16
+        u = rs.random_sample(2 * draw).reshape(draw, 2)
+        x = 2.0 * u + (-1.0)
+        r2 = x[:, 0] * x[:, 0] + x[:, 1] * x[:, 1]
+        ok = (r2 < 1.0) & (r2 != 0.0)
+        xs.append((x, r2)); oks.append(ok)
+        have += int(ok.sum())
+    x = np.concatenate([a for a, _ in xs]); r2 = np.concatenate([b for _, b in xs]); ok = np.concatenate(oks)
+    idx = np.flatnonzero(ok)[:m]
+    rs.set_state(st)
+    rs.random_sample(2 * (int(idx[-1]) + 1))                      # leave the stream where the m-th acceptance left it
+    x = x[idx]; r2 = r2[idx]
+    f = np.sqrt((-2.0 * tvf_log(r2)) / r2)
+    return np.stack([f * x[:, 1], f * x[:, 0]], axis=1)
+
+
+
 class SceneRNG:
     def __init__(self, seed):
         self.rs = np.random.RandomState(int(seed))
+        self._cached = None                      # second value of the last pair when an odd count was drawn
 
     def rand(self, r, c):
         return np.ascontiguousarray(self.rs.random_sample((c, r)).T)
 
     def randn(self, r, c):
-        return np.ascontiguousarray(self.rs.standard_normal((c, r)).T)
+        count = r * c
+        out = np.empty(count)
+        k = 0
+        if self._cached is not None and count > 0:
+            out[0] = self._cached; self._cached = None; k = 1
+        pairs = polar_pairs(self.rs, (count - k + 1) // 2).ravel()
+        out[k:] = pairs[:count - k]
+        if (count - k) % 2:
+            self._cached = pairs[-1]
+        return np.ascontiguousarray(out.reshape(c, r).T)
 
     def randsample(self, n, k):
         return self.rs.permutation(n)[:k]
@@ -133,7 +202,7 @@ def _sweep_range(args):
         rs.seed(seed)
         X = 400 * np.ascontiguousarray(rs.random_sample((M, 3)).T) - 200
         clean = np.vstack([_project(P, X) for P in Ps])
-        Z = np.vstack([np.ascontiguousarray(rs.standard_normal((M, 2)).T) for _ in range(3)])
+        Z = np.vstack([np.ascontiguousarray(polar_pairs(rs, M).T) for _ in range(3)])
         rs2.seed(seed)
         idx = rs2.permutation(M)[:n]                                 # experiments.m:94-95
         for lv in range(lv0, lv1):
@@ -150,12 +219,12 @@ def _sweep_range(args):
             Corresp[:, :keep.size] = c6[:, keep]
             filled = keep.size
             rs.seed(seed)
-            rs.random_sample((M, 3)); rs.standard_normal((3 * M, 2))
+            rs.random_sample((M, 3)); polar_pairs(rs, 3 * M)
             while filled < M:
                 m = M - filled
                 Xm = 400 * np.ascontiguousarray(rs.random_sample((m, 3)).T) - 200
                 cm = np.vstack([_project(P, Xm) for P in Ps])
-                zm = np.vstack([np.ascontiguousarray(rs.standard_normal((m, 2)).T) for _ in range(3)])
+                zm = np.vstack([np.ascontiguousarray(polar_pairs(rs, m).T) for _ in range(3)])
                 cm = cm + zm * noise
                 kp = np.flatnonzero(_inside(cm))
                 Corresp[:, filled:filled + kp.size] = cm[:, kp]
@@ -193,8 +262,7 @@ def sweep_batch(B, n=20, first_trial=0, noise_levels=None, focalL=50, angle=0, w
 def sweep_batch_device(B, n=20, first_trial=0, noise_levels=None, focalL=50, angle=0, device=None, out_ptr=None):
     """Same trials as sweep_batch, generated by the CUDA kernel behind tvf_generate_sweep (one thread per trial).
     Returns the same dict (Corresp as a NumPy array) or, with `out_ptr` (a device pointer to 6*n*B doubles),
-    fills that buffer in place and returns the dict without "Corresp".  Integer work and the projections are
-    bit-exact with sweep_batch; noisy coordinates may differ in the last ulp (device log())."""
+    fills that buffer in place and returns the dict without "Corresp".  Bit-exact with sweep_batch."""
     import ctypes as C
     from . import _lib
     if noise_levels is None:
