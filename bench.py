@@ -274,6 +274,12 @@ def run_gpu(args, rank, local_rank, world):
         h.call("tvf_linear_f_pose_dev", ptr(d_corresp), ptr(d_calm), 0, n, B, ptr(d_Rt2), ptr(d_Rt3), ptr(d_rec),
                ptr(d_T), ptr(d_rep), None, None, ptr(d_st))
 
+    d_iter = torch.zeros((B,), dtype=torch.int32, device=dev)
+
+    def step_optf():
+        h.call("tvf_optim_f_pose_dev", ptr(d_corresp), ptr(d_calm), 0, n, B, ptr(d_Rt2), ptr(d_Rt3), ptr(d_rec),
+               ptr(d_T), ptr(d_rep), None, None, ptr(d_iter), ptr(d_st))
+
     def barrier():
         torch.cuda.synchronize(dev)
         if world > 1:
@@ -325,6 +331,15 @@ def run_gpu(args, rank, local_rank, world):
         step_f()
     ms_f, _ = timed(step_f, max(3, args.steps // 2))
     f_value = world * B * max(3, args.steps // 2) / (ms_f * 1e-3)
+
+    # OptimFPoseEstimation (Gauss-Helmert refinement of both F), same inputs
+    optf_steps = max(3, args.steps // 4)
+    for _ in range(2):
+        step_optf()
+    ms_o, prof_o = timed(step_optf, optf_steps, profile=True)
+    optf_value = world * B * optf_steps / (ms_o * 1e-3)
+    optf_iters = float(d_iter.double().mean().item())
+    gh_ms = prof_o.get("optimf_gh_kernel", (float("nan"), 1)) if prof_o else (float("nan"), 1)
 
     # 5. end to end through the host-pointer C ABI: pinned host buffers, H2D + kernels + D2H inside the timed region
     lib.tvf_host_alloc.restype = C.c_void_p
@@ -458,11 +473,14 @@ def run_gpu(args, rank, local_rank, world):
         "f_method": {"metric": "3-view linear F pose solves/sec (LinearFPoseEstimation + ReprError)", "value": f_value,
                      "unit": UNIT, "ms_per_step": ms_f / max(3, args.steps // 2),
                      "roofline_step_frac_fp64": f_flops(n) * B / (ms_f * 1e-3 / max(3, args.steps // 2)) / 1e12 / fp64_peak},
+        "optimf_method": {"metric": "3-view optimal-F pose solves/sec (OptimFPoseEstimation + ReprError)", "value": optf_value,
+                          "unit": UNIT, "ms_per_step": ms_o / optf_steps, "mean_gauss_helmert_iterations_per_solve": optf_iters,
+                          "optimf_gh_kernel_share": gh_ms[0] / ms_o if ms_o > 0 else None},
         "device_resident_sweep": {"api": "tvf_sweep_run: trials generated, solved and reduced per noise level on the device",
                                   "value": sweep_value, "unit": UNIT, "d2h_bytes_per_step": int(table.nbytes),
                                   "mean_repr_err_px_by_level": (table[:, 0] / np.maximum(table[:, 3], 1)).round(4).tolist()},
         "flagged_problems": flagged,
-        "input_generation": {"where": "device (tvf_generate_sweep_dev, TVF scene RNG v1)", "seconds": t_gen, "check": gen_check},
+        "input_generation": {"where": "device (tvf_generate_sweep_dev, TVF scene RNG v2)", "seconds": t_gen, "check": gen_check},
     }
     print(json.dumps(line), flush=True)
     if world > 1:

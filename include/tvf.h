@@ -168,7 +168,7 @@ int tvf_generate_sweep_dev(tvf_handle_t h, int64_t first_trial, int64_t B, int n
                            const double* P, double hi_x, double hi_y, double* d_corresp);
 
 /* The inner loops of experiments.m:74-124 for one method (1 = LinearTFTPoseEstimation, 7 =
- * LinearFPoseEstimation), entirely device-resident: trials [first_trial, first_trial+B) are generated
+ * LinearFPoseEstimation, 8 = OptimFPoseEstimation; numbering of experiments.m:51-59), entirely device-resident: trials [first_trial, first_trial+B) are generated
  * (as tvf_generate_sweep), solved, and their ReprError / AngError (auxiliar_functions/AngError.m, mean of the
  * two views as in :117-120) summed per noise level in a fixed order.  table: L x 5 row-major =
  * [sum repr_err, sum rot_err, sum t_err, trials counted, trials skipped (no pose / non-finite)].

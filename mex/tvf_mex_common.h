@@ -1,4 +1,4 @@
-// tvf_mex_common.h -- shared plumbing of the four MEX gateways: one persistent libtvf handle per MATLAB
+// tvf_mex_common.h -- shared plumbing of the MEX gateways: one persistent libtvf handle per MATLAB
 // process (mexLock + mexAtExit), argument checks, batched shapes.
 //
 // Contract: inputs are borrowed `const mxArray*` (real, full, double); outputs are created
@@ -67,7 +67,7 @@ inline void check(int rc, tvf_handle_t h) {
     if (rc < 0) mexErrMsgIdAndTxt("TFT_vs_Fund:runtime", "libtvf error %d: %s", rc, tvf_last_error(h));
 }
 
-// [R_t_2,R_t_3,Reconst,T,iter] = Method(Corresp,CalM) for both linear methods
+// [R_t_2,R_t_3,Reconst,T,iter] = Method(Corresp,CalM) for the pose-estimation methods
 template <typename Call>
 inline void pose_gateway(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[], const char* name, Call call) {
     if (nrhs != 2) mexErrMsgIdAndTxt("TFT_vs_Fund:nargin", "%s(Corresp,CalM) takes two inputs", name);
@@ -80,9 +80,9 @@ inline void pose_gateway(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prh
     tvf_handle_t h = handle();
     mxArray* Rt2 = make(3, 4, c.B); mxArray* Rt3 = make(3, 4, c.B);
     mxArray* Rec = make(3, c.n, c.B); mxArray* T = make_tensor(c.B);
-    std::vector<int32_t> status(c.B);
+    std::vector<int32_t> status(c.B), iters(c.B, 0);
     const int rc = call(h, mxGetPr(prhs[0]), mxGetPr(prhs[1]), k.B != 1, (int)c.n, (int64_t)c.B, mxGetPr(Rt2),
-                        mxGetPr(Rt3), mxGetPr(Rec), mxGetPr(T), status.data());
+                        mxGetPr(Rt3), mxGetPr(Rec), mxGetPr(T), status.data(), iters.data());
     mxArray* outs[5] = {Rt2, Rt3, Rec, T, nullptr};
     if (rc < 0 || (c.B == 1 && (status[0] & (TVF_ST_NO_POSE_2 | TVF_ST_NO_POSE_3)))) {
         for (int i = 0; i < 4; ++i) mxDestroyArray(outs[i]);
@@ -90,7 +90,9 @@ inline void pose_gateway(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prh
         // the reference stops here with "Undefined function or variable 'R_f'" (R_t_from_TFT.m:91-104)
         mexErrMsgIdAndTxt("TFT_vs_Fund:undefinedPose", "recover_R_t: no candidate pose received a non-negative vote");
     }
-    outs[4] = (c.B == 1) ? mxCreateDoubleScalar(0.0) : make(c.B, 1, 1);      // iter=0 (:62 / :77)
+    // iter: the constant 0 of the linear methods (:62 / :77), it1+it2 for OptimFPoseEstimation (:49)
+    outs[4] = (c.B == 1) ? mxCreateDoubleScalar((double)iters[0]) : make(c.B, 1, 1);
+    if (c.B != 1) for (mwSize b = 0; b < c.B; ++b) mxGetPr(outs[4])[b] = (double)iters[b];
     const int nout = nlhs < 1 ? 1 : nlhs;
     for (int i = 0; i < 5; ++i) {
         if (i < nout) plhs[i] = outs[i]; else mxDestroyArray(outs[i]);

@@ -12,7 +12,7 @@ from conftest import ROOT, assert_pose_close, rel_frob_up_to_sign
 
 MEX = os.path.join(ROOT, "mex")
 BUILD = os.path.join(MEX, "_build")
-GATEWAYS = ["LinearTFTPoseEstimation", "LinearFPoseEstimation", "linearTFT", "linearF"]
+GATEWAYS = ["LinearTFTPoseEstimation", "LinearFPoseEstimation", "OptimFPoseEstimation", "linearTFT", "linearF", "optimF"]
 
 
 @pytest.fixture(scope="module")
@@ -52,6 +52,8 @@ def test_linearF_gateway_error_text_without_device(built, tmp_path):
     p = np.zeros((2, 7))
     out = _run(built, "linearF", 1, [(p.T, (2, 7)), (p.T, (2, 7))], str(tmp_path))
     assert isinstance(out, str) and out.startswith("MEXERROR TFT_vs_Fund:linearF|At least 8 correspondences are necessary")
+    out = _run(built, "optimF", 2, [(p.T, (2, 7)), (p.T, (2, 7))], str(tmp_path))                   # optimF.m:36-38
+    assert isinstance(out, str) and out.startswith("MEXERROR TFT_vs_Fund:linearF|At least 8 correspondences are necessary")
     out = _run(built, "LinearTFTPoseEstimation", 5, [(np.zeros((5, 20)).T, (5, 20)), (np.zeros((9, 3)).T, (9, 3))], str(tmp_path))
     assert isinstance(out, str) and "Corresp must be 6xN" in out
 
@@ -88,3 +90,21 @@ def test_estimator_gateways(built, tmp_path):
     assert outs[2].shape == (3, 4) and outs[3].shape == (3, 4)
     F = _run(built, "linearF", 1, [(C[0:2].T, (2, 20)), (C[2:4].T, (2, 20))], str(tmp_path))[0]
     assert rel_frob_up_to_sign(F, o.linearF(C[0:2], C[2:4])) < 1e-9
+
+
+@pytest.mark.gpu
+def test_optimf_gateways_match_golden(built, tmp_path):
+    """[R_t_2,R_t_3,Reconst,T,iter]=OptimFPoseEstimation(Corresp,CalM) and [F,iter]=optimF(p1,p2) through mexFunction."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "optimf_n20.npz"))
+    b = 17
+    C, CalM = g["Corresp"][b], g["CalM"][b]
+    outs = _run(built, "OptimFPoseEstimation", 5, [(C.T, (6, 20)), (CalM.T, (9, 3))], str(tmp_path))
+    assert [o.shape for o in outs] == [(3, 4), (3, 4), (3, 20), (3, 3, 3), (1, 1)]
+    assert outs[4][0, 0] == float(g["optf_iter"][b])
+    ref = (g["optf_Rt2"][b], g["optf_Rt3"][b], g["optf_Reconst"][b], g["optf_T"][b], 0.0)
+    assert_pose_close(ref, (outs[0], outs[1], outs[2], outs[3], 0.0))
+    F, it = _run(built, "optimF", 2, [(C[0:2].T, (2, 20)), (C[2:4].T, (2, 20))], str(tmp_path))
+    assert rel_frob_up_to_sign(F, g["optf_F_single"][b]) < 1e-9 and it[0, 0] == float(g["optf_iter_single"][b])
+    Cb = g["Corresp"][:4]
+    outs = _run(built, "OptimFPoseEstimation", 5, [(Cb.transpose(0, 2, 1), (6, 20, 4)), (CalM.T, (9, 3))], str(tmp_path))
+    assert outs[4].shape == (4, 1) and np.array_equal(outs[4][:, 0], g["optf_iter"][:4].astype(np.float64))

@@ -842,8 +842,9 @@ int tvf_sweep_run(tvf_handle_t h, int method, int64_t first_trial, int64_t B, in
                   const double* P, double hi_x, double hi_y, const double* calm, const double* Rt0_2, const double* Rt0_3,
                   double* table) {
     int rc = sweep_check(h, first_trial, B, n, noise_levels, L, P, table); if (rc) return rc;
-    if (!calm || !Rt0_2 || !Rt0_3 || (method != 1 && method != 7)) return fail(h, TVF_ERR_ARG, "method must be 1 (TFT) or 7 (F); calm/Rt0 required");
-    if (method == 7 && n < 8) return fail(h, TVF_ERR_TOO_FEW_POINTS, TVF_LINEARF_ERRMSG);
+    if (!calm || !Rt0_2 || !Rt0_3 || (method != 1 && method != 7 && method != 8))
+        return fail(h, TVF_ERR_ARG, "method must be 1 (linear TFT), 7 (linear F) or 8 (optimal F); calm/Rt0 required");
+    if (method != 1 && n < 8) return fail(h, TVF_ERR_TOO_FEW_POINTS, TVF_LINEARF_ERRMSG);
     TVF_CK(cudaSetDevice(h->device));
     Slot& s = h->slot[0];
     cudaStream_t st = s.stream;
@@ -864,8 +865,8 @@ int tvf_sweep_run(tvf_handle_t h, int method, int64_t first_trial, int64_t B, in
     for (int64_t done = 0; done < B; done += C) {
         const int64_t Bc = (B - done < C) ? (B - done) : C;
         rc = sweep_common(h, first_trial + done, Bc, n, noise_levels, L, P, hi_x, hi_y, b.in, st); if (rc) return rc;
-        rc = run_pose_chunk(h, st, method == 1 ? METHOD_TFT : METHOD_F, b.in, (const double*)pc, 0, n, Bc, b.T, b.F, b.core, b.cand,
-                            b.votes, b.scale, b.Rt2, b.Rt3, b.reconst, b.repr, b.status);
+        rc = run_pose_chunk(h, st, method == 1 ? METHOD_TFT : (method == 7 ? METHOD_F : METHOD_OPTF), b.in, (const double*)pc, 0, n,
+                            Bc, b.T, b.F, b.core, b.cand, b.votes, b.scale, b.Rt2, b.Rt3, b.reconst, b.repr, b.status, b.iters, nullptr);
         if (rc) return rc;
         launch_sweep_eval_accumulate(b.Rt2, b.Rt3, b.repr, b.status, first_trial + done, Bc, L, Q, (const double*)pr, (double*)pp, st);
         h->launches += 1;
