@@ -103,6 +103,15 @@ void hc_scene_trial(const double* P, int n, double noise, unsigned seed, double 
     scene_trial(rng, P, n, noise, seed, hi_x, hi_y, out, c, arr, outpos);
 }
 
+void hc_scene_seed(const double* P, int n, const double* noise_levels, int lv_lo, int lv_hi, unsigned seed, double hi_x,
+                   double hi_y, double* out) {
+    static MT19937 rng, snap;
+    static double clean[6 * SCENE_MAX_POINTS], z[6 * SCENE_MAX_POINTS], c[6 * SCENE_MAX_POINTS];
+    unsigned char arr[SCENE_MAX_POINTS];
+    signed char outpos[SCENE_MAX_POINTS];
+    scene_seed_levels(rng, snap, P, n, noise_levels, lv_lo, lv_hi, seed, hi_x, hi_y, out, clean, z, c, arr, outpos);
+}
+
 void hc_mt_streams(unsigned seed, int n, double* uniform, double* normal, unsigned* ints, unsigned maxv) {
     MT19937 r;
     r.seed(seed);

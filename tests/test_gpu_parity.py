@@ -412,6 +412,10 @@ def test_device_scene_generator(tvf):
     dev = scene.sweep_batch_device(B, 20, first_trial=1300)
     assert np.array_equal(host["noise"], dev["noise"]) and np.array_equal(host["seed"], dev["seed"])
     assert np.array_equal(host["Corresp"], dev["Corresp"])
+    # shard boundaries that cut through a seed's 13 levels
+    host = scene.sweep_batch(1000, 20, first_trial=1305)
+    dev = scene.sweep_batch_device(1000, 20, first_trial=1305)
+    assert np.array_equal(host["Corresp"], dev["Corresp"])
     # a shape with many inside-image rejections (second and third passes of the generator loop)
     host = scene.sweep_batch(260, 12, noise_levels=[3.0, 20.0, 60.0])
     dev = scene.sweep_batch_device(260, 12, noise_levels=[3.0, 20.0, 60.0])

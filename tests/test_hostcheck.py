@@ -105,6 +105,22 @@ def test_scene_generator_code_is_bit_exact_with_host_generator(hostcheck):
         hostcheck.hc_scene_trial(dp(P), 20, C.c_double(d["noise"][j]), C.c_uint(int(d["seed"][j])), C.c_double(1800.0),
                                  C.c_double(1200.0), dp(out))
         assert np.array_equal(out.T, d["Corresp"][j]), j
+    # the per-seed generator the CUDA kernel uses (first pass shared by the 13 levels) gives the same bits
+    lv = np.ascontiguousarray(np.arange(0.0, 3.0 + 1e-9, 0.25))
+    for seed in range(1, 13):
+        out = np.zeros((13, 20, 6))
+        hostcheck.hc_scene_seed(dp(P), 20, dp(lv), 0, 13, C.c_uint(seed), C.c_double(1800.0), C.c_double(1200.0), dp(out))
+        assert np.array_equal(out.transpose(0, 2, 1), d["Corresp"][13 * (seed - 1):13 * seed]), seed
+    out = np.zeros((4, 20, 6))                                  # a partial range of levels (shard boundaries)
+    hostcheck.hc_scene_seed(dp(P), 20, dp(lv), 5, 9, C.c_uint(3), C.c_double(1800.0), C.c_double(1200.0), dp(out))
+    assert np.array_equal(out.transpose(0, 2, 1), d["Corresp"][26 + 5:26 + 9])
+    # many refill passes and state regenerations inside them: huge noise
+    lvh = np.ascontiguousarray([3.0, 20.0, 60.0, 200.0, 500.0])
+    dh = scene.sweep_batch(5 * 6, 12, noise_levels=lvh)
+    for seed in range(1, 7):
+        out = np.zeros((5, 12, 6))
+        hostcheck.hc_scene_seed(dp(P), 12, dp(lvh), 0, 5, C.c_uint(seed), C.c_double(1800.0), C.c_double(1200.0), dp(out))
+        assert np.array_equal(out.transpose(0, 2, 1), dh["Corresp"][5 * (seed - 1):5 * seed]), seed
     # another shape: n = 12 (experiments.m's default N), high noise -> more rejections
     d = scene.sweep_batch(26, 12, noise_levels=[3.0, 20.0])
     for j in range(26):

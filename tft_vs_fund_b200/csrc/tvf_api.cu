@@ -19,7 +19,7 @@ using namespace tvf;
 namespace {
 
 constexpr int NSLOT = 3;
-constexpr int NSCRATCH = 12;
+constexpr int NSCRATCH = 16;
 constexpr int64_t DEFAULT_CHUNK = 65536;
 constexpr size_t ARENA_BUDGET = 384u << 20;   // bytes of per-slot work space the automatic chunk aims for
 
@@ -862,14 +862,23 @@ int tvf_sweep_run(tvf_handle_t h, int method, int64_t first_trial, int64_t B, in
     TVF_CK(cudaMemcpyAsync(pr, Rt0_2, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
     TVF_CK(cudaMemcpyAsync((double*)pr + 12, Rt0_3, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
     TVF_CK(cudaMemsetAsync(pp, 0, (size_t)L * Q * 5 * sizeof(double), st));
-    for (int64_t done = 0; done < B; done += C) {
-        const int64_t Bc = (B - done < C) ? (B - done) : C;
-        rc = sweep_common(h, first_trial + done, Bc, n, noise_levels, L, P, hi_x, hi_y, b.in, st); if (rc) return rc;
-        rc = run_pose_chunk(h, st, method == 1 ? METHOD_TFT : (method == 7 ? METHOD_F : METHOD_OPTF), b.in, (const double*)pc, 0, n,
-                            Bc, b.T, b.F, b.core, b.cand, b.votes, b.scale, b.Rt2, b.Rt3, b.reconst, b.repr, b.status, b.iters, nullptr);
-        if (rc) return rc;
-        launch_sweep_eval_accumulate(b.Rt2, b.Rt3, b.repr, b.status, first_trial + done, Bc, L, Q, (const double*)pr, (double*)pp, st);
-        h->launches += 1;
+    // The generator shares one pass per seed among its L noise levels (one thread per seed), so it wants many seeds
+    // per launch: trials are generated in super-chunks of up to 16 solver chunks into a staging buffer.
+    const int64_t G = (B < 16 * C) ? B : 16 * C;
+    void* pg;
+    rc = ensure_scratch(h, NSCRATCH - 7, (size_t)G * 6 * n * sizeof(double), &pg); if (rc) return rc;
+    for (int64_t gdone = 0; gdone < B; gdone += G) {
+        const int64_t Gc = (B - gdone < G) ? (B - gdone) : G;
+        rc = sweep_common(h, first_trial + gdone, Gc, n, noise_levels, L, P, hi_x, hi_y, (double*)pg, st); if (rc) return rc;
+        for (int64_t off = 0; off < Gc; off += C) {
+            const int64_t Bc = (Gc - off < C) ? (Gc - off) : C;
+            const double* d_in = (const double*)pg + off * 6 * n;
+            rc = run_pose_chunk(h, st, method == 1 ? METHOD_TFT : (method == 7 ? METHOD_F : METHOD_OPTF), d_in, (const double*)pc, 0, n,
+                                Bc, b.T, b.F, b.core, b.cand, b.votes, b.scale, b.Rt2, b.Rt3, b.reconst, b.repr, b.status, b.iters, nullptr);
+            if (rc) return rc;
+            launch_sweep_eval_accumulate(b.Rt2, b.Rt3, b.repr, b.status, first_trial + gdone + off, Bc, L, Q, (const double*)pr, (double*)pp, st);
+            h->launches += 1;
+        }
     }
     launch_sweep_eval_finish((const double*)pp, L, Q, (double*)pt, st);
     h->launches += 1;

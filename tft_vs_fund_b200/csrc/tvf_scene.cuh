@@ -76,6 +76,7 @@ struct MT19937 {
     uint32_t mt[624];
     int pos;
     int has_gauss;
+    int twists;          // state regenerations since seed(): lets a caller rewind cheaply when none happened
     double gauss;
 
     TVF_HD void seed(uint32_t s) {              // numpy mt19937_seed == init_genrand
@@ -83,7 +84,7 @@ struct MT19937 {
             mt[i] = s;
             s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
         }
-        pos = 624; has_gauss = 0; gauss = 0.0;
+        pos = 624; has_gauss = 0; gauss = 0.0; twists = 0;
     }
     TVF_HD void twist() {
         const uint32_t UPPER = 0x80000000u, LOWER = 0x7fffffffu, MATRIX = 0x9908b0dfu;
@@ -98,7 +99,7 @@ struct MT19937 {
         }
         const uint32_t y = (mt[623] & UPPER) | (mt[0] & LOWER);
         mt[623] = mt[396] ^ (y >> 1) ^ ((y & 1u) ? MATRIX : 0u);
-        pos = 0;
+        pos = 0; ++twists;
     }
     TVF_HD uint32_t next32() {
         if (pos == 624) twist();
@@ -184,6 +185,101 @@ TVF_HD void scene_trial(MT19937& rng, const double* P, int n, double noise, uint
             }
         }
         M = N - filled;                                                   // :110
+    }
+}
+
+// All L noise levels of ONE seed (experiments.m:91-95: the trials j = (seed-1)*L + lv share rng(seed)).  The first
+// pass of generateSyntheticScene's while-loop (:80-92) does not depend on the noise level -- same 3-D points, same
+// projections, same Gaussian draws, same number of variates consumed -- and neither does the sub-sample
+// permutation, so both are computed once; per level only the scaling by `noise`, the inside-image mask and the
+// (short) refill passes differ.  The refill passes continue from the stream position the first pass left: the
+// generator is rewound to a snapshot (just the read position unless a state regeneration happened in between).
+// Produces exactly the bits of scene_trial for every level.  Levels [lv_lo, lv_hi) are written to
+// out + (lv - lv_lo)*6*n.  Scratch: clean, z, c of 6*N doubles each; arr, outpos of N.
+TVF_HD void scene_seed_levels(MT19937& rng, MT19937& snap, const double* P, int n, const double* noise_levels, int lv_lo,
+                              int lv_hi, uint32_t seed, double hi_x, double hi_y, double* out, double* clean, double* z,
+                              double* c, unsigned char* arr, signed char* outpos) {
+    const int N = n + 100;
+    rng.seed(seed);
+    for (int i = 0; i < N; ++i) { arr[i] = (unsigned char)i; outpos[i] = -1; }
+    for (int i = N - 1; i >= 1; --i) {
+        const uint32_t j = rng.interval((uint32_t)i);
+        const unsigned char tmp = arr[i]; arr[i] = arr[j]; arr[j] = tmp;
+    }
+    for (int k = 0; k < n; ++k) outpos[arr[k]] = (signed char)k;
+    rng.seed(seed);
+    for (int i = 0; i < N; ++i) {                                         // first pass, noise-independent part
+        const double X = TVF_ADD(TVF_MUL(400.0, rng.res53()), -200.0);
+        const double Y = TVF_ADD(TVF_MUL(400.0, rng.res53()), -200.0);
+        const double Z = TVF_ADD(TVF_MUL(400.0, rng.res53()), -200.0);
+        for (int v = 0; v < 3; ++v) {
+            const double* Pv = P + 12 * v;
+            double x[3];
+            for (int r = 0; r < 3; ++r)
+                x[r] = TVF_ADD(TVF_ADD(TVF_ADD(TVF_MUL(Pv[4 * r], X), TVF_MUL(Pv[4 * r + 1], Y)), TVF_MUL(Pv[4 * r + 2], Z)), Pv[4 * r + 3]);
+            clean[6 * i + 2 * v] = TVF_DIV(x[0], x[2]);
+            clean[6 * i + 2 * v + 1] = TVF_DIV(x[1], x[2]);
+        }
+    }
+    for (int v = 0; v < 3; ++v)
+        for (int i = 0; i < N; ++i) { z[6 * i + 2 * v] = rng.normal(); z[6 * i + 2 * v + 1] = rng.normal(); }
+    snap = rng;
+    for (int lv = lv_lo; lv < lv_hi; ++lv) {
+        const double noise = noise_levels[lv];
+        double* o = out + (size_t)(lv - lv_lo) * 6 * n;
+        if (rng.twists != snap.twists) rng = snap;
+        else { rng.pos = snap.pos; rng.has_gauss = snap.has_gauss; rng.gauss = snap.gauss; }
+        int filled = 0;
+        for (int i = 0; i < N; ++i) {
+            double p[6];
+            bool inside = true;
+            for (int v = 0; v < 3; ++v) {
+                const double x = TVF_ADD(clean[6 * i + 2 * v], TVF_MUL(z[6 * i + 2 * v], noise));
+                const double y = TVF_ADD(clean[6 * i + 2 * v + 1], TVF_MUL(z[6 * i + 2 * v + 1], noise));
+                inside = inside && (x <= hi_x) && (y <= hi_y) && (x >= 0.0) && (y >= 0.0);
+                p[2 * v] = x; p[2 * v + 1] = y;
+            }
+            if (inside) {
+                const int k = outpos[filled++];
+                if (k >= 0)
+                    for (int q = 0; q < 6; ++q) o[6 * k + q] = p[q];
+            }
+        }
+        int M = N - filled;
+        while (M > 0) {                                                   // refill passes: as in scene_trial
+            for (int i = 0; i < M; ++i) {
+                const double X = TVF_ADD(TVF_MUL(400.0, rng.res53()), -200.0);
+                const double Y = TVF_ADD(TVF_MUL(400.0, rng.res53()), -200.0);
+                const double Z = TVF_ADD(TVF_MUL(400.0, rng.res53()), -200.0);
+                for (int v = 0; v < 3; ++v) {
+                    const double* Pv = P + 12 * v;
+                    double x[3];
+                    for (int r = 0; r < 3; ++r)
+                        x[r] = TVF_ADD(TVF_ADD(TVF_ADD(TVF_MUL(Pv[4 * r], X), TVF_MUL(Pv[4 * r + 1], Y)), TVF_MUL(Pv[4 * r + 2], Z)), Pv[4 * r + 3]);
+                    c[6 * i + 2 * v] = TVF_DIV(x[0], x[2]);
+                    c[6 * i + 2 * v + 1] = TVF_DIV(x[1], x[2]);
+                }
+            }
+            for (int v = 0; v < 3; ++v)
+                for (int i = 0; i < M; ++i) {
+                    const double z0 = rng.normal(), z1 = rng.normal();
+                    c[6 * i + 2 * v] = TVF_ADD(c[6 * i + 2 * v], TVF_MUL(z0, noise));
+                    c[6 * i + 2 * v + 1] = TVF_ADD(c[6 * i + 2 * v + 1], TVF_MUL(z1, noise));
+                }
+            for (int i = 0; i < M; ++i) {
+                bool inside = true;
+                for (int v = 0; v < 3; ++v) {
+                    const double x = c[6 * i + 2 * v], y = c[6 * i + 2 * v + 1];
+                    inside = inside && (x <= hi_x) && (y <= hi_y) && (x >= 0.0) && (y >= 0.0);
+                }
+                if (inside) {
+                    const int k = outpos[filled++];
+                    if (k >= 0)
+                        for (int q = 0; q < 6; ++q) o[6 * k + q] = c[6 * i + q];
+                }
+            }
+            M = N - filled;
+        }
     }
 }
 
