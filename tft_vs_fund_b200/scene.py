@@ -203,6 +203,7 @@ def _sweep_range(args):
         X = 400 * np.ascontiguousarray(rs.random_sample((M, 3)).T) - 200
         clean = np.vstack([_project(P, X) for P in Ps])
         Z = np.vstack([np.ascontiguousarray(polar_pairs(rs, M).T) for _ in range(3)])
+        after_first_pass = rs.get_state()                            # where every level's refill passes continue
         rs2.seed(seed)
         idx = rs2.permutation(M)[:n]                                 # experiments.m:94-95
         for lv in range(lv0, lv1):
@@ -218,8 +219,7 @@ def _sweep_range(args):
             Corresp = np.empty((6, M))
             Corresp[:, :keep.size] = c6[:, keep]
             filled = keep.size
-            rs.seed(seed)
-            rs.random_sample((M, 3)); polar_pairs(rs, 3 * M)
+            rs.set_state(after_first_pass)
             while filled < M:
                 m = M - filled
                 Xm = 400 * np.ascontiguousarray(rs.random_sample((m, 3)).T) - 200
