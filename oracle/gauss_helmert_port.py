@@ -134,3 +134,89 @@ def OptimFPoseEstimation(Corresp, CalM, return_F=False):
     if return_F:
         return R_t_2, R_t_3, Reconst, T, iter_, F21, F31
     return R_t_2, R_t_3, Reconst, T, iter_
+
+
+# --------------------------------------------------------------------------------------------------
+# FaugPapaTFTPoseEstimation (TFT_methods/FaugPapaTFTPoseEstimation.m): Gauss-Helmert on the 27 tensor entries with
+# the 12 Faugeras-Papadopoulo constraints
+# --------------------------------------------------------------------------------------------------
+def _minor(A, i, j):
+    """FaugPapaTFTPoseEstimation.m:150-153 (1-based i, j)."""
+    h, w = A.shape
+    rows = [r for r in range(h) if r != i - 1]; cols = [c for c in range(w) if c != j - 1]
+    return np.linalg.det(A[np.ix_(rows, cols)]) * (-1.0) ** (i + j)
+
+
+def constrGH_FaugPapa(obs, x, _y=None):
+    """FaugPapaTFTPoseEstimation.m:84-147 (local function constrGH): f, g, A, B, C, D."""
+    T = x.reshape(3, 3, 3, order='F')                               # :86
+    obs = obs.reshape(6, -1, order='F')                             # :87
+    N = obs.shape[1]                                                # :88
+    f = np.zeros(4 * N); A = np.zeros((4 * N, 27)); B = np.zeros((4 * N, 6 * N))   # :90-92
+    J = np.array([[0.0, 1.0], [1.0, 0.0]])
+    for i in range(N):                                              # :93
+        x1 = obs[0:2, i]; x2 = obs[2:4, i]; x3 = obs[4:6, i]        # :95
+        ind2 = 4 * i                                                # :98
+        S2 = np.array([[0.0, -1.0], [-1.0, 0.0], [x2[1], x2[0]]])   # :99
+        S3 = np.array([[0.0, -1.0], [-1.0, 0.0], [x3[1], x3[0]]])   # :100
+        f[ind2:ind2 + 4] = (S2.T @ (x1[0] * T[:, :, 0] + x1[1] * T[:, :, 1] + T[:, :, 2]) @ S3).reshape(4, order='F')   # :101
+        x1h = np.array([x1[0], x1[1], 1.0])
+        A[ind2:ind2 + 4, :] = np.kron(S3, S2).T @ np.kron(x1h.reshape(1, 3), np.eye(9))   # :104
+        B[ind2:ind2 + 4, 6 * i + 0] = (S2.T @ T[:, :, 0] @ S3).reshape(4, order='F')       # :105
+        B[ind2:ind2 + 4, 6 * i + 1] = (S2.T @ T[:, :, 1] @ S3).reshape(4, order='F')       # :106
+        B[ind2:ind2 + 4, 6 * i + 2:6 * i + 4] = np.kron((S3.T @ T[2, :, :].reshape(3, 3, order='F') @ x1h).reshape(2, 1), J)   # :107
+        B[ind2:ind2 + 4, 6 * i + 4:6 * i + 6] = np.kron(J, (S2.T @ T[:, 2, :].reshape(3, 3, order='F') @ x1h).reshape(2, 1))   # :108
+    g = np.zeros(12); C = np.zeros((12, 27)); D = np.zeros((12, 0))   # :111-113
+    for i in range(1, 4):                                           # :114
+        g[i - 1] = np.linalg.det(T[:, :, i - 1])                    # :115
+        for j in range(1, 4):
+            for k in range(1, 4):
+                C[i - 1, (j + 3 * (k - 1) + 9 * (i - 1)) - 1] = _minor(T[:, :, i - 1], j, k)   # :118
+    i = 0                                                           # :123
+    for k2 in range(1, 3):
+        for k3 in range(1, 3):
+            for l2 in range(k2 + 1, 4):
+                for l3 in range(k3 + 1, 4):
+                    i += 1                                          # :128
+                    t = lambda a, b: T[a - 1, b - 1, :]
+                    A1 = np.vstack([t(k2, k3), t(k2, l3), t(l2, l3)])   # :129 reshape of a 1x3x3 array: ROW r is the r-th vector
+                    A2 = np.vstack([t(k2, k3), t(l2, k3), t(l2, l3)])   # :130
+                    A3 = np.vstack([t(l2, k3), t(k2, l3), t(l2, l3)])   # :131
+                    A4 = np.vstack([t(k2, k3), t(l2, k3), t(k2, l3)])   # :132
+                    d1, d2, d3, d4 = (np.linalg.det(M_) for M_ in (A1, A2, A3, A4))
+                    g[3 + i - 1] = d1 * d2 - d3 * d4                # :133
+                    for i1 in range(1, 4):                          # :134
+                        col = lambda a, b: (a + 3 * (b - 1) + 9 * (i1 - 1)) - 1
+                        C[3 + i - 1, col(k2, k3)] = _minor(A1, i1, 1) * d2 + d1 * _minor(A2, i1, 1) - d3 * _minor(A4, i1, 1)   # :135-136
+                        C[3 + i - 1, col(k2, l3)] = _minor(A1, i1, 2) * d2 - _minor(A3, i1, 2) * d4 - d3 * _minor(A4, i1, 3)   # :137-138
+                        C[3 + i - 1, col(l2, l3)] = _minor(A1, i1, 3) * d2 + d1 * _minor(A2, i1, 3) - _minor(A3, i1, 3) * d4   # :139-140
+                        C[3 + i - 1, col(l2, k3)] = d1 * _minor(A2, i1, 2) - _minor(A3, i1, 1) * d4 - d3 * _minor(A4, i1, 2)   # :141-142
+    return f, g, A, B, C, D
+
+
+def FaugPapaTFTPoseEstimation(Corresp, CalM):
+    """TFT_methods/FaugPapaTFTPoseEstimation.m:48-80."""
+    from .reference_port import R_t_from_TFT, linearTFT, transform_TFT
+    Corresp = np.asarray(Corresp, dtype=np.float64); CalM = np.asarray(CalM, dtype=np.float64)
+    x1, Normal1 = Normalize2Ddata(Corresp[0:2, :])                  # :48-50
+    x2, Normal2 = Normalize2Ddata(Corresp[2:4, :])
+    x3, Normal3 = Normalize2Ddata(Corresp[4:6, :])
+    T, P1, P2, P3 = linearTFT(x1, x2, x3)                           # :53
+    points3D = triangulation3D([P1, P2, P3], np.vstack([x1, x2, x3]))   # :57
+    est = []
+    for P in (P1, P2, P3):                                          # :58-60
+        p = P @ points3D
+        est.append(p[0:2, :] / p[2:3, :])
+    N = x1.shape[1]                                                 # :63
+    param0 = T.reshape(27, order='F')                               # :64
+    obs = np.vstack([x1[0:2, :], x2[0:2, :], x3[0:2, :]]).reshape(6 * N, order='F')   # :65
+    obs_est = np.vstack(est).reshape(6 * N, order='F')              # :66
+    y = np.zeros(0)                                                 # :67
+    _, param, _, it = Gauss_Helmert(constrGH_FaugPapa, obs_est, param0, y, obs, np.eye(6 * N))   # :68
+    T = param.reshape(3, 3, 3, order='F')                           # :69
+    T = transform_TFT(T, Normal1, Normal2, Normal3, 1)              # :72
+    R_t_2, R_t_3 = R_t_from_TFT(T, CalM, Corresp)                   # :75
+    K1 = CalM[0:3, :]; K2 = CalM[3:6, :]; K3 = CalM[6:9, :]
+    Reconst = triangulation3D([K1 @ np.eye(3, 4), K2 @ R_t_2, K3 @ R_t_3], Corresp)   # :78
+    Reconst = Reconst[0:3, :] / Reconst[3:4, :]                     # :79
+    return R_t_2, R_t_3, Reconst, T, it

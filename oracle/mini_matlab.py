@@ -911,8 +911,15 @@ class Interpreter:
         return np.tile(_num(a[0]), reps)
 
     def bi_reshape(self, a, n):
-        shp = self._shape_args(a[1:])
-        return _num(a[0]).reshape(shp, order="F").copy()
+        v = _num(a[0])
+        dims = a[1:]
+        if len(dims) > 1 and any(_num(d).size == 0 for d in dims):        # reshape(x, 6, []): one dimension inferred
+            known = [None if _num(d).size == 0 else int(_scalar(d)) for d in dims]
+            prod = int(np.prod([k for k in known if k is not None])) if any(k is not None for k in known) else 1
+            shp = tuple(v.size // prod if k is None else k for k in known)
+        else:
+            shp = self._shape_args(dims)
+        return v.reshape(shp, order="F").copy()
 
     def bi_diag(self, a, n):
         v = _num(a[0])
