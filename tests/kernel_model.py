@@ -159,15 +159,19 @@ def dlt_null(rows, max_iter=40, tol=1e-15):
     x = np.linalg.solve(R, np.array([0, 0, 0, 1.0]))
     x /= np.linalg.norm(x)
     its = 0
+    dprev = 0.0
     for its in range(1, max_iter + 1):
         y = np.linalg.solve(R.T, x)
         z = np.linalg.solve(R, y)
         z /= np.linalg.norm(z)
         if z @ x < 0:
             z = -z
-        d = np.max(np.abs(z - x)); x = z
-        if d < tol:
+        d2 = float(np.sum((z - x) ** 2)); x = z
+        # tvf_math.cuh::dlt_null (TVF_DLT_PREDICT): stop on a change below 1e-13, or as soon as the error LEFT,
+        # |z - x| * rate with rate ~ |z - x| / |previous change|, is below 1e-14
+        if not d2 > 1e-26 or not d2 * d2 > 1e-28 * dprev:
             break
+        dprev = d2
     return x, its
 
 

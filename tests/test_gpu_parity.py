@@ -304,6 +304,38 @@ def test_large_n_cluster_tma_path(tvf, n):
     assert np.array_equal(one[3], res[3][0])
 
 
+@pytest.mark.parametrize("n,B", [(1100, 700), (2500, 300), (4003, 150)])
+def test_large_n_stream_many_scenes(tvf, n, B):
+    """Many scenes per cluster (the steady state of the streaming chunk ring: slot recycling, rotating finaliser,
+    barrier phase wrap-around).  Scene b is a copy of scene b % 5, so every copy must give the SAME BITS wherever it
+    lands in a cluster's stream (the per-scene summation order is fixed).  The tensor of each original is checked
+    against the generic warp-per-problem estimator (tvf.linearTFT on oracle-normalised points, undone with the
+    oracle's transform_TFT), and at the smallest size the whole pose against the oracle (its full SVD is too slow
+    for more)."""
+    base = []
+    for s_ in range(1, 6):
+        CalM, R_t0, C, _ = o.generateSyntheticScene(n, 1.0, s_, 50, 0)
+        base.append(C)
+    base = np.stack(base)
+    Cs = base[np.arange(B) % 5]
+    res = tvf.LinearTFTPoseEstimation(Cs, CalM)
+    assert np.all(res.status == 0)
+    for k in range(5):
+        same = res[3][k::5]
+        assert np.array_equal(same, np.broadcast_to(same[0], same.shape)), "scene copies of %d differ" % k
+        assert np.array_equal(res.repr_err[k::5], np.full(same.shape[0], res.repr_err[k]))
+        xs, Ns = zip(*[o.Normalize2Ddata(base[k][2 * v:2 * v + 2]) for v in range(3)])
+        Tn = tvf.linearTFT(*xs)[0]
+        T = o.transform_TFT(Tn, Ns[0], Ns[1], Ns[2], 1)
+        assert rel_frob_up_to_sign(T, res[3][k]) < TOL_MODEL, "stream n=%d scene %d" % (n, k)
+    if n <= 1100:
+        K = CalM[:3]
+        R2, R3, Rec, T, _ = o.LinearTFTPoseEstimation(base[0], CalM)
+        rep = o.ReprError([K @ np.eye(3, 4), K @ R2, K @ R3], base[0], Rec)
+        assert_pose_close((R2, R3, Rec, T, rep), (res[0][0], res[1][0], res[2][0], res[3][0], res.repr_err[0]),
+                          "stream n=%d scene 0" % n)
+
+
 def test_large_n_config5_golden(tvf):
     """BASELINE config 5 shape (n = 10 000): CUDA path vs the oracle outputs stored in tests/golden/large_n10000.npz
     (the oracle needs ~90 s per scene at this size; inputs are regenerated from the seed)."""

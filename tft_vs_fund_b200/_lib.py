@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtvf.so")
+# TVF_LIBPATH: development switch (benchmarking compile-time variants of the library); never a CPU fallback
+LIB_PATH = os.environ.get("TVF_LIBPATH") or os.path.join(_HERE, "libtvf.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -20,7 +20,25 @@
 
 namespace tvf {
 
-constexpr int CORE_WARPS = 4;
+// Launch-shape knobs of the estimator kernels.  The defaults are the measured optimum on B200 (tools/build_variants.py
+// builds the alternatives, profiles/r01_variants.md has the sweep): 4 warps per CTA, 5 CTAs per SM (96 registers), warps
+// of a CTA kept in step.
+#ifndef TVF_CORE_WARPS
+#define TVF_CORE_WARPS 4
+#endif
+#ifndef TVF_CORE_MINB
+#define TVF_CORE_MINB 5
+#endif
+#ifndef TVF_STEP_SYNC
+#define TVF_STEP_SYNC 1
+#endif
+#if TVF_STEP_SYNC
+#define STEP_SYNC() __syncthreads()
+#else
+#define STEP_SYNC() ((void)0)
+#endif
+constexpr int CORE_WARPS = TVF_CORE_WARPS;
+constexpr int CORE_MINB = TVF_CORE_MINB;      // resident CTAs per SM the estimator kernels are compiled for
 constexpr int FEAT_STRIDE = 15;   // 14 features + 1 pad: conflict-free 64-bit lane-strided stores
 
 // per-problem work-space record handed from stage to stage (doubles)
@@ -203,17 +221,18 @@ __device__ __forceinline__ void solve_from_moments(Stage1Scratch& sc, const unsi
 }
 
 template <bool PACKED, bool REFINE>
-__global__ void __launch_bounds__(CORE_WARPS * 32, REFINE ? 3 : 5)
+__global__ void __launch_bounds__(CORE_WARPS * 32, REFINE ? 3 : CORE_MINB)
 tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
     __shared__ Stage1Scratch scratch[CORE_WARPS];
     __shared__ unsigned char gidx[32 * 27];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     build_gidx(gidx);
+    __syncthreads();
     Stage1Scratch& sc = scratch[warp];
     const int beta = (lane >> 2) & 3, gamma = lane & 3, alpha0 = lane >> 4;
 
     for (long long base = (long long)blockIdx.x * CORE_WARPS; base < in.B; base += (long long)gridDim.x * CORE_WARPS) {
-        __syncthreads();             // keeps the CTA's warps in step: they share instruction-cache lines
+        STEP_SYNC();                 // keeps the CTA's warps in step: they share instruction-cache lines
         const long long prob = base + warp;
         if (prob >= in.B) continue;
         double* rec = ws + prob * CORE_WS_TFT;
@@ -266,15 +285,16 @@ tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ statu
 
 // Large-n path: the moments were produced by tft_moments_large_kernel (tvf_large_kernels.cu); this is the
 // second half of stage 1 on its own (27x27 Gram from the 96 moments -> null vector).
-__global__ void __launch_bounds__(CORE_WARPS * 32, 5)
+__global__ void __launch_bounds__(CORE_WARPS * 32, CORE_MINB)
 tft_stage1_solve_kernel(long long B, double* __restrict__ ws, int* __restrict__ status) {
     __shared__ Stage1Scratch scratch[CORE_WARPS];
     __shared__ unsigned char gidx[32 * 27];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     build_gidx(gidx);
+    __syncthreads();
     Stage1Scratch& sc = scratch[warp];
     for (long long base = (long long)blockIdx.x * CORE_WARPS; base < B; base += (long long)gridDim.x * CORE_WARPS) {
-        __syncthreads();
+        STEP_SYNC();
         const long long prob = base + warp;
         if (prob >= B) continue;
         double* rec = ws + prob * CORE_WS_TFT;
@@ -311,7 +331,7 @@ struct __align__(16) Stage2Scratch {
 };
 
 template <bool PACKED, bool REFINE>
-__global__ void __launch_bounds__(CORE_WARPS * 32, REFINE ? 3 : 5)
+__global__ void __launch_bounds__(CORE_WARPS * 32, REFINE ? 3 : CORE_MINB)
 tft_stage2_kernel(CoreInput in, const double* __restrict__ ws, double* __restrict__ Tout,
                   double* __restrict__ P2out, double* __restrict__ P3out, int* __restrict__ status) {
     const int normalize = in.normalize;
@@ -320,11 +340,12 @@ tft_stage2_kernel(CoreInput in, const double* __restrict__ ws, double* __restric
     __shared__ unsigned char gidx[32 * 27];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     build_gidx(gidx);
+    __syncthreads();
     Stage2Scratch& sc = scratch[warp];
     const int jr = lane % 3, kr = (lane / 3) % 3, ir = (lane < 27) ? lane / 9 : 0;
 
     for (long long base = (long long)blockIdx.x * CORE_WARPS; base < B; base += (long long)gridDim.x * CORE_WARPS) {
-        __syncthreads();
+        STEP_SYNC();
         const long long prob = base + warp;
         if (prob >= B) continue;
         const double* rec = ws + prob * CORE_WS_TFT;
@@ -425,7 +446,7 @@ tft_stage2_kernel(CoreInput in, const double* __restrict__ ws, double* __restric
                 const double* tp = sc.tp + 5 * ir;
                 acc = pe * (qe * tp[0] + qv1 * tp[1] + qv2 * tp[2]) + qe * (pu1 * tp[3] + pu2 * tp[4]);
             }
-            tl2 = acc * rsqrt(warp_sum(acc * acc));
+            tl2 = acc * rsqrt_(warp_sum(acc * acc));
         }
         if (lane < 27) sc.T[lane] = tl2;
         __syncwarp();
@@ -474,7 +495,7 @@ tft_stage2_kernel(CoreInput in, const double* __restrict__ ws, double* __restric
                         acc = fma(sc.Nm[9 + jr + 3 * a] * sc.Nm[18 + kr + 3 * b], sab, acc);
                     }
             }
-            tout = acc * rsqrt(warp_sum(acc * acc));                                         // :49
+            tout = acc * rsqrt_(warp_sum(acc * acc));                                         // :49
         }
         if (lane < 27) Tout[prob * 27 + lane] = tout;
         if (status != nullptr && lane == 0 && st != 0) status[prob] |= st;
@@ -490,7 +511,7 @@ struct __align__(16) FScratch {
 
 // mode: in.normalize != 0 -> pose path (two pairs 1-2 and 1-3, outer normalisation); else one pair
 template <bool PACKED, bool REFINE>
-__global__ void __launch_bounds__(CORE_WARPS * 32, REFINE ? 3 : 5)
+__global__ void __launch_bounds__(CORE_WARPS * 32, REFINE ? 3 : CORE_MINB)
 f_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
     __shared__ FScratch scratch[CORE_WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -501,7 +522,7 @@ f_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status)
     const int ar = (lane < 9) ? lane / 3 : 0, br = (lane < 9) ? lane % 3 : 0;
 
     for (long long base = (long long)blockIdx.x * CORE_WARPS; base < in.B; base += (long long)gridDim.x * CORE_WARPS) {
-        __syncthreads();
+        STEP_SYNC();
         const long long prob = base + warp;
         if (prob >= in.B) continue;
         double* rec = ws + prob * CORE_WS_F;
@@ -608,7 +629,7 @@ f_finish_kernel(const double* __restrict__ ws, int normalize, long long B, doubl
 // ---------------------------------------------------------------------------
 static inline unsigned core_grid(long long B, int sm_count) {
     long long blocks = (B + CORE_WARPS - 1) / CORE_WARPS;
-    const long long cap = (long long)sm_count * 5 * 4;
+    const long long cap = (long long)sm_count * CORE_MINB * 4;
     if (blocks > cap) blocks = cap;
     return (unsigned)(blocks < 1 ? 1 : blocks);
 }

@@ -222,7 +222,10 @@ final_kernel(PoseTailArgs a) {
 // in shared memory (36 doubles per problem), not in registers, between the phases.
 constexpr int FUSED_MAX_PPB = PT_THREADS / TAIL_FUSED_MIN_N;     // 36 problems per CTA at most
 
-__global__ void __launch_bounds__(PT_THREADS, 2)
+#ifndef TVF_TAIL_MINB
+#define TVF_TAIL_MINB 2
+#endif
+__global__ void __launch_bounds__(PT_THREADS, TVF_TAIL_MINB)
 pose_tail_fused_kernel(PoseTailArgs a) {
     __shared__ int sv[FUSED_MAX_PPB * 4];       // per local problem: vote(R,t), vote(Rp,t) for pairs 2 and 3
     __shared__ int snan[FUSED_MAX_PPB];

@@ -23,6 +23,10 @@ namespace tvf {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int EIG_MAX_ITER = 80;
+#ifndef TVF_EIG_TOL
+#define TVF_EIG_TOL 4.0e-15
+#endif
+constexpr double EIG_TOL = TVF_EIG_TOL;      // largest component change of the unit eigenvector between two steps
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
 
@@ -114,7 +118,7 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
     }
     __syncwarp();                              // last sweep's row buffer is reused below
     // g now holds -(G + delta I)^-1 (scaled).  Power iteration on its negative.
-    double x = (lane < N) ? rsqrt((double)N) : 0.0;
+    double x = (lane < N) ? rsqrt_((double)N) : 0.0;
     bool ok = false;
 #pragma unroll 1
     for (int it = 0; it < EIG_MAX_ITER; ++it) {
@@ -130,10 +134,10 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
             if (2 * m2 + 1 < N) z1 = fma(g[2 * m2 + 1], r.y, z1);
         }
         double z = -(z0 + z1);
-        z *= rsqrt(warp_sum(z * z));
-        const double diff = warp_max(fabs(z - x));
+        z *= rsqrt_(warp_sum(z * z));
+        const bool moving = fabs(z - x) > EIG_TOL;            // max_lane |z - x| > tol, as one warp vote
         x = z;
-        if (!(diff > 4.0e-15)) { ok = true; break; }
+        if (!__any_sync(FULL, moving)) { ok = true; break; }
     }
     for (int step = 0; step < nrefine; ++step) {
         __syncwarp();
@@ -154,7 +158,7 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
             if (2 * m2 + 1 < N) z1 = fma(g[2 * m2 + 1], rr.y, z1);
         }
         x += z0 + z1;                                        // g holds -(G+dI)^-1
-        x *= rsqrt(warp_sum(x * x));
+        x *= rsqrt_(warp_sum(x * x));
     }
     *converged = ok;
     return x;
