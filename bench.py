@@ -245,6 +245,8 @@ def run_gpu(args, rank, local_rank, world):
     lib = h.lib
     stream = torch.cuda.Stream(device=dev)
     h.call("tvf_set_stream", C.c_void_p(stream.cuda_stream))
+    if args.chunk > 0:
+        h.call("tvf_set_chunk", args.chunk)
 
     # 3. inputs generated on the device (tvf_generate_sweep_dev: one thread per trial), outputs preallocated
     t_gen = time.perf_counter()
@@ -591,6 +593,7 @@ def main():
     ap.add_argument("--n", type=int, default=20)
     ap.add_argument("--cpu-sample", type=int, default=0, help="trials in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--chunk", type=int, default=0, help="problems per launch (0 = the library's default)")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "large-n"],
                     help="sweep = BASELINE config 3/4 (headline); large-n = config 5 (use with --n 10000 --trials 65536)")
     args = ap.parse_args()

@@ -28,6 +28,38 @@ struct PointMap {
     }
 };
 
+#ifndef TVF_TAIL_SERIAL_SUM
+#define TVF_TAIL_SERIAL_SUM 1
+#endif
+
+// Sums of the tpp partials of each problem in TWO arrays at once, result at lpt==0.  Up to 32 points per problem the
+// owner thread adds them in index order after ONE barrier (a fixed order, so still bit-reproducible); the log-depth
+// tree of seg_reduce costs a CTA barrier per level, which is what the fused tail was waiting on.
+__device__ __forceinline__ void seg_reduce2(double* ra, double* rb, const PointMap& m) {
+#if TVF_TAIL_SERIAL_SUM
+    if (m.tpp <= 32) {
+        __syncthreads();
+        if (m.lp < m.ppb && m.lpt == 0) {
+            double a = ra[threadIdx.x], b = rb[threadIdx.x];
+            for (int i = 1; i < m.tpp; ++i) { a += ra[threadIdx.x + i]; b += rb[threadIdx.x + i]; }
+            ra[threadIdx.x] = a; rb[threadIdx.x] = b;
+        }
+        __syncthreads();
+        return;
+    }
+#endif
+    int s = 1;
+    while (s < m.tpp) s <<= 1;
+    for (s >>= 1; s >= 1; s >>= 1) {
+        __syncthreads();
+        if (m.lp < m.ppb && m.lpt < s && m.lpt + s < m.tpp) {
+            ra[threadIdx.x] += ra[threadIdx.x + s];
+            rb[threadIdx.x] += rb[threadIdx.x + s];
+        }
+    }
+    __syncthreads();
+}
+
 // fixed-shape tree over the tpp partials of each problem; result lands at lpt==0
 __device__ __forceinline__ void seg_reduce(double* red, const PointMap& m) {
     int s = 1;
@@ -44,7 +76,13 @@ __device__ __forceinline__ const double* calm_of(const PoseTailArgs& a, long lon
 }
 
 // ------------------------------------------------------------------ candidates
-__global__ void __launch_bounds__(128, 4)
+#ifndef TVF_CAND_STORE128
+#define TVF_CAND_STORE128 1
+#endif
+#ifndef TVF_CAND_THREADS
+#define TVF_CAND_THREADS 128
+#endif
+__global__ void __launch_bounds__(TVF_CAND_THREADS, 512 / TVF_CAND_THREADS)
 candidates_kernel(int mode, const double* __restrict__ model, PoseTailArgs a) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
@@ -65,8 +103,16 @@ candidates_kernel(int mode, const double* __restrict__ model, PoseTailArgs a) {
         for (int i = 0; i < 18; ++i) F[i] = model[b * 18 + i];
         st = candidates_from_f(F, F + 9, calm, cand);
     }
+#if TVF_CAND_STORE128
+    {   // the record is 672 bytes and the arena 256-byte aligned: 42 128-bit stores instead of 84 64-bit ones
+        double2* dst = reinterpret_cast<double2*>(a.cand + b * CAND_SIZE);
+#pragma unroll
+        for (int i = 0; i < CAND_SIZE / 2; ++i) dst[i] = make_double2(cand[2 * i], cand[2 * i + 1]);
+    }
+#else
 #pragma unroll
     for (int i = 0; i < CAND_SIZE; ++i) a.cand[b * CAND_SIZE + i] = cand[i];
+#endif
     if (a.status != nullptr && st != 0) a.status[b] |= st;
 }
 
@@ -301,8 +347,7 @@ pose_tail_fused_kernel(PoseTailArgs a) {
             den = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
         }
         red0[threadIdx.x] = num; red1[threadIdx.x] = den;
-        seg_reduce(red0, m);
-        seg_reduce(red1, m);
+        seg_reduce2(red0, red1, m);
         const bool ok = ((sel & 15) != 15) && ((sel >> 4) != 15);
         if (live && m.lpt == 0) {
             const double lam = -red0[threadIdx.x] / red1[threadIdx.x];
@@ -342,8 +387,8 @@ pose_tail_fused_kernel(PoseTailArgs a) {
                 dst[0] = ok ? X[0] : qnan; dst[1] = ok ? X[1] : qnan; dst[2] = ok ? X[2] : qnan;
             }
         }
-        red0[threadIdx.x] = sq;
-        seg_reduce(red0, m);
+        red0[threadIdx.x] = sq; red1[threadIdx.x] = 0.0;
+        seg_reduce2(red0, red1, m);
         if (live && m.lpt == 0) {
             const double err = sqrt(red0[threadIdx.x] / (3.0 * (double)a.n));       // ReprError.m:65
             if (a.repr_err != nullptr) a.repr_err[b] = ok ? err : qnan;
@@ -598,7 +643,7 @@ static inline unsigned grid_for(long long work, int per_block, long long cap) {
 
 void launch_candidates(int mode, const double* model, const PoseTailArgs& a, cudaStream_t stream) {
     if (a.B <= 0) return;
-    candidates_kernel<<<grid_for(a.B, 128, 1LL << 30), 128, 0, stream>>>(mode, model, a);
+    candidates_kernel<<<grid_for(a.B, TVF_CAND_THREADS, 1LL << 30), TVF_CAND_THREADS, 0, stream>>>(mode, model, a);
 }
 
 static inline unsigned tail_grid(const PoseTailArgs& a, int sm_count) {

@@ -23,6 +23,9 @@ namespace tvf {
 
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int EIG_MAX_ITER = 80;
+#ifndef TVF_EIG_PIVOTNORM
+#define TVF_EIG_PIVOTNORM 1
+#endif
 #ifndef TVF_EIG_TOL
 #define TVF_EIG_TOL 4.0e-15
 #endif
@@ -118,8 +121,38 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
     }
     __syncwarp();                              // last sweep's row buffer is reused below
     // g now holds -(G + delta I)^-1 (scaled).  Power iteration on its negative.
-    double x = (lane < N) ? rsqrt_((double)N) : 0.0;
     bool ok = false;
+#if TVF_EIG_PIVOTNORM
+    // The iterate is kept normalised to "largest component = 1": the pivot lane comes from one REDUX over the high
+    // words and a ballot, its value from one shuffle, so the serial chain product -> normalise -> vote is a broadcast and
+    // a reciprocal instead of a five-level shuffle reduction and a reciprocal square root.  Dividing by the signed pivot
+    // also removes the sign flip of -M.  One exact 2-norm normalisation follows the loop.
+    double x = (lane < N) ? 1.0 : 0.0;
+#pragma unroll 1
+    for (int it = 0; it < EIG_MAX_ITER; ++it) {
+        double* buf = sbuf + (it & 1) * 32;
+        if (lane < NP) buf[lane] = x;
+        __syncwarp();
+        const double2* b2 = reinterpret_cast<const double2*>(buf);
+        double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+        for (int m2 = 0; m2 < NP / 2; ++m2) {
+            const double2 r = b2[m2];
+            if (2 * m2 < N) z0 = fma(g[2 * m2], r.x, z0);
+            if (2 * m2 + 1 < N) z1 = fma(g[2 * m2 + 1], r.y, z1);
+        }
+        double z = z0 + z1;
+        const unsigned hz = (unsigned)__double2hiint(z) & 0x7fffffffu;
+        const unsigned hmax = __reduce_max_sync(FULL, hz);
+        const int piv = __ffs(__ballot_sync(FULL, hz == hmax)) - 1;
+        z *= fast_rcp(shfl_d(z, piv));
+        const bool moving = fabs(z - x) > EIG_TOL;            // max_lane |z - x| > tol, as one warp vote
+        x = z;
+        if (!__any_sync(FULL, moving)) { ok = true; break; }
+    }
+    x *= rsqrt_(warp_sum(x * x));
+#else
+    double x = (lane < N) ? rsqrt_((double)N) : 0.0;
 #pragma unroll 1
     for (int it = 0; it < EIG_MAX_ITER; ++it) {
         double* buf = sbuf + (it & 1) * 32;
@@ -139,6 +172,7 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
         x = z;
         if (!__any_sync(FULL, moving)) { ok = true; break; }
     }
+#endif
     for (int step = 0; step < nrefine; ++step) {
         __syncwarp();
         if (lane < NP) sbuf[lane] = x;

@@ -11,10 +11,9 @@ from tft_vs_fund_b200 import build as B   # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "norsq": ["-DTVF_FAST_RSQRT=0"],
-    "nopred": ["-DTVF_DLT_PREDICT=0"],
-    "nopair": ["-DTVF_EIG_PAIR=0"],
-    "w15": ["-DTVF_W_STRIDE=15"],
+    "st64": ["-DTVF_CAND_STORE128=0"],
+    "cand64": ["-DTVF_CAND_THREADS=64"],
+    "cand256": ["-DTVF_CAND_THREADS=256"],
 }
 
 
