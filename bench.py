@@ -332,83 +332,91 @@ def run_gpu(args, rank, local_rank, world):
     value = world * B * args.steps / (ms * 1e-3)
     rep_device_path = d_rep.cpu().numpy()
 
-    # F method, same inputs (reported beside the headline)
-    for _ in range(3):
-        step_f()
-    ms_f, _ = timed(step_f, max(3, args.steps // 2))
-    f_value = world * B * max(3, args.steps // 2) / (ms_f * 1e-3)
-
-    # OptimFPoseEstimation (Gauss-Helmert refinement of both F), same inputs
-    optf_steps = max(3, args.steps // 4)
-    for _ in range(2):
-        step_optf()
-    ms_o, prof_o = timed(step_optf, optf_steps, profile=True)
-    optf_value = world * B * optf_steps / (ms_o * 1e-3)
-    optf_iters = float(d_iter.double().mean().item())
-    gh_ms = prof_o.get("optimf_gh_kernel", (float("nan"), 1)) if prof_o else (float("nan"), 1)
-
-    # 5. end to end through the host-pointer C ABI: pinned host buffers, H2D + kernels + D2H inside the timed region
-    lib.tvf_host_alloc.restype = C.c_void_p
-
-    def pinned(shape, dtype=np.float64):
-        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        p = lib.tvf_host_alloc(nbytes)
-        if not p:
-            raise RuntimeError("tvf_host_alloc failed")
-        buf = (C.c_char * nbytes).from_address(p)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape), p
-
-    h_in, p0 = pinned((B, n, 6)); h_in[...] = corresp_host
-    h_calm = np.ascontiguousarray(CalM.T)
-    h_Rt2, p1 = pinned((B, 12)); h_Rt3, p2 = pinned((B, 12)); h_rec, p3 = pinned((B, 3 * n))
-    h_T, p4 = pinned((B, 27)); h_rep, p5 = pinned((B,)); h_st, p6 = pinned((B,), np.int32)
-    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
-
-    def step_e2e():
-        return h.call("tvf_linear_tft_pose", dp(h_in), dp(h_calm), 0, n, B, dp(h_Rt2), dp(h_Rt3), dp(h_rec), dp(h_T),
-                      dp(h_rep), h_st.ctypes.data_as(_lib.c_int32_p))
-
-    for _ in range(2):
-        step_e2e()
-    e2e_steps = max(3, min(args.steps, 10))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    torch.cuda.synchronize(dev)
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    barrier()
-    e2e_value = world * B * e2e_steps / dt
-    e2e_check = float(np.abs(h_rep - rep_device_path).max())       # host path and device path agree bit for bit
+    full = args.legs == "all"
+    f_value = ms_f = optf_value = ms_o = optf_iters = e2e_value = e2e_check = sweep_value = None
+    optf_steps = e2e_steps = 0
+    gh_ms = (float("nan"), 1)
     h2d = B * n * 6 * 8 + 27 * 8
     d2h = B * (12 + 12 + 3 * n + 27 + 1) * 8 + B * 4
-    for p in (p0, p1, p2, p3, p4, p5, p6):
-        lib.tvf_host_free(C.c_void_p(p))
+    table = np.zeros((13, 5))
+    if full:
+        # F method, same inputs (reported beside the headline)
+        for _ in range(3):
+            step_f()
+        ms_f, _ = timed(step_f, max(3, args.steps // 2))
+        f_value = world * B * max(3, args.steps // 2) / (ms_f * 1e-3)
 
-    # 5b. the whole inner loop of experiments.m device-resident (generate + solve + per-level reduction; only a
-    #     13 x 5 table crosses the bus): tvf_sweep_run
-    K_, Ps_, Rt0_ = scene.scene_cameras(50, 0)
-    lv = np.ascontiguousarray(np.arange(0.0, 3.0 + 1e-9, 0.25)); Pm = np.ascontiguousarray(np.stack(Ps_))
-    g2 = np.ascontiguousarray(Rt0_[0].T); g3 = np.ascontiguousarray(Rt0_[1].T); table = np.zeros((lv.size, 5))
+        # OptimFPoseEstimation (Gauss-Helmert refinement of both F), same inputs
+        optf_steps = max(3, args.steps // 4)
+        for _ in range(2):
+            step_optf()
+        ms_o, prof_o = timed(step_optf, optf_steps, profile=True)
+        optf_value = world * B * optf_steps / (ms_o * 1e-3)
+        optf_iters = float(d_iter.double().mean().item())
+        gh_ms = prof_o.get("optimf_gh_kernel", (float("nan"), 1)) if prof_o else (float("nan"), 1)
 
-    def step_sweep():
-        h.call("tvf_sweep_run", 1, rank * B, B, n, dp(lv), lv.size, dp(Pm), 1800.0, 1200.0, dp(h_calm), dp(g2), dp(g3), dp(table))
+        # 5. end to end through the host-pointer C ABI: pinned host buffers, H2D + kernels + D2H inside the timed region
+        lib.tvf_host_alloc.restype = C.c_void_p
 
-    step_sweep()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(3):
+        def pinned(shape, dtype=np.float64):
+            nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+            p = lib.tvf_host_alloc(nbytes)
+            if not p:
+                raise RuntimeError("tvf_host_alloc failed")
+            buf = (C.c_char * nbytes).from_address(p)
+            return np.frombuffer(buf, dtype=dtype).reshape(shape), p
+
+        h_in, p0 = pinned((B, n, 6)); h_in[...] = corresp_host
+        h_calm = np.ascontiguousarray(CalM.T)
+        h_Rt2, p1 = pinned((B, 12)); h_Rt3, p2 = pinned((B, 12)); h_rec, p3 = pinned((B, 3 * n))
+        h_T, p4 = pinned((B, 27)); h_rep, p5 = pinned((B,)); h_st, p6 = pinned((B,), np.int32)
+        dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
+
+        def step_e2e():
+            return h.call("tvf_linear_tft_pose", dp(h_in), dp(h_calm), 0, n, B, dp(h_Rt2), dp(h_Rt3), dp(h_rec), dp(h_T),
+                          dp(h_rep), h_st.ctypes.data_as(_lib.c_int32_p))
+
+        for _ in range(2):
+            step_e2e()
+        e2e_steps = max(3, min(args.steps, 10))
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            step_e2e()
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        barrier()
+        e2e_value = world * B * e2e_steps / dt
+        e2e_check = float(np.abs(h_rep - rep_device_path).max())       # host path and device path agree bit for bit
+        h2d = B * n * 6 * 8 + 27 * 8
+        d2h = B * (12 + 12 + 3 * n + 27 + 1) * 8 + B * 4
+        for p in (p0, p1, p2, p3, p4, p5, p6):
+            lib.tvf_host_free(C.c_void_p(p))
+
+        # 5b. the whole inner loop of experiments.m device-resident (generate + solve + per-level reduction; only a
+        #     13 x 5 table crosses the bus): tvf_sweep_run
+        K_, Ps_, Rt0_ = scene.scene_cameras(50, 0)
+        lv = np.ascontiguousarray(np.arange(0.0, 3.0 + 1e-9, 0.25)); Pm = np.ascontiguousarray(np.stack(Ps_))
+        g2 = np.ascontiguousarray(Rt0_[0].T); g3 = np.ascontiguousarray(Rt0_[1].T); table = np.zeros((lv.size, 5))
+
+        def step_sweep():
+            h.call("tvf_sweep_run", 1, rank * B, B, n, dp(lv), lv.size, dp(Pm), 1800.0, 1200.0, dp(h_calm), dp(g2), dp(g3), dp(table))
+
         step_sweep()
-    dt_sweep = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt_sweep], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt_sweep = float(t.item())
-    sweep_value = world * B * 3 / dt_sweep
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            step_sweep()
+        dt_sweep = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt_sweep], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt_sweep = float(t.item())
+        sweep_value = world * B * 3 / dt_sweep
 
     if rank != 0:
         if world > 1:
@@ -471,20 +479,22 @@ def run_gpu(args, rank, local_rank, world):
         "roofline": roofline, "roofline_step": roofline_step, "roofline_hbm": roofline_hbm,
         "kernels": per_kernel,
         "cpu_baseline": cpu_baseline,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_check,
-                "api": "tvf_linear_tft_pose (host pointers, pinned; chunked H2D/compute/D2H over 3 streams)"},
+        "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                 "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_check,
+                 "api": "tvf_linear_tft_pose (host pointers, pinned; chunked H2D/compute/D2H over 3 streams)"} if full else None),
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "f_method": {"metric": "3-view linear F pose solves/sec (LinearFPoseEstimation + ReprError)", "value": f_value,
-                     "unit": UNIT, "ms_per_step": ms_f / max(3, args.steps // 2),
-                     "roofline_step_frac_fp64": f_flops(n) * B / (ms_f * 1e-3 / max(3, args.steps // 2)) / 1e12 / fp64_peak},
-        "optimf_method": {"metric": "3-view optimal-F pose solves/sec (OptimFPoseEstimation + ReprError)", "value": optf_value,
-                          "unit": UNIT, "ms_per_step": ms_o / optf_steps, "mean_gauss_helmert_iterations_per_solve": optf_iters,
-                          "optimf_gh_kernel_share": gh_ms[0] / ms_o if ms_o > 0 else None},
-        "device_resident_sweep": {"api": "tvf_sweep_run: trials generated, solved and reduced per noise level on the device",
-                                  "value": sweep_value, "unit": UNIT, "d2h_bytes_per_step": int(table.nbytes),
-                                  "mean_repr_err_px_by_level": (table[:, 0] / np.maximum(table[:, 3], 1)).round(4).tolist()},
+        "f_method": ({"metric": "3-view linear F pose solves/sec (LinearFPoseEstimation + ReprError)", "value": f_value,
+                      "unit": UNIT, "ms_per_step": ms_f / max(3, args.steps // 2),
+                      "roofline_step_frac_fp64": f_flops(n) * B / (ms_f * 1e-3 / max(3, args.steps // 2)) / 1e12 / fp64_peak}
+                     if full else None),
+        "optimf_method": ({"metric": "3-view optimal-F pose solves/sec (OptimFPoseEstimation + ReprError)", "value": optf_value,
+                           "unit": UNIT, "ms_per_step": ms_o / optf_steps, "mean_gauss_helmert_iterations_per_solve": optf_iters,
+                           "optimf_gh_kernel_share": gh_ms[0] / ms_o if ms_o > 0 else None} if full else None),
+        "device_resident_sweep": ({"api": "tvf_sweep_run: trials generated, solved and reduced per noise level on the device",
+                                   "value": sweep_value, "unit": UNIT, "d2h_bytes_per_step": int(table.nbytes),
+                                   "mean_repr_err_px_by_level": (table[:, 0] / np.maximum(table[:, 3], 1)).round(4).tolist()}
+                                  if full else None),
         "flagged_problems": flagged,
         "input_generation": {"where": "device (tvf_generate_sweep_dev, TVF scene RNG v2)", "seconds": t_gen, "seconds_warm": t_gen2, "trials_per_s_warm": B / t_gen2, "check": gen_check},
     }
@@ -594,6 +604,9 @@ def main():
     ap.add_argument("--cpu-sample", type=int, default=0, help="trials in the CPU-baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="problems per launch (0 = the library's default)")
+    ap.add_argument("--legs", default="all", choices=["all", "headline"],
+                    help="headline = only the device-resident TFT step (what `value` times): used for the ncu launch list, so "
+                         "that the list holds the kernels of the step and nothing else")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "large-n"],
                     help="sweep = BASELINE config 3/4 (headline); large-n = config 5 (use with --n 10000 --trials 65536)")
     args = ap.parse_args()

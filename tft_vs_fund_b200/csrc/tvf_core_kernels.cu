@@ -502,6 +502,186 @@ tft_stage2_kernel(CoreInput in, const double* __restrict__ ws, double* __restric
     }
 }
 
+// ---- two problems per warp (n >= REFINE_N_MAX): the 27-lane parts run once per problem, the 15-lane parts (the
+// projected Gram Up'(G Up), its Gauss-Jordan inverse and the power iteration: half of this kernel's instructions) run
+// for both problems at once on the two half-warps (smallest_eigvec_spd_half).
+struct __align__(16) Stage2DualScratch {
+    double sbuf[64];
+    double W[2][27 * FEAT_STRIDE + 3];   // G*Up of the two problems
+    double mom[98];
+    double T[28];
+    double tp[2][16];
+    double Nm[28];
+};
+
+#ifndef TVF_STAGE2_DUAL
+#define TVF_STAGE2_DUAL 1
+#endif
+
+__global__ void __launch_bounds__(CORE_WARPS * 32, CORE_MINB)
+tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws, double* __restrict__ Tout,
+                       double* __restrict__ P2out, double* __restrict__ P3out, int* __restrict__ status) {
+    __shared__ Stage2DualScratch scratch[CORE_WARPS];
+    __shared__ unsigned char gidx[32 * 27];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    build_gidx(gidx);
+    __syncthreads();
+    Stage2DualScratch& sc = scratch[warp];
+    const int jr = lane % 3, kr = (lane / 3) % 3, ir = (lane < 27) ? lane / 9 : 0;
+    const int h = lane >> 4, r15 = lane & 15;
+    const int ia = (r15 < 15) ? r15 / 5 : 0, aa = (r15 < 15) ? r15 % 5 : 0;
+    const long long npairs = (B + 1) / 2;
+
+    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < npairs; base += (long long)gridDim.x * CORE_WARPS) {
+        STEP_SYNC();
+        const long long pair = base + warp;
+        if (pair >= npairs) continue;
+        const long long prob0 = 2 * pair;
+        const int nprob = (prob0 + 1 < B) ? 2 : 1;
+        // ---- 27-lane part, problem by problem: W = G*Up (linearTFT.m:82-84 without svd(E), see tft_stage2_kernel) ----
+        for (int p = 0; p < nprob; ++p) {
+            const double* rec = ws + (prob0 + p) * CORE_WS_TFT;
+            __syncwarp();
+            sc.mom[lane] = rec[CW_MOM + lane]; sc.mom[lane + 32] = rec[CW_MOM + 32 + lane]; sc.mom[lane + 64] = rec[CW_MOM + 64 + lane];
+            if (lane == 0) { sc.mom[96] = 0.0; sc.mom[97] = 0.0; }
+            const double e21[3] = {rec[CW_EPI], rec[CW_EPI + 1], rec[CW_EPI + 2]};
+            const double e31[3] = {rec[CW_EPI + 3], rec[CW_EPI + 4], rec[CW_EPI + 5]};
+            double u1[3], u2[3], v1[3], v2[3];
+            onb3(e21, u1, u2);
+            onb3(e31, v1, v2);
+            __syncwarp();
+            double Ze[9], Zu1[9], Zu2[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) {
+                const double g0 = sc.mom[gidx[lane * 27 + 3 * q]];
+                const double g1 = sc.mom[gidx[lane * 27 + 3 * q + 1]];
+                const double g2 = sc.mom[gidx[lane * 27 + 3 * q + 2]];
+                Ze[q] = g0 * e21[0] + g1 * e21[1] + g2 * e21[2];
+                Zu1[q] = g0 * u1[0] + g1 * u1[1] + g2 * u1[2];
+                Zu2[q] = g0 * u2[0] + g1 * u2[1] + g2 * u2[2];
+            }
+            if (lane < 27) {
+                double* W = sc.W[p] + lane * FEAT_STRIDE;
+#pragma unroll
+                for (int i2 = 0; i2 < 3; ++i2) {
+                    const double* ze = Ze + 3 * i2; const double* zu1 = Zu1 + 3 * i2; const double* zu2 = Zu2 + 3 * i2;
+                    W[5 * i2 + 0] = ze[0] * e31[0] + ze[1] * e31[1] + ze[2] * e31[2];
+                    W[5 * i2 + 1] = ze[0] * v1[0] + ze[1] * v1[1] + ze[2] * v1[2];
+                    W[5 * i2 + 2] = ze[0] * v2[0] + ze[1] * v2[1] + ze[2] * v2[2];
+                    W[5 * i2 + 3] = zu1[0] * e31[0] + zu1[1] * e31[1] + zu1[2] * e31[2];
+                    W[5 * i2 + 4] = zu2[0] * e31[0] + zu2[1] * e31[1] + zu2[2] * e31[2];
+                }
+            }
+        }
+        __syncwarp();
+        // ---- 15-lane part, both problems at once: half h = problem prob0 + h ------------------------------------
+        {
+            const bool live = h < nprob;
+            const double* rec = ws + (prob0 + (live ? h : 0)) * CORE_WS_TFT;
+            const double e21[3] = {rec[CW_EPI], rec[CW_EPI + 1], rec[CW_EPI + 2]};
+            const double e31[3] = {rec[CW_EPI + 3], rec[CW_EPI + 4], rec[CW_EPI + 5]};
+            double u1[3], u2[3], v1[3], v2[3];
+            onb3(e21, u1, u2);
+            onb3(e31, v1, v2);
+            double pa[3], qa[3];
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                pa[q] = (aa < 3) ? e21[q] : ((aa == 3) ? u1[q] : u2[q]);
+                qa[q] = (aa == 1) ? v1[q] : ((aa == 2) ? v2[q] : e31[q]);
+            }
+            double g15[15];
+#pragma unroll
+            for (int c = 0; c < 15; ++c) g15[c] = 0.0;
+            const double* Wh = sc.W[live ? h : 0];
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const double coef = (r15 < 15) ? pa[j] * qa[k] : 0.0;
+                    const double* W = Wh + (9 * ia + 3 * k + j) * FEAT_STRIDE;
+#pragma unroll
+                    for (int c = 0; c < 15; ++c) g15[c] = fma(coef, W[c], g15[c]);
+                }
+            if (!live) {                                   // odd batch: the idle half solves the identity
+#pragma unroll
+                for (int c = 0; c < 15; ++c) g15[c] = (c == r15) ? 1.0 : 0.0;
+            }
+            bool conv2;
+            const double tpl = smallest_eigvec_spd_half<15>(g15, lane, sc.sbuf, &conv2);
+            __syncwarp();
+            if (r15 < 15) sc.tp[h][r15] = tpl;
+            if (live && !conv2 && r15 == 0 && status != nullptr) status[prob0 + h] |= ST_EIG_NOCONV;
+        }
+        __syncwarp();
+        // ---- back to 27 lanes, problem by problem: t = Up*tp, P2/P3, undo the normalisation -----------------------
+        for (int p = 0; p < nprob; ++p) {
+            const long long prob = prob0 + p;
+            const double* rec = ws + prob * CORE_WS_TFT;
+            const double e21[3] = {rec[CW_EPI], rec[CW_EPI + 1], rec[CW_EPI + 2]};
+            const double e31[3] = {rec[CW_EPI + 3], rec[CW_EPI + 4], rec[CW_EPI + 5]};
+            double u1[3], u2[3], v1[3], v2[3];
+            onb3(e21, u1, u2);
+            onb3(e31, v1, v2);
+            const double pe = sel3(e21, jr), pu1 = sel3(u1, jr), pu2 = sel3(u2, jr);
+            const double qe = sel3(e31, kr), qv1 = sel3(v1, kr), qv2 = sel3(v2, kr);
+            double acc = 0.0;                                                   // t = Up*tp  (linearTFT.m:85)
+            if (lane < 27) {
+                const double* tp = sc.tp[p] + 5 * ir;
+                acc = pe * (qe * tp[0] + qv1 * tp[1] + qv2 * tp[2]) + qe * (pu1 * tp[3] + pu2 * tp[4]);
+            }
+            const double tl2 = acc * rsqrt_(warp_sum(acc * acc));
+            __syncwarp();
+            if (lane < 27) sc.T[lane] = tl2;
+            __syncwarp();
+            if (P2out != nullptr && P3out != nullptr) {                          // linearTFT.m:86-90, a = pinv(E) t in closed form
+                if (lane < 3) {
+                    const double* Ti = sc.T + 9 * lane;
+                    double a[3], b[3];
+                    mat3_vec(Ti, e31, a);
+                    mat3_tvec(Ti, e21, b);
+                    const double tau = e21[0] * a[0] + e21[1] * a[1] + e21[2] * a[2];
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) {
+                        P2out[prob * 12 + 3 * lane + q] = a[q] - 0.5 * tau * e21[q];
+                        P3out[prob * 12 + 3 * lane + q] = 0.5 * tau * e31[q] - b[q];
+                    }
+                } else if (lane == 3) {
+#pragma unroll
+                    for (int q = 0; q < 3; ++q) { P2out[prob * 12 + 9 + q] = e21[q]; P3out[prob * 12 + 9 + q] = e31[q]; }
+                }
+            }
+            double tout = tl2;
+            if (normalize) {                                                     // LinearTFTPoseEstimation.m:53 -> transform_TFT.m:43-49
+                const double s0 = rec[CW_STATS], s1 = rec[CW_STATS + 1], s2 = rec[CW_STATS + 2];
+                const double N1[9] = {s0, 0, 0, 0, s0, 0, rec[CW_STATS + 3], rec[CW_STATS + 4], 1.0};
+                const double N2[9] = {s1, 0, 0, 0, s1, 0, rec[CW_STATS + 5], rec[CW_STATS + 6], 1.0};
+                const double N3[9] = {s2, 0, 0, 0, s2, 0, rec[CW_STATS + 7], rec[CW_STATS + 8], 1.0};
+                double N2i[9], N3i[9];
+                inv3(N2, N2i); inv3(N3, N3i);
+                if (lane == 0) {
+#pragma unroll
+                    for (int q = 0; q < 9; ++q) { sc.Nm[q] = N1[q]; sc.Nm[9 + q] = N2i[q]; sc.Nm[18 + q] = N3i[q]; }
+                }
+                __syncwarp();
+                double acc2 = 0.0;
+                if (lane < 27) {
+#pragma unroll
+                    for (int b = 0; b < 3; ++b)
+#pragma unroll
+                        for (int a = 0; a < 3; ++a) {
+                            const double sab = sc.Nm[3 * ir] * sc.T[a + 3 * b] + sc.Nm[1 + 3 * ir] * sc.T[9 + a + 3 * b] +
+                                               sc.Nm[2 + 3 * ir] * sc.T[18 + a + 3 * b];
+                            acc2 = fma(sc.Nm[9 + jr + 3 * a] * sc.Nm[18 + kr + 3 * b], sab, acc2);
+                        }
+                }
+                tout = acc2 * rsqrt_(warp_sum(acc2 * acc2));                       // :49
+            }
+            if (lane < 27) Tout[prob * 27 + lane] = tout;
+            __syncwarp();                                                        // sc.T / sc.Nm are reused by the next problem
+        }
+    }
+}
+
 // =========================================================================== linearF stage 1
 struct __align__(16) FScratch {
     double sbuf[64];
@@ -659,6 +839,12 @@ void launch_tft_stage2(const CoreInput& in, const double* ws, double* T, double*
     if (in.B <= 0) return;
     const unsigned g = core_grid(in.B, sm_count);
     const bool refine = in.n < REFINE_N_MAX;
+#if TVF_STAGE2_DUAL
+    if (!refine) {          // the un-refined step never touches the points again: two problems per warp
+        tft_stage2_dual_kernel<<<core_grid((in.B + 1) / 2, sm_count), CORE_WARPS * 32, 0, stream>>>(in.normalize, in.B, ws, T, P2, P3, status);
+        return;
+    }
+#endif
     if (in.packed && refine) tft_stage2_kernel<true, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, T, P2, P3, status);
     else if (in.packed) tft_stage2_kernel<true, false><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, T, P2, P3, status);
     else if (refine) tft_stage2_kernel<false, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, T, P2, P3, status);

@@ -198,4 +198,85 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
     return x;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Two independent problems per warp: the same solver on HALF-warps (N <= 16; lane = 16 h + r, lane r of half h owns row
+// r of problem h).  The 15 x 15 projected system of linearTFT's second step keeps 15 of 32 lanes busy in the full-warp
+// solver; here both halves work.  Nothing crosses between the halves except the loop-exit vote: each half freezes its
+// iterate at the step where IT converged, so a problem's result does not depend on its neighbour (bit-reproducible under
+// any batching).  sbuf: 64 doubles; half h uses [16 h, 16 h + 16) of each 32-double parity buffer.
+__device__ __forceinline__ double half_sum(double v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+template <int N>
+__device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const int lane, double* sbuf, bool* converged) {
+    static_assert(N <= 16 && N >= 2, "one matrix row per lane of a half-warp");
+    const int r = lane & 15, h16 = lane & 16;
+    const unsigned hmask = 0xffffu << h16;
+    double diag = 0.0;
+#pragma unroll
+    for (int m = 0; m < N; ++m) diag = (r == m) ? g[m] : diag;
+    const double tr = half_sum(diag);
+    const double sc = 1.0 / tr;
+    const double delta = 1.0e-13 / N;         // relative to the unit trace
+    const double floor_piv = 1.0e-3 * delta;
+#pragma unroll
+    for (int m = 0; m < N; ++m) g[m] = g[m] * sc + ((r == m) ? delta : 0.0);
+
+    __syncwarp();                              // sbuf may still be read by a previous phase
+    if (r >= N) { sbuf[lane] = 0.0; sbuf[32 + lane] = 0.0; }
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double colj = g[k];
+        const double d = fmax(__shfl_sync(FULL, colj, k, 16), floor_piv);
+        const double piv = fast_rcp(d);
+        const double rk = colj * piv;
+        double* buf = sbuf + (k & 1) * 32 + h16;
+        if (r < N) buf[r] = rk;
+        __syncwarp();
+        const double c = colj - ((r == k) ? 1.0 : 0.0);
+        const double2* b2 = reinterpret_cast<const double2*>(buf);
+#pragma unroll
+        for (int m2 = 0; m2 < 8; ++m2) {
+            const double2 q = b2[m2];
+            if (2 * m2 != k && 2 * m2 < N) g[2 * m2] = fma(-c, q.x, g[2 * m2]);
+            if (2 * m2 + 1 != k && 2 * m2 + 1 < N) g[2 * m2 + 1] = fma(-c, q.y, g[2 * m2 + 1]);
+        }
+        g[k] = (r == k) ? -piv : rk;
+    }
+    __syncwarp();
+    // g holds -(G + delta I)^-1.  Pivot-normalised power iteration (see smallest_eigvec_spd), per half.
+    double x = (r < N) ? 1.0 : 0.0;
+    bool done = false;                          // uniform within a half
+#pragma unroll 1
+    for (int it = 0; it < EIG_MAX_ITER; ++it) {
+        double* buf = sbuf + (it & 1) * 32 + h16;
+        buf[r] = x;
+        __syncwarp();
+        const double2* b2 = reinterpret_cast<const double2*>(buf);
+        double z0 = 0.0, z1 = 0.0;
+#pragma unroll
+        for (int m2 = 0; m2 < 8; ++m2) {
+            const double2 q = b2[m2];
+            if (2 * m2 < N) z0 = fma(g[2 * m2], q.x, z0);
+            if (2 * m2 + 1 < N) z1 = fma(g[2 * m2 + 1], q.y, z1);
+        }
+        double z = z0 + z1;
+        const unsigned hz = (unsigned)__double2hiint(z) & 0x7fffffffu;
+        const unsigned hmax = __reduce_max_sync(hmask, hz);
+        const int piv = __ffs(__ballot_sync(hmask, hz == hmax)) - 1;
+        z *= fast_rcp(shfl_d(z, piv));
+        const bool moving = !done && (fabs(z - x) > EIG_TOL);
+        if (!done) x = z;
+        const unsigned bal = __ballot_sync(FULL, moving);
+        done = done || ((bal & hmask) == 0u);
+        if (bal == 0u) break;
+    }
+    x *= rsqrt_(half_sum(x * x));
+    *converged = done;
+    return x;
+}
+
 }  // namespace tvf

@@ -11,9 +11,7 @@ from tft_vs_fund_b200 import build as B   # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "st64": ["-DTVF_CAND_STORE128=0"],
-    "cand64": ["-DTVF_CAND_THREADS=64"],
-    "cand256": ["-DTVF_CAND_THREADS=256"],
+    "nodual": ["-DTVF_STAGE2_DUAL=0"],
 }
 
 
