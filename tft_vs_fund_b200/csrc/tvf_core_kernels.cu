@@ -686,7 +686,7 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
 struct __align__(16) FScratch {
     double sbuf[64];
     double feat[32 * FEAT_STRIDE];
-    double mom[40];
+    double mom[2][40];               // 36 moments of the view pairs (1,2) and (1,3)
 };
 
 // mode: in.normalize != 0 -> pose path (two pairs 1-2 and 1-3, outer normalisation); else one pair
@@ -742,25 +742,40 @@ f_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status)
                 }
             }
             __syncwarp();
-            sc.mom[lane] = acc0;
-            if (lane < 4) sc.mom[32 + lane] = acc1;
+            sc.mom[pr][lane] = acc0;
+            if (lane < 4) sc.mom[pr][32 + lane] = acc1;
             __syncwarp();
-            // G9(r,c), r = 3*a + b for the row [x1x2, x1y2, x1, y1x2, y1y2, y1, x2, y2, 1] (linearF.m:51-52)
+            if constexpr (REFINE) {
+                // G9(r,c), r = 3*a + b for the row [x1x2, x1y2, x1, y1x2, y1y2, y1, x2, y2, 1] (linearF.m:51-52)
+                double g[9];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) {
+                    const double v = sc.mom[pr][c_sym6[ar * 3 + c / 3] * 6 + c_sym6[br * 3 + c % 3]];
+                    g[c] = (lane < 9) ? v : 0.0;
+                }
+                bool conv;                                                                 // linearF.m:54-55
+                const double fl = smallest_eigvec_spd<9>(g, lane, sc.sbuf, &conv, [&](const double* xs) {
+                    return f_apply_AtA<PACKED>(in, prob, lane, vb, sa, tax, tay, sb, tbx, tby, xs); }, 2);
+                if (!conv) st |= ST_EIG_NOCONV;
+                if (lane < 9) rec[FW_F + 9 * pr + lane] = fl;
+            }
+        }
+        if constexpr (!REFINE) {
+            // both 9x9 systems at once, one per half-warp (half 1 solves the identity when there is a single pair)
+            const int h = lane >> 4, r = lane & 15;
+            const int arh = (r < 9) ? r / 3 : 0, brh = (r < 9) ? r % 3 : 0;
+            const bool live = h < npairs && r < 9;
             double g[9];
 #pragma unroll
             for (int c = 0; c < 9; ++c) {
-                const double v = sc.mom[c_sym6[ar * 3 + c / 3] * 6 + c_sym6[br * 3 + c % 3]];
-                g[c] = (lane < 9) ? v : 0.0;
+                const double v = sc.mom[h < npairs ? h : 0][c_sym6[arh * 3 + c / 3] * 6 + c_sym6[brh * 3 + c % 3]];
+                g[c] = live ? v : ((h >= npairs && c == r) ? 1.0 : 0.0);
             }
-            bool conv;
-            double fl;                                                                     // linearF.m:54-55
-            if constexpr (REFINE)
-                fl = smallest_eigvec_spd<9>(g, lane, sc.sbuf, &conv, [&](const double* xs) {
-                    return f_apply_AtA<PACKED>(in, prob, lane, vb, sa, tax, tay, sb, tbx, tby, xs); }, 2);
-            else
-                fl = smallest_eigvec_spd<9>(g, lane, sc.sbuf, &conv);
-            if (!conv) st |= ST_EIG_NOCONV;
-            if (lane < 9) rec[FW_F + 9 * pr + lane] = fl;
+            bool conv;                                                                     // linearF.m:54-55
+            const double fl = smallest_eigvec_spd_half<9>(g, lane, sc.sbuf, &conv);
+            if (h < npairs && !conv) st |= ST_EIG_NOCONV;
+            st |= __shfl_xor_sync(0xffffffffu, st, 16);                                    // lane 0 reports both halves
+            if (live) rec[FW_F + 9 * h + r] = fl;
         }
         if (lane < 3) { rec[FW_STATS + lane] = sel3(s0, lane); rec[FW_STATS + 9 + lane] = sel3(si, lane); }
         if (lane < 6) {
