@@ -44,7 +44,7 @@ def gram27_from_moments(mom):
     return G
 
 
-def smallest_eigvec_spd(G, max_iter=80, tol=1e-15):
+def smallest_eigvec_spd(G, max_iter=80, tol=4e-15):
     """What tvf_warp.cuh::smallest_eigvec_spd does: scale to unit trace, relative diagonal shift 1e-13,
     N Gauss-Jordan sweeps in place (pivot row updated through c_k = d - 1), then power iteration with
     the (negated) inverse."""
@@ -62,15 +62,18 @@ def smallest_eigvec_spd(G, max_iter=80, tol=1e-15):
         newA = A - np.outer(c, rk)
         newA[:, k] = rk; newA[k, k] = -piv
         A = newA
-    x = np.ones(N) / np.sqrt(N)
+    # pivot-normalised power iteration (TVF_EIG_PIVOTNORM): the iterate is scaled so that its largest component is 1
+    # (dividing by the signed pivot also absorbs the sign of -M); one exact 2-norm normalisation at the end
+    x = np.ones(N)
     its = 0
     for its in range(1, max_iter + 1):
-        z = -(A @ x)
-        z /= np.linalg.norm(z)
+        z = A @ x
+        z = z / z[np.argmax(np.abs(z))]
         d = np.max(np.abs(z - x))
         x = z
         if not d > tol:
             break
+    x = x / np.linalg.norm(x)
     return x, its
 
 

@@ -29,6 +29,11 @@ namespace tvf {
 #ifndef TVF_CORE_MINB
 #define TVF_CORE_MINB 5
 #endif
+// MUFU-seeded square root / reciprocal (full precision, not correctly rounded) in the normalisation statistics of the
+// estimator kernels; the stand-alone Normalize2Ddata kernel keeps the IEEE operations
+#ifndef TVF_FAST_STATS
+#define TVF_FAST_STATS 1
+#endif
 #ifndef TVF_STEP_SYNC
 #define TVF_STEP_SYNC 1
 #endif
@@ -95,13 +100,21 @@ __device__ __forceinline__ void view_stats(const CoreInput& in, long long prob, 
         for (int v = 0; v < 3; ++v) {
             const double dx = (s0[v] * p[2 * v] + t0[2 * v]) - c[2 * v];
             const double dy = (s0[v] * p[2 * v + 1] + t0[2 * v + 1]) - c[2 * v + 1];
+#if TVF_FAST_STATS
+            d[v] += sqrt_(dx * dx + dy * dy);
+#else
             d[v] += sqrt(dx * dx + dy * dy);
+#endif
         }
     }
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
         const double norm0 = warp_sum(d[v]) * invn;
+#if TVF_FAST_STATS
+        s[v] = 1.4142135623730951 * rcp_(norm0);
+#else
         s[v] = 1.4142135623730951 / norm0;
+#endif
         t[2 * v] = -s[v] * c[2 * v];
         t[2 * v + 1] = -s[v] * c[2 * v + 1];
     }

@@ -11,7 +11,8 @@ from tft_vs_fund_b200 import build as B   # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "nodual": ["-DTVF_STAGE2_DUAL=0"],
+    "nopredict": ["-DTVF_EIG_PREDICT=0"],
+    "ieeestats": ["-DTVF_FAST_STATS=0"],
 }
 
 
