@@ -5,6 +5,10 @@
 #pragma once
 #include "tvf_math.cuh"
 
+#ifndef TVF_CHEIR_UNROLL
+#define TVF_CHEIR_UNROLL 1
+#endif
+
 namespace tvf {
 
 // Per-problem candidate record written by the "candidates" stage and read by
@@ -130,7 +134,8 @@ TVF_HD void triangulate3(const double* Pa, const double* Pb, const double* Pc, c
 // Xa/Xb (may be null) receive the homogeneous solutions for (R,t) and (Rp,t).
 TVF_HD void cheirality_point(const double* ra, const double* rb, const double* c, double x2, double y2,
                              int* v, int* nanmask, double* Xa, double* Xb) {
-#pragma unroll 1
+    constexpr int kUnroll = TVF_CHEIR_UNROLL;
+#pragma unroll(kUnroll)
     for (int q = 0; q < 2; ++q) {
         double P[12], r3[3], tz;
         candidate_camera(c, q == 0 ? 0 : 3, P, r3, &tz);

@@ -8,8 +8,7 @@ try:
 except Exception as e: print("variant $1 parse fail", e)
 PY
 }
-timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/t_all.log 2>&1; echo "all tests exit $?"; tail -12 gpurun_out/t_all.log | cut -c1-400
-for v in base nopredict ieeestats; do
+for v in base cheir2 cheir2_t1; do
   TVF_LIBPATH=$PWD/tools/_build/variants/libtvf_$v.so timeout 240 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --legs headline > gpurun_out/v_$v.json 2> gpurun_out/v_$v.err
   show $v
 done

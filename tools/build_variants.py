@@ -11,8 +11,8 @@ from tft_vs_fund_b200 import build as B   # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "nopredict": ["-DTVF_EIG_PREDICT=0"],
-    "ieeestats": ["-DTVF_FAST_STATS=0"],
+    "cheir2": ["-DTVF_CHEIR_UNROLL=2"],
+    "cheir2_t1": ["-DTVF_CHEIR_UNROLL=2", "-DTVF_TAIL_MINB=1"],
 }
 
 
