@@ -93,6 +93,8 @@ def counters_json(rep, out, problems_per_launch):
     out_d = {"source": rep, "problems_per_launch": problems_per_launch, "kernels": {}}
     for r in rows[2:]:
         name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
+        launched = name
+        name = {"tft_stage2_dual_kernel": "tft_stage2_kernel"}.get(name, name)   # the library's profile slot (tvf_kernel_name)
         if name in out_d["kernels"]:
             continue
         rd = num(r, "dram__bytes_read.sum"); wr = num(r, "dram__bytes_write.sum")
@@ -103,6 +105,7 @@ def counters_json(rep, out, problems_per_launch):
             "issue_active_pct": num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
             "warp_instructions": num(r, "smsp__inst_executed.sum"),
             "registers": num(r, "launch__registers_per_thread"),
+            "launched_as": launched,
         }
     json.dump(out_d, open(out, "w"), indent=1)
 
