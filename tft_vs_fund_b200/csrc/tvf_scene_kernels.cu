@@ -1,5 +1,7 @@
 // tvf_scene_kernels.cu -- batched trials of the synthetic sweep generated on the device.
 // One thread per trial; the MT19937 state and the 6 x (n+100) coordinate scratch live in local memory.
+#include <cstdlib>
+
 #include "tvf_kernels.h"
 #include "tvf_scene.cuh"
 
@@ -43,11 +45,303 @@ sweep_seeds_kernel(long long first_trial, long long B, int n, const double* __re
                       out + (j_lo + lv_lo - first_trial) * 6 * n, clean, z, c, arr, outpos);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// One WARP per seed.  The thread-per-seed kernel above keeps ~23 KB of generator state per thread in local memory and
+// runs 77 k serial threads for a 1 M-trial sweep: latency bound (27 ms, twice the time of the solver it feeds).  Here
+// the warp shares one generator whose state lives in shared memory, and every phase that the reference's stream order
+// allows is spread over the lanes -- with exactly the bits of scene_seed_levels:
+//   * MT19937 state regeneration ("twist"): element i depends on old i, i+1 and on i+397 (old) or i-227 (new), so 32
+//     consecutive elements are independent: 20 lane-parallel steps, out of place into the other half of a two-block ring.
+//     The ring holds blocks [cur, cur+1] of the stream, so a consumer may look 624 words ahead and a noise level can
+//     rewind to the position its refill passes start from; a rewind past the ring re-twists from the seeded state,
+//     which every lane keeps in 20 registers (never needed at the reference's scene parameters, but exact if it is).
+//   * uniforms (3-D points): fixed stream positions, lane = point.
+//   * polar Gaussian pairs: lane = candidate pair (4 words); accepted pairs are ranked with a ballot / popcount, the
+//     rank gives (view, point) in the reference's v-major order, and the stream position after the last needed pair
+//     is where the next consumer continues.  log / sqrt / divide run only on accepted lanes.
+//   * inside-image compaction: ballot ranks in point order -> position in the sub-sample (outpos) -> 48-byte store.
+//   * the seeding recurrence (624 dependent steps) and the sub-sample shuffle (data-dependent swaps) are serial; the
+//     shuffle runs on lane 0 over words that all lanes tempered beforehand.
+constexpr int SW_WARPS = 1;                     // warps (= seeds) per CTA
+constexpr unsigned SW_FULL = 0xffffffffu;
+
+struct WarpMT {
+    uint32_t* raw;        // shared memory, 2 x 624 words: block b of the stream's state sits in raw[(b & 1) * 624]
+    uint32_t init[20];    // this lane's words (32 q + lane) of the seeded state ("block -1")
+    int cur;              // lowest block in the ring (-1: the seeded state itself)
+    bool have_next;       // block cur + 1 is in the other half
+    int lane;
+
+    __device__ __forceinline__ void seed(uint32_t s) {                     // init_genrand
+        uint32_t* dst = raw + 624;
+        __syncwarp();
+#pragma unroll 4
+        for (int i = 0; i < 624; ++i) {
+            if (lane == 0) dst[i] = s;
+            s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 20; ++q) init[q] = (32 * q + lane < 624) ? dst[32 * q + lane] : 0u;
+        cur = -1; have_next = false;
+    }
+    __device__ __forceinline__ void reset() {
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 20; ++q)
+            if (32 * q + lane < 624) raw[624 + 32 * q + lane] = init[q];
+        __syncwarp();
+        cur = -1; have_next = false;
+    }
+    __device__ __forceinline__ void make_next() {                           // block cur + 1 from block cur
+        const uint32_t* src = raw + (cur & 1) * 624;
+        uint32_t* dst = raw + ((cur + 1) & 1) * 624;
+#pragma unroll 1
+        for (int s = 0; s < 20; ++s) {
+            const int i = 32 * s + lane;
+            __syncwarp();                                                   // dst[i - 227], dst[0] of earlier steps
+            if (i < 624) {
+                const uint32_t a = src[i];
+                const uint32_t b = (i < 623) ? src[i + 1] : dst[0];
+                const uint32_t m = (i < 227) ? src[i + 397] : dst[i - 227];
+                const uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+                dst[i] = m ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+        }
+        __syncwarp();
+        have_next = true;
+    }
+    // make the words [pos_lo, pos_hi] readable (pos_hi - pos_lo < 624); all arguments warp-uniform
+    __device__ __forceinline__ void prepare(int pos_lo, int pos_hi) {
+        const int b_lo = pos_lo / 624, b_hi = pos_hi / 624;
+        if (b_lo < cur) reset();
+        while (b_hi > cur + 1) {
+            if (!have_next) make_next();
+            ++cur; have_next = false;
+        }
+        if (b_hi == cur + 1 && !have_next) make_next();
+    }
+    __device__ __forceinline__ uint32_t word(int pos) const {               // genrand_int32 output number `pos`
+        const int b = pos / 624;
+        uint32_t y = raw[(b & 1) * 624 + (pos - b * 624)];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    __device__ __forceinline__ double res53(int pos) const {                // genrand_res53 from words pos, pos + 1
+        const uint32_t a = word(pos) >> 5, b = word(pos + 1) >> 6;
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+};
+
+// X = 400*rand(3,1)-200 from the six words at `pos`, projected by the three cameras (generateSyntheticScene.m:82-87)
+__device__ __forceinline__ void sw_point(const WarpMT& mt, int pos, const double* __restrict__ P, double* __restrict__ dst) {
+    const double X = TVF_ADD(TVF_MUL(400.0, mt.res53(pos)), -200.0);
+    const double Y = TVF_ADD(TVF_MUL(400.0, mt.res53(pos + 2)), -200.0);
+    const double Z = TVF_ADD(TVF_MUL(400.0, mt.res53(pos + 4)), -200.0);
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const double* Pv = P + 12 * v;
+        double x[3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+            x[r] = TVF_ADD(TVF_ADD(TVF_ADD(TVF_MUL(Pv[4 * r], X), TVF_MUL(Pv[4 * r + 1], Y)), TVF_MUL(Pv[4 * r + 2], Z)), Pv[4 * r + 3]);
+        dst[2 * v] = TVF_DIV(x[0], x[2]);
+        dst[2 * v + 1] = TVF_DIV(x[1], x[2]);
+    }
+}
+
+// 3*M accepted polar pairs from stream position `pos` on, in the reference's order (view-major, then point; the first
+// value returned for a pair is f*x2, the cached one f*x1).  ADD: buf[6i+2v..] += z*noise (refill passes, :90-92), else
+// buf = z (first pass, noise applied per level).  Returns the stream position after the last pair consumed.
+template <bool ADD>
+__device__ __forceinline__ int sw_normals(WarpMT& mt, int pos, int M, double noise, double* __restrict__ buf) {
+    const int need = 3 * M, lane = mt.lane;
+    const unsigned lt = (1u << lane) - 1u;
+    int got = 0;
+    while (got < need) {
+        mt.prepare(pos, pos + 127);
+        const int p = pos + 4 * lane;
+        const double x1 = TVF_ADD(TVF_MUL(2.0, mt.res53(p)), -1.0);
+        const double x2 = TVF_ADD(TVF_MUL(2.0, mt.res53(p + 2)), -1.0);
+        const double r2 = TVF_ADD(TVF_MUL(x1, x1), TVF_MUL(x2, x2));
+        const bool acc = !(r2 >= 1.0 || r2 == 0.0);
+        const unsigned bal = __ballot_sync(SW_FULL, acc);
+        const int idx = got + __popc(bal & lt);
+        if (acc && idx < need) {
+            const double f = TVF_SQRT(TVF_DIV(TVF_MUL(-2.0, tvf_log(r2)), r2));
+            const double z0 = TVF_MUL(f, x2), z1 = TVF_MUL(f, x1);
+            const int v = idx / M, i = idx - v * M;
+            double* d = buf + 6 * i + 2 * v;
+            if (ADD) { d[0] = TVF_ADD(d[0], TVF_MUL(z0, noise)); d[1] = TVF_ADD(d[1], TVF_MUL(z1, noise)); }
+            else { d[0] = z0; d[1] = z1; }
+        }
+        const unsigned last = __ballot_sync(SW_FULL, acc && idx == need - 1);
+        if (last) { pos += 4 * __ffs(last); got = need; }
+        else { got += __popc(bal); pos += 128; }
+    }
+    __syncwarp();
+    return pos;
+}
+
+__device__ __forceinline__ bool sw_inside(const double* p, double hi_x, double hi_y) {      // :95-100
+    bool inside = true;
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        const double x = p[2 * v], y = p[2 * v + 1];
+        inside = inside && (x <= hi_x) && (y <= hi_y) && (x >= 0.0) && (y >= 0.0);
+    }
+    return inside;
+}
+
+__host__ __device__ inline size_t sw_warp_bytes(int N) { return 2 * 624 * 4 + (size_t)3 * 48 * N + 2 * (size_t)((N + 15) & ~15); }
+
+__global__ void __launch_bounds__(SW_WARPS * 32)
+sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double* __restrict__ noise_levels, int L,
+                        const double* __restrict__ Pg, double hi_x, double hi_y, double* __restrict__ out) {
+    extern __shared__ __align__(16) unsigned char sw_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int N = n + 100, Npad = (N + 15) & ~15;
+    double* P = reinterpret_cast<double*>(sw_smem);                          // 36 doubles, shared by the CTA
+    for (int i = threadIdx.x; i < 36; i += blockDim.x) P[i] = Pg[i];
+    __syncthreads();
+    unsigned char* base = sw_smem + 288 + (size_t)warp * sw_warp_bytes(N);
+    double* clean = reinterpret_cast<double*>(base);                         // first pass: projections without noise
+    double* z = clean + 6 * N;                                               // first pass: the Gaussian draws
+    double* c = z + 6 * N;                                                   // refill passes; tempered words for the shuffle
+    WarpMT mt;
+    mt.raw = reinterpret_cast<uint32_t*>(c + 6 * N);
+    mt.lane = lane;
+    unsigned char* arr = reinterpret_cast<unsigned char*>(mt.raw + 2 * 624);
+    signed char* outpos = reinterpret_cast<signed char*>(arr + Npad);
+
+    const long long s0 = first_trial / L;
+    const long long s = s0 + (long long)blockIdx.x * SW_WARPS + warp;         // 0-based seed index, seed = s + 1
+    const long long j_lo = s * L, last_trial = first_trial + B;
+    if (j_lo >= last_trial) return;
+    const int lv_lo = (int)((first_trial > j_lo) ? first_trial - j_lo : 0);
+    const int lv_hi = (int)((last_trial - j_lo < L) ? last_trial - j_lo : L);
+    double* out0 = out + (j_lo + lv_lo - first_trial) * 6 * n;
+    const unsigned lt = (1u << lane) - 1u;
+
+    // ---- experiments.m:94-95: rng(it); randsample(N+100, N) = first n entries of a legacy shuffle of 0..N-1
+    for (int i = lane; i < N; i += 32) { arr[i] = (unsigned char)i; outpos[i] = -1; }
+    mt.seed((uint32_t)(s + 1));
+    {
+        uint32_t* tw = reinterpret_cast<uint32_t*>(c);
+        int top = N - 1, pos = 0;
+        uint32_t mask = (top >= 1) ? (0xffffffffu >> __clz(top)) : 0u;     // random_interval: smallest 2^k - 1 >= max
+        while (top >= 1) {
+            mt.prepare(pos, pos + 255);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) tw[32 * q + lane] = mt.word(pos + 32 * q + lane);
+            __syncwarp();
+            if (lane == 0) {
+                int k = 0;
+                while (k < 256 && top >= 1) {
+                    const uint32_t v = tw[k++] & mask;
+                    if (v <= (uint32_t)top) {
+                        const unsigned char t = arr[top]; arr[top] = arr[v]; arr[v] = t;
+                        --top;
+                        if ((uint32_t)top == (mask >> 1)) mask >>= 1;
+                    }
+                }
+                pos += k;
+            }
+            top = __shfl_sync(SW_FULL, top, 0); pos = __shfl_sync(SW_FULL, pos, 0); mask = __shfl_sync(SW_FULL, mask, 0);
+            __syncwarp();
+        }
+        for (int k = lane; k < n; k += 32) outpos[arr[k]] = (signed char)k;
+        __syncwarp();
+    }
+    // ---- generateSyntheticScene.m:75-92, first pass (rng(seed) again: the same stream from its start)
+    for (int i0 = 0; i0 < N; i0 += 32) {
+        const int i1 = (i0 + 32 < N) ? i0 + 32 : N;
+        mt.prepare(6 * i0, 6 * i1 - 1);
+        const int i = i0 + lane;
+        if (i < N) sw_point(mt, 6 * i, P, clean + 6 * i);
+    }
+    const int snap_pos = sw_normals<false>(mt, 6 * N, N, 0.0, z);
+    // ---- per noise level: scale the draws, inside-image mask + compaction, refill passes (:95-110)
+    for (int lv = lv_lo; lv < lv_hi; ++lv) {
+        const double noise = noise_levels[lv];
+        double* o = out0 + (size_t)(lv - lv_lo) * 6 * n;
+        int filled = 0;
+        for (int i0 = 0; i0 < N; i0 += 32) {
+            const int i = i0 + lane;
+            double p[6];
+            bool inside = false;
+            if (i < N) {
+#pragma unroll
+                for (int q = 0; q < 6; ++q) p[q] = TVF_ADD(clean[6 * i + q], TVF_MUL(z[6 * i + q], noise));
+                inside = sw_inside(p, hi_x, hi_y);
+            }
+            const unsigned bal = __ballot_sync(SW_FULL, inside);
+            if (inside) {
+                const int k = outpos[filled + __popc(bal & lt)];
+                if (k >= 0) {
+                    double2* d = reinterpret_cast<double2*>(o + 6 * k);
+                    d[0] = make_double2(p[0], p[1]); d[1] = make_double2(p[2], p[3]); d[2] = make_double2(p[4], p[5]);
+                }
+            }
+            filled += __popc(bal);
+        }
+        int M = N - filled, pos = snap_pos;
+        while (M > 0) {
+            __syncwarp();
+            for (int i0 = 0; i0 < M; i0 += 32) {
+                const int i1 = (i0 + 32 < M) ? i0 + 32 : M;
+                mt.prepare(pos + 6 * i0, pos + 6 * i1 - 1);
+                const int i = i0 + lane;
+                if (i < M) sw_point(mt, pos + 6 * i, P, c + 6 * i);
+            }
+            __syncwarp();
+            pos = sw_normals<true>(mt, pos + 6 * M, M, noise, c);
+            for (int i0 = 0; i0 < M; i0 += 32) {
+                const int i = i0 + lane;
+                double p[6];
+                bool inside = false;
+                if (i < M) {
+#pragma unroll
+                    for (int q = 0; q < 6; ++q) p[q] = c[6 * i + q];
+                    inside = sw_inside(p, hi_x, hi_y);
+                }
+                const unsigned bal = __ballot_sync(SW_FULL, inside);
+                if (inside) {
+                    const int k = outpos[filled + __popc(bal & lt)];
+                    if (k >= 0) {
+                        double2* d = reinterpret_cast<double2*>(o + 6 * k);
+                        d[0] = make_double2(p[0], p[1]); d[1] = make_double2(p[2], p[3]); d[2] = make_double2(p[4], p[5]);
+                    }
+                }
+                filled += __popc(bal);
+            }
+            M = N - filled;
+        }
+    }
+}
+
+
 void launch_sweep_trials(long long first_trial, long long B, int n, const double* d_noise_levels, int L, const double* d_P,
                          double hi_x, double hi_y, double* d_out, cudaStream_t stream) {
     if (B <= 0) return;
+    // development switch for A/B timing: TVF_SCENE_THREAD_PER_SEED=1 selects the thread-per-seed / per-trial kernels
+    static const bool per_thread = [] { const char* e = getenv("TVF_SCENE_THREAD_PER_SEED"); return e && e[0] == '1'; }();
+    const long long seeds = (first_trial + B - 1) / L - first_trial / L + 1;
+    if (!per_thread && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
+        const size_t smem = 288 + SW_WARPS * sw_warp_bytes(n + 100);
+        static size_t smem_set = 0;
+        if (smem > smem_set) {
+            cudaFuncSetAttribute(sweep_seeds_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            smem_set = smem;
+        }
+        sweep_seeds_warp_kernel<<<(unsigned)((seeds + SW_WARPS - 1) / SW_WARPS), SW_WARPS * 32, smem, stream>>>(
+            first_trial, B, n, d_noise_levels, L, d_P, hi_x, hi_y, d_out);
+        return;
+    }
     if (L >= 4) {
-        const long long seeds = (first_trial + B - 1) / L - first_trial / L + 1;
         sweep_seeds_kernel<<<(unsigned)((seeds + 63) / 64), 64, 0, stream>>>(first_trial, B, n, d_noise_levels, L, d_P, hi_x, hi_y, d_out);
         return;
     }
