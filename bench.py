@@ -251,11 +251,11 @@ def run_gpu(args, rank, local_rank, world):
     # 3. inputs generated on the device (tvf_generate_sweep_dev: one thread per trial), outputs preallocated
     t_gen = time.perf_counter()
     d_corresp = torch.empty((B, n, 6), dtype=torch.float64, device=dev)
-    scene.sweep_batch_device(B, n, first_trial=rank * B, device=local_rank, out_ptr=d_corresp.data_ptr())
+    scene.sweep_batch_device(B, n, first_trial=rank * B, device=local_rank, out_ptr=d_corresp.data_ptr(), meta=False)
     torch.cuda.synchronize(dev)
     t_gen = time.perf_counter() - t_gen
     t_gen2 = time.perf_counter()                                             # second call: no first-launch set-up cost
-    scene.sweep_batch_device(B, n, first_trial=rank * B, device=local_rank, out_ptr=d_corresp.data_ptr())
+    scene.sweep_batch_device(B, n, first_trial=rank * B, device=local_rank, out_ptr=d_corresp.data_ptr(), meta=False)
     torch.cuda.synchronize(dev)
     t_gen2 = time.perf_counter() - t_gen2
     corresp_host = d_corresp.cpu().numpy()                                   # for the end-to-end (host-pointer) leg

@@ -459,6 +459,28 @@ def test_device_scene_generator(tvf):
     assert np.max(np.abs(a.repr_err - b.repr_err)) < 1e-7
 
 
+def test_device_scene_generator_small_image(tvf, hostcheck):
+    """A small image makes most points fall outside: many refill passes per trial, refill passes with more than 32
+    points (the chunked path of the warp-per-seed kernel), streams that run over dozens of MT19937 state blocks and
+    noise levels whose refill passes differ in size.  Checked bit for bit against the host build of the serial
+    generator (tests/hostcheck: scene_trial, itself pinned to the NumPy generator by tests/test_scene.py)."""
+    import ctypes as C
+    from tft_vs_fund_b200 import scene
+    K, Ps, _ = scene.scene_cameras(50, 0)
+    P = np.ascontiguousarray(np.stack(Ps), dtype=np.float64)
+    dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+    for n, image, levels, first, B in ((20, (1100.0, 800.0), [0.0, 1.0, 2.5], 6, 90), (45, (1000.0, 900.0), [0.5, 30.0], 0, 40),
+                                       (20, (1800.0, 1200.0), [0.0, 0.25, 0.5, 0.75, 1.0], 3, 100)):
+        L = len(levels)
+        dev = scene.sweep_batch_device(B, n, first_trial=first, noise_levels=levels, image=image)
+        out = np.zeros(6 * n)
+        for b in range(B):
+            j = first + b
+            hostcheck.hc_scene_trial(dp(P), n, C.c_double(levels[j % L]), C.c_uint(j // L + 1), C.c_double(image[0]),
+                                     C.c_double(image[1]), dp(out))
+            assert np.array_equal(out.reshape(n, 6).T, dev["Corresp"][b]), (n, image, j)
+
+
 def test_device_resident_sweep_equals_host_driven_sweep(tvf):
     """f3: tvf_sweep_run (generate + solve + per-level reduction on the device) == run_sweep (host-generated
     inputs, results copied back, NumPy reduction)."""

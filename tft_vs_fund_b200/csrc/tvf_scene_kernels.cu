@@ -63,6 +63,7 @@ sweep_seeds_kernel(long long first_trial, long long B, int n, const double* __re
 //   * the seeding recurrence (624 dependent steps) and the sub-sample shuffle (data-dependent swaps) are serial; the
 //     shuffle runs on lane 0 over words that all lanes tempered beforehand.
 constexpr int SW_WARPS = 1;                     // warps (= seeds) per CTA
+constexpr int SW_CAP = 32;                      // points per chunk of a refill pass (one per lane)
 constexpr unsigned SW_FULL = 0xffffffffu;
 
 struct WarpMT {
@@ -75,7 +76,7 @@ struct WarpMT {
     __device__ __forceinline__ void seed(uint32_t s) {                     // init_genrand
         uint32_t* dst = raw + 624;
         __syncwarp();
-#pragma unroll 4
+#pragma unroll 8
         for (int i = 0; i < 624; ++i) {
             if (lane == 0) dst[i] = s;
             s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
@@ -121,26 +122,35 @@ struct WarpMT {
         }
         if (b_hi == cur + 1 && !have_next) make_next();
     }
-    __device__ __forceinline__ uint32_t word(int pos) const {               // genrand_int32 output number `pos`
-        const int b = pos / 624;
-        uint32_t y = raw[(b & 1) * 624 + (pos - b * 624)];
+    static __device__ __forceinline__ uint32_t temper(uint32_t y) {
         y ^= (y >> 11);
         y ^= (y << 7) & 0x9d2c5680u;
         y ^= (y << 15) & 0xefc60000u;
         y ^= (y >> 18);
         return y;
     }
-    __device__ __forceinline__ double res53(int pos) const {                // genrand_res53 from words pos, pos + 1
-        const uint32_t a = word(pos) >> 5, b = word(pos + 1) >> 6;
+    // genrand_int32 outputs number pos .. pos + K - 1
+    template <int K>
+    __device__ __forceinline__ void words(int pos, uint32_t (&w)[K]) const {
+        const int b = pos / 624, off = pos - b * 624;
+        const uint32_t* lo = raw + (b & 1) * 624 + off;
+        const uint32_t* hi = raw + ((b + 1) & 1) * 624 + off - 624;
+#pragma unroll
+        for (int t = 0; t < K; ++t) w[t] = temper((off + t < 624) ? lo[t] : hi[t]);
+    }
+    static __device__ __forceinline__ double res53(uint32_t w0, uint32_t w1) {          // genrand_res53
+        const uint32_t a = w0 >> 5, b = w1 >> 6;
         return (a * 67108864.0 + b) / 9007199254740992.0;
     }
 };
 
 // X = 400*rand(3,1)-200 from the six words at `pos`, projected by the three cameras (generateSyntheticScene.m:82-87)
 __device__ __forceinline__ void sw_point(const WarpMT& mt, int pos, const double* __restrict__ P, double* __restrict__ dst) {
-    const double X = TVF_ADD(TVF_MUL(400.0, mt.res53(pos)), -200.0);
-    const double Y = TVF_ADD(TVF_MUL(400.0, mt.res53(pos + 2)), -200.0);
-    const double Z = TVF_ADD(TVF_MUL(400.0, mt.res53(pos + 4)), -200.0);
+    uint32_t w[6];
+    mt.words<6>(pos, w);
+    const double X = TVF_ADD(TVF_MUL(400.0, WarpMT::res53(w[0], w[1])), -200.0);
+    const double Y = TVF_ADD(TVF_MUL(400.0, WarpMT::res53(w[2], w[3])), -200.0);
+    const double Z = TVF_ADD(TVF_MUL(400.0, WarpMT::res53(w[4], w[5])), -200.0);
 #pragma unroll
     for (int v = 0; v < 3; ++v) {
         const double* Pv = P + 12 * v;
@@ -153,30 +163,30 @@ __device__ __forceinline__ void sw_point(const WarpMT& mt, int pos, const double
     }
 }
 
-// 3*M accepted polar pairs from stream position `pos` on, in the reference's order (view-major, then point; the first
-// value returned for a pair is f*x2, the cached one f*x1).  ADD: buf[6i+2v..] += z*noise (refill passes, :90-92), else
-// buf = z (first pass, noise applied per level).  Returns the stream position after the last pair consumed.
-template <bool ADD>
-__device__ __forceinline__ int sw_normals(WarpMT& mt, int pos, int M, double noise, double* __restrict__ buf) {
+// The 3*M accepted polar pairs that follow stream position `pos`, in the reference's order (view-major, then point;
+// the first value returned for a pair is f*x2, the cached one f*x1).  The draws of the points i in [i_lo, i_hi) are
+// stored at buf[6*(i - i_lo) + 2*view ..]; the others are only counted.  Returns the stream position after the last pair.
+__device__ __forceinline__ int sw_normals(WarpMT& mt, int pos, int M, int i_lo, int i_hi, double* __restrict__ buf) {
     const int need = 3 * M, lane = mt.lane;
     const unsigned lt = (1u << lane) - 1u;
     int got = 0;
     while (got < need) {
         mt.prepare(pos, pos + 127);
-        const int p = pos + 4 * lane;
-        const double x1 = TVF_ADD(TVF_MUL(2.0, mt.res53(p)), -1.0);
-        const double x2 = TVF_ADD(TVF_MUL(2.0, mt.res53(p + 2)), -1.0);
+        uint32_t w[4];
+        mt.words<4>(pos + 4 * lane, w);
+        const double x1 = TVF_ADD(TVF_MUL(2.0, WarpMT::res53(w[0], w[1])), -1.0);
+        const double x2 = TVF_ADD(TVF_MUL(2.0, WarpMT::res53(w[2], w[3])), -1.0);
         const double r2 = TVF_ADD(TVF_MUL(x1, x1), TVF_MUL(x2, x2));
         const bool acc = !(r2 >= 1.0 || r2 == 0.0);
         const unsigned bal = __ballot_sync(SW_FULL, acc);
         const int idx = got + __popc(bal & lt);
         if (acc && idx < need) {
-            const double f = TVF_SQRT(TVF_DIV(TVF_MUL(-2.0, tvf_log(r2)), r2));
-            const double z0 = TVF_MUL(f, x2), z1 = TVF_MUL(f, x1);
             const int v = idx / M, i = idx - v * M;
-            double* d = buf + 6 * i + 2 * v;
-            if (ADD) { d[0] = TVF_ADD(d[0], TVF_MUL(z0, noise)); d[1] = TVF_ADD(d[1], TVF_MUL(z1, noise)); }
-            else { d[0] = z0; d[1] = z1; }
+            if (i >= i_lo && i < i_hi) {
+                const double f = TVF_SQRT(TVF_DIV(TVF_MUL(-2.0, tvf_log(r2)), r2));
+                double* d = buf + 6 * (i - i_lo) + 2 * v;
+                d[0] = TVF_MUL(f, x2); d[1] = TVF_MUL(f, x1);
+            }
         }
         const unsigned last = __ballot_sync(SW_FULL, acc && idx == need - 1);
         if (last) { pos += 4 * __ffs(last); got = need; }
@@ -196,7 +206,32 @@ __device__ __forceinline__ bool sw_inside(const double* p, double hi_x, double h
     return inside;
 }
 
-__host__ __device__ inline size_t sw_warp_bytes(int N) { return 2 * 624 * 4 + (size_t)3 * 48 * N + 2 * (size_t)((N + 15) & ~15); }
+// x = clean + z*noise for this lane's point (:90-92); the inside-image points of the warp, in lane order, go to the
+// sub-sample positions outpos[filled ...] (-1: not sampled).  Returns the number of inside points.
+__device__ __forceinline__ int sw_emit(bool have, const double* __restrict__ cl, const double* __restrict__ zz, double noise,
+                                       double hi_x, double hi_y, const signed char* __restrict__ outpos, int filled,
+                                       unsigned lt, double* __restrict__ o) {
+    double p[6];
+    bool inside = false;
+    if (have) {
+#pragma unroll
+        for (int q = 0; q < 6; ++q) p[q] = TVF_ADD(cl[q], TVF_MUL(zz[q], noise));
+        inside = sw_inside(p, hi_x, hi_y);
+    }
+    const unsigned bal = __ballot_sync(SW_FULL, inside);
+    if (inside) {
+        const int k = outpos[filled + __popc(bal & lt)];
+        if (k >= 0) {
+            double2* d = reinterpret_cast<double2*>(o + 6 * k);
+            d[0] = make_double2(p[0], p[1]); d[1] = make_double2(p[2], p[3]); d[2] = make_double2(p[4], p[5]);
+        }
+    }
+    return __popc(bal);
+}
+
+__host__ __device__ inline size_t sw_warp_bytes(int N) {
+    return 2 * 624 * 4 + (size_t)2 * 48 * N + (size_t)2 * 48 * SW_CAP + 2 * (size_t)((N + 15) & ~15);
+}
 
 __global__ void __launch_bounds__(SW_WARPS * 32)
 sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double* __restrict__ noise_levels, int L,
@@ -210,9 +245,10 @@ sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double*
     unsigned char* base = sw_smem + 288 + (size_t)warp * sw_warp_bytes(N);
     double* clean = reinterpret_cast<double*>(base);                         // first pass: projections without noise
     double* z = clean + 6 * N;                                               // first pass: the Gaussian draws
-    double* c = z + 6 * N;                                                   // refill passes; tempered words for the shuffle
+    double* cc = z + 6 * N;                                                  // refill chunk: projections  (shuffle: tempered words)
+    double* cz = cc + 6 * SW_CAP;                                            // refill chunk: Gaussian draws (shuffle: swap list)
     WarpMT mt;
-    mt.raw = reinterpret_cast<uint32_t*>(c + 6 * N);
+    mt.raw = reinterpret_cast<uint32_t*>(cz + 6 * SW_CAP);
     mt.lane = lane;
     unsigned char* arr = reinterpret_cast<unsigned char*>(mt.raw + 2 * 624);
     signed char* outpos = reinterpret_cast<signed char*>(arr + Npad);
@@ -230,28 +266,39 @@ sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double*
     for (int i = lane; i < N; i += 32) { arr[i] = (unsigned char)i; outpos[i] = -1; }
     mt.seed((uint32_t)(s + 1));
     {
-        uint32_t* tw = reinterpret_cast<uint32_t*>(c);
+        // random_interval(top) = first word w (masked to the smallest 2^k - 1 >= top) with w <= top, for top = N-1 .. 1.
+        // Whether word l of a batch is accepted depends on how many words before it were: a triangular system, solved
+        // by fixed-point iteration on the ballot (bits 0..t-1 are final after t rounds; 2-4 rounds in practice).  The
+        // swaps themselves are order dependent and run on lane 0 from the compacted (top, j) list.
+        unsigned short* swaps = reinterpret_cast<unsigned short*>(cz);
         int top = N - 1, pos = 0;
-        uint32_t mask = (top >= 1) ? (0xffffffffu >> __clz(top)) : 0u;     // random_interval: smallest 2^k - 1 >= max
         while (top >= 1) {
-            mt.prepare(pos, pos + 255);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) tw[32 * q + lane] = mt.word(pos + 32 * q + lane);
+            mt.prepare(pos, pos + 31);
+            uint32_t w[1];
+            mt.words<1>(pos + lane, w);
+            unsigned acc = 0;
+            int my_top; uint32_t v = 0;
+            while (true) {
+                my_top = top - __popc(acc & lt);
+                bool a = false;
+                if (my_top >= 1) { v = w[0] & (0xffffffffu >> __clz(my_top)); a = v <= (uint32_t)my_top; }
+                const unsigned nacc = __ballot_sync(SW_FULL, a);
+                if (nacc == acc) break;
+                acc = nacc;
+            }
+            const unsigned past = __ballot_sync(SW_FULL, my_top < 1);       // words after the shuffle has finished
+            const int used = past ? __ffs(past) - 1 : 32;
+            const int cnt = __popc(acc);
+            if ((acc >> lane) & 1u) swaps[__popc(acc & lt)] = (unsigned short)((my_top << 8) | (int)v);
             __syncwarp();
             if (lane == 0) {
-                int k = 0;
-                while (k < 256 && top >= 1) {
-                    const uint32_t v = tw[k++] & mask;
-                    if (v <= (uint32_t)top) {
-                        const unsigned char t = arr[top]; arr[top] = arr[v]; arr[v] = t;
-                        --top;
-                        if ((uint32_t)top == (mask >> 1)) mask >>= 1;
-                    }
+                for (int r = 0; r < cnt; ++r) {
+                    const int pr = swaps[r], t = pr >> 8, j = pr & 255;
+                    const unsigned char tmp = arr[t]; arr[t] = arr[j]; arr[j] = tmp;
                 }
-                pos += k;
             }
-            top = __shfl_sync(SW_FULL, top, 0); pos = __shfl_sync(SW_FULL, pos, 0); mask = __shfl_sync(SW_FULL, mask, 0);
             __syncwarp();
+            top -= cnt; pos += used;
         }
         for (int k = lane; k < n; k += 32) outpos[arr[k]] = (signed char)k;
         __syncwarp();
@@ -263,66 +310,41 @@ sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double*
         const int i = i0 + lane;
         if (i < N) sw_point(mt, 6 * i, P, clean + 6 * i);
     }
-    const int snap_pos = sw_normals<false>(mt, 6 * N, N, 0.0, z);
-    // ---- per noise level: scale the draws, inside-image mask + compaction, refill passes (:95-110)
+    const int snap_pos = sw_normals(mt, 6 * N, N, 0, N, z);
+    // ---- per noise level: scale the draws, inside-image mask + compaction, refill passes (:95-110).
+    // The first refill pass of a level starts at snap_pos for every level, and its points and draws do not depend on
+    // the noise level -- only their number M does.  Levels with the same M (the usual case) reuse them.
+    int memo_M = -1, memo_end = 0;
     for (int lv = lv_lo; lv < lv_hi; ++lv) {
         const double noise = noise_levels[lv];
         double* o = out0 + (size_t)(lv - lv_lo) * 6 * n;
         int filled = 0;
         for (int i0 = 0; i0 < N; i0 += 32) {
-            const int i = i0 + lane;
-            double p[6];
-            bool inside = false;
-            if (i < N) {
-#pragma unroll
-                for (int q = 0; q < 6; ++q) p[q] = TVF_ADD(clean[6 * i + q], TVF_MUL(z[6 * i + q], noise));
-                inside = sw_inside(p, hi_x, hi_y);
-            }
-            const unsigned bal = __ballot_sync(SW_FULL, inside);
-            if (inside) {
-                const int k = outpos[filled + __popc(bal & lt)];
-                if (k >= 0) {
-                    double2* d = reinterpret_cast<double2*>(o + 6 * k);
-                    d[0] = make_double2(p[0], p[1]); d[1] = make_double2(p[2], p[3]); d[2] = make_double2(p[4], p[5]);
-                }
-            }
-            filled += __popc(bal);
+            const int i = (i0 + lane < N) ? i0 + lane : N - 1;
+            filled += sw_emit(i0 + lane < N, clean + 6 * i, z + 6 * i, noise, hi_x, hi_y, outpos, filled, lt, o);
         }
         int M = N - filled, pos = snap_pos;
+        bool first = true;
         while (M > 0) {
-            __syncwarp();
-            for (int i0 = 0; i0 < M; i0 += 32) {
-                const int i1 = (i0 + 32 < M) ? i0 + 32 : M;
-                mt.prepare(pos + 6 * i0, pos + 6 * i1 - 1);
-                const int i = i0 + lane;
-                if (i < M) sw_point(mt, pos + 6 * i, P, c + 6 * i);
-            }
-            __syncwarp();
-            pos = sw_normals<true>(mt, pos + 6 * M, M, noise, c);
-            for (int i0 = 0; i0 < M; i0 += 32) {
-                const int i = i0 + lane;
-                double p[6];
-                bool inside = false;
-                if (i < M) {
-#pragma unroll
-                    for (int q = 0; q < 6; ++q) p[q] = c[6 * i + q];
-                    inside = sw_inside(p, hi_x, hi_y);
+            int end_pos = pos;
+            for (int c0 = 0; c0 < M; c0 += SW_CAP) {
+                const int c1 = (c0 + SW_CAP < M) ? c0 + SW_CAP : M;
+                const bool memoable = first && M <= SW_CAP;
+                if (memoable && memo_M == M) end_pos = memo_end;
+                else {
+                    __syncwarp();
+                    mt.prepare(pos + 6 * c0, pos + 6 * c1 - 1);
+                    if (c0 + lane < c1) sw_point(mt, pos + 6 * (c0 + lane), P, cc + 6 * lane);
+                    __syncwarp();
+                    end_pos = sw_normals(mt, pos + 6 * M, M, c0, c1, cz);
+                    memo_M = memoable ? M : -1; memo_end = end_pos;
                 }
-                const unsigned bal = __ballot_sync(SW_FULL, inside);
-                if (inside) {
-                    const int k = outpos[filled + __popc(bal & lt)];
-                    if (k >= 0) {
-                        double2* d = reinterpret_cast<double2*>(o + 6 * k);
-                        d[0] = make_double2(p[0], p[1]); d[1] = make_double2(p[2], p[3]); d[2] = make_double2(p[4], p[5]);
-                    }
-                }
-                filled += __popc(bal);
+                filled += sw_emit(c0 + lane < c1, cc + 6 * lane, cz + 6 * lane, noise, hi_x, hi_y, outpos, filled, lt, o);
             }
-            M = N - filled;
+            pos = end_pos; M = N - filled; first = false;
         }
     }
 }
-
 
 void launch_sweep_trials(long long first_trial, long long B, int n, const double* d_noise_levels, int L, const double* d_P,
                          double hi_x, double hi_y, double* d_out, cudaStream_t stream) {

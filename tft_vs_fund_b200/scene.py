@@ -259,10 +259,13 @@ def sweep_batch(B, n=20, first_trial=0, noise_levels=None, focalL=50, angle=0, w
     return dict(Corresp=out, CalM=np.tile(K, (3, 1)), R_t0=R_t0, noise=noise_levels[jj % L], seed=jj // L + 1)
 
 
-def sweep_batch_device(B, n=20, first_trial=0, noise_levels=None, focalL=50, angle=0, device=None, out_ptr=None):
-    """Same trials as sweep_batch, generated by the CUDA kernel behind tvf_generate_sweep (one thread per trial).
+def sweep_batch_device(B, n=20, first_trial=0, noise_levels=None, focalL=50, angle=0, device=None, out_ptr=None,
+                       image=None, meta=True):
+    """Same trials as sweep_batch, generated by the CUDA kernel behind tvf_generate_sweep (one warp per seed).
     Returns the same dict (Corresp as a NumPy array) or, with `out_ptr` (a device pointer to 6*n*B doubles),
-    fills that buffer in place and returns the dict without "Corresp".  Bit-exact with sweep_batch."""
+    fills that buffer in place and returns the dict without "Corresp".  Bit-exact with sweep_batch.
+    `image` = (width, height) of the inside-image test (default: the reference's 36 x 24 mm sensor in pixels);
+    `meta=False` skips the per-trial noise / seed arrays (B-sized host work that can exceed the kernel time)."""
     import ctypes as C
     from . import _lib
     if noise_levels is None:
@@ -273,12 +276,15 @@ def sweep_batch_device(B, n=20, first_trial=0, noise_levels=None, focalL=50, ang
     P = np.ascontiguousarray(np.stack(Ps), dtype=np.float64)            # (3,3,4) row-major
     h = _lib.handle(device)
     dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
-    jj = np.arange(first_trial, first_trial + B)
-    d = dict(CalM=np.tile(K, (3, 1)), R_t0=R_t0, noise=noise_levels[jj % L], seed=jj // L + 1)
+    d = dict(CalM=np.tile(K, (3, 1)), R_t0=R_t0)
+    if meta:
+        jj = np.arange(first_trial, first_trial + B)
+        d.update(noise=noise_levels[jj % L], seed=jj // L + 1)
+    hi_x, hi_y = (36 * PIX, 24 * PIX) if image is None else (float(image[0]), float(image[1]))
     if out_ptr is not None:
-        h.call("tvf_generate_sweep_dev", first_trial, B, n, dp(noise_levels), L, dp(P), 36 * PIX, 24 * PIX, C.c_void_p(out_ptr))
+        h.call("tvf_generate_sweep_dev", first_trial, B, n, dp(noise_levels), L, dp(P), hi_x, hi_y, C.c_void_p(out_ptr))
         return d
     out = np.empty((B, n, 6))
-    h.call("tvf_generate_sweep", first_trial, B, n, dp(noise_levels), L, dp(P), 36 * PIX, 24 * PIX, dp(out))
+    h.call("tvf_generate_sweep", first_trial, B, n, dp(noise_levels), L, dp(P), hi_x, hi_y, dp(out))
     d["Corresp"] = np.ascontiguousarray(out.transpose(0, 2, 1))
     return d
