@@ -18,7 +18,13 @@ using namespace tvf;
 
 namespace {
 
-constexpr int NSLOT = 3;
+#ifndef TVF_NSLOT
+#define TVF_NSLOT 3
+#endif
+#ifndef TVF_RAMP
+#define TVF_RAMP 0
+#endif
+constexpr int NSLOT = TVF_NSLOT;
 constexpr int NSCRATCH = 16;
 constexpr int64_t DEFAULT_CHUNK = 65536;        // host-pointer entry points: chunks are the H2D / kernels / D2H pipeline stages
 constexpr int64_t DEFAULT_CHUNK_DEV = 524288;   // device-pointer entry points: fewer, larger launches (less launch and wave-tail
@@ -262,9 +268,26 @@ int pose_host(tvf_handle_t h, Method method, const double* corresp, const double
     int32_t* st_host = status;
     if (!st_host) { st_tmp.resize((size_t)B); st_host = st_tmp.data(); }
 
+    // Chunk schedule.  The call is bound by the host link (H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1
+    // overlap).  Quarter- and half-size chunks at both ends, meant to shorten the pipeline's fill and drain, were
+    // measured SLOWER (4.31e7 vs 4.56e7 solves/s end to end at 1 M problems, profiles/r01_variants.md) and are off.
+    const bool ramp = TVF_RAMP && B >= 6 * C && C >= 4096;
     int64_t done = 0; int ci = 0;
     while (done < B) {
-        const int64_t Bc = (B - done < C) ? (B - done) : C;
+        const int64_t rem = B - done;
+        int64_t Bc = (rem < C) ? rem : C;
+        if (ramp) {
+            const int64_t tail = C / 2 + C / 4;          // the last two chunks: C/2, then C/4
+            if (rem > tail) {
+                const int64_t body = rem - tail;
+                if (ci == 0) Bc = C / 4;
+                else if (ci == 1) Bc = C / 2;
+                else if (body >= 2 * C) Bc = C;
+                else if (body > C) Bc = (body + 1) / 2;
+                else Bc = body;
+            } else if (rem > C / 4) Bc = rem - C / 4;
+            else Bc = rem;
+        }
         Slot& s = h->slot[ci % NSLOT];
         TVF_CK(cudaStreamSynchronize(s.stream));        // slot reuse: its previous chunk (incl. D2H) is finished
         rc = ensure_arena(h, s, need); if (rc) return rc;

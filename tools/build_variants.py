@@ -11,8 +11,9 @@ from tft_vs_fund_b200 import build as B   # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "cheir2": ["-DTVF_CHEIR_UNROLL=2"],
-    "cheir2_t1": ["-DTVF_CHEIR_UNROLL=2", "-DTVF_TAIL_MINB=1"],
+    "nslot4": ["-DTVF_NSLOT=4"],
+    "nslot6": ["-DTVF_NSLOT=6"],
+    "ramp_nslot4": ["-DTVF_NSLOT=4", "-DTVF_RAMP=1"],
 }
 
 
