@@ -875,7 +875,9 @@ int tvf_sweep_run(tvf_handle_t h, int method, int64_t first_trial, int64_t B, in
     Slot& s = h->slot[0];
     cudaStream_t st = s.stream;
     const int Q = 512;
-    const int64_t C = pick_chunk(h, n, B > 0 ? B : 1, true);
+    // nothing crosses the bus here, so the solver runs its large device-path launches (the per-problem output buffers of
+    // the host-path layout are still needed: the evaluation kernels read them)
+    const int64_t C = pick_chunk(h, n, B > 0 ? B : 1, false);
     const size_t need = carve(nullptr, n, C, true, false, nullptr);
     rc = ensure_arena(h, s, need); if (rc) return rc;
     ChunkBufs b; carve(s.arena, n, C, true, false, &b);
@@ -888,9 +890,9 @@ int tvf_sweep_run(tvf_handle_t h, int method, int64_t first_trial, int64_t B, in
     TVF_CK(cudaMemcpyAsync(pr, Rt0_2, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
     TVF_CK(cudaMemcpyAsync((double*)pr + 12, Rt0_3, 12 * sizeof(double), cudaMemcpyHostToDevice, st));
     TVF_CK(cudaMemsetAsync(pp, 0, (size_t)L * Q * 5 * sizeof(double), st));
-    // The generator shares one pass per seed among its L noise levels (one thread per seed), so it wants many seeds
-    // per launch: trials are generated in super-chunks of up to 16 solver chunks into a staging buffer.
-    const int64_t G = (B < 16 * C) ? B : 16 * C;
+    // The generator shares one pass per seed among its L noise levels (one warp per seed), so it wants many seeds
+    // per launch: trials are generated in super-chunks of up to 4 solver chunks into a staging buffer.
+    const int64_t G = (B < 4 * C) ? B : 4 * C;
     void* pg;
     rc = ensure_scratch(h, NSCRATCH - 7, (size_t)G * 6 * n * sizeof(double), &pg); if (rc) return rc;
     for (int64_t gdone = 0; gdone < B; gdone += G) {

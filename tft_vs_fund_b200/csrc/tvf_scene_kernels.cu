@@ -62,6 +62,9 @@ sweep_seeds_kernel(long long first_trial, long long B, int n, const double* __re
 //   * inside-image compaction: ballot ranks in point order -> position in the sub-sample (outpos) -> 48-byte store.
 //   * the seeding recurrence (624 dependent steps) and the sub-sample shuffle (data-dependent swaps) are serial; the
 //     shuffle runs on lane 0 over words that all lanes tempered beforehand.
+#ifndef TVF_SW_MINB
+#define TVF_SW_MINB 14                             // resident warps per SM the kernel is compiled for (128 registers)
+#endif
 constexpr int SW_WARPS = 1;                     // warps (= seeds) per CTA
 constexpr int SW_CAP = 32;                      // points per chunk of a refill pass (one per lane)
 constexpr unsigned SW_FULL = 0xffffffffu;
@@ -230,10 +233,12 @@ __device__ __forceinline__ int sw_emit(bool have, const double* __restrict__ cl,
 }
 
 __host__ __device__ inline size_t sw_warp_bytes(int N) {
-    return 2 * 624 * 4 + (size_t)2 * 48 * N + (size_t)2 * 48 * SW_CAP + 2 * (size_t)((N + 15) & ~15);
+    return 2 * 624 * 4 + (size_t)48 * N + (size_t)2 * 48 * SW_CAP + 2 * (size_t)((N + 15) & ~15);
 }
 
-__global__ void __launch_bounds__(SW_WARPS * 32)
+// SLOTS = ceil(N / 32): the noise-free projections of a lane's points (32 q + lane) stay in registers.
+template <int SLOTS>
+__global__ void __launch_bounds__(SW_WARPS * 32, TVF_SW_MINB)
 sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double* __restrict__ noise_levels, int L,
                         const double* __restrict__ Pg, double hi_x, double hi_y, double* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char sw_smem[];
@@ -243,8 +248,7 @@ sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double*
     for (int i = threadIdx.x; i < 36; i += blockDim.x) P[i] = Pg[i];
     __syncthreads();
     unsigned char* base = sw_smem + 288 + (size_t)warp * sw_warp_bytes(N);
-    double* clean = reinterpret_cast<double*>(base);                         // first pass: projections without noise
-    double* z = clean + 6 * N;                                               // first pass: the Gaussian draws
+    double* z = reinterpret_cast<double*>(base);                             // first pass: the Gaussian draws
     double* cc = z + 6 * N;                                                  // refill chunk: projections  (shuffle: tempered words)
     double* cz = cc + 6 * SW_CAP;                                            // refill chunk: Gaussian draws (shuffle: swap list)
     WarpMT mt;
@@ -304,11 +308,17 @@ sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double*
         __syncwarp();
     }
     // ---- generateSyntheticScene.m:75-92, first pass (rng(seed) again: the same stream from its start)
-    for (int i0 = 0; i0 < N; i0 += 32) {
-        const int i1 = (i0 + 32 < N) ? i0 + 32 : N;
-        mt.prepare(6 * i0, 6 * i1 - 1);
-        const int i = i0 + lane;
-        if (i < N) sw_point(mt, 6 * i, P, clean + 6 * i);
+    double clean[SLOTS][6];                                                  // first pass: projections without noise
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+        const int i0 = 32 * q;
+#pragma unroll
+        for (int t = 0; t < 6; ++t) clean[q][t] = 0.0;
+        if (i0 < N) {
+            const int i1 = (i0 + 32 < N) ? i0 + 32 : N;
+            mt.prepare(6 * i0, 6 * i1 - 1);
+            if (i0 + lane < N) sw_point(mt, 6 * (i0 + lane), P, clean[q]);
+        }
     }
     const int snap_pos = sw_normals(mt, 6 * N, N, 0, N, z);
     // ---- per noise level: scale the draws, inside-image mask + compaction, refill passes (:95-110).
@@ -319,9 +329,13 @@ sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double*
         const double noise = noise_levels[lv];
         double* o = out0 + (size_t)(lv - lv_lo) * 6 * n;
         int filled = 0;
-        for (int i0 = 0; i0 < N; i0 += 32) {
-            const int i = (i0 + lane < N) ? i0 + lane : N - 1;
-            filled += sw_emit(i0 + lane < N, clean + 6 * i, z + 6 * i, noise, hi_x, hi_y, outpos, filled, lt, o);
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) {
+            const int i0 = 32 * q;
+            if (i0 < N) {
+                const int i = (i0 + lane < N) ? i0 + lane : N - 1;
+                filled += sw_emit(i0 + lane < N, clean[q], z + 6 * i, noise, hi_x, hi_y, outpos, filled, lt, o);
+            }
         }
         int M = N - filled, pos = snap_pos;
         bool first = true;
@@ -354,13 +368,11 @@ void launch_sweep_trials(long long first_trial, long long B, int n, const double
     const long long seeds = (first_trial + B - 1) / L - first_trial / L + 1;
     if (!per_thread && (reinterpret_cast<uintptr_t>(d_out) & 15) == 0) {
         const size_t smem = 288 + SW_WARPS * sw_warp_bytes(n + 100);
-        static size_t smem_set = 0;
-        if (smem > smem_set) {
-            cudaFuncSetAttribute(sweep_seeds_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            smem_set = smem;
-        }
-        sweep_seeds_warp_kernel<<<(unsigned)((seeds + SW_WARPS - 1) / SW_WARPS), SW_WARPS * 32, smem, stream>>>(
-            first_trial, B, n, d_noise_levels, L, d_P, hi_x, hi_y, d_out);
+        const unsigned grid = (unsigned)((seeds + SW_WARPS - 1) / SW_WARPS);
+        if (n + 100 <= 128)
+            sweep_seeds_warp_kernel<4><<<grid, SW_WARPS * 32, smem, stream>>>(first_trial, B, n, d_noise_levels, L, d_P, hi_x, hi_y, d_out);
+        else
+            sweep_seeds_warp_kernel<5><<<grid, SW_WARPS * 32, smem, stream>>>(first_trial, B, n, d_noise_levels, L, d_P, hi_x, hi_y, d_out);
         return;
     }
     if (L >= 4) {

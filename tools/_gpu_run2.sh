@@ -1,16 +1,12 @@
-set -x
 mkdir -p gpurun_out
-show() { python - <<PY
+timeout 300 python -m pytest tests -x -q -m gpu -k "device_scene_generator or device_resident_sweep or experiments_sweep_table" > gpurun_out/gen_tests.log 2>&1; echo "tests exit $?"; tail -3 gpurun_out/gen_tests.log | cut -c1-300
+for v in base swminb12; do
+  TVF_LIBPATH=$PWD/tools/_build/variants/libtvf_$v.so timeout 240 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/v_$v.json 2> gpurun_out/v_$v.err
+  python - <<PY
 import json
 try:
-    d=json.loads(open("gpurun_out/v_$1.json").read().strip().splitlines()[-1])
-    print("variant $1 value %.4g e2e %.4g" % (d["value"], d["e2e"]["value"]))
-except Exception as e: print("variant $1 parse fail", e)
+    d=json.loads(open("gpurun_out/v_$v.json").read().strip().splitlines()[-1])
+    print("variant $v value %.4g e2e %.4g sweep %.4g gen_warm_ms %.3f" % (d["value"], d["e2e"]["value"], d["device_resident_sweep"]["value"], d["input_generation"]["seconds_warm"]*1e3))
+except Exception as e: print("variant $v parse fail", e)
 PY
-}
-for v in base nslot4 nslot6 ramp_nslot4; do
-  for c in 0 32768; do
-  TVF_LIBPATH=$PWD/tools/_build/variants/libtvf_$v.so timeout 240 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --chunk $c > gpurun_out/v_${v}_$c.json 2> gpurun_out/v_${v}_$c.err
-  show ${v}_$c
-  done
 done

@@ -11,9 +11,7 @@ from tft_vs_fund_b200 import build as B   # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "nslot4": ["-DTVF_NSLOT=4"],
-    "nslot6": ["-DTVF_NSLOT=6"],
-    "ramp_nslot4": ["-DTVF_NSLOT=4", "-DTVF_RAMP=1"],
+    "swminb12": ["-DTVF_SW_MINB=12"],
 }
 
 
