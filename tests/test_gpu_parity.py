@@ -459,6 +459,33 @@ def test_device_scene_generator(tvf):
     assert np.max(np.abs(a.repr_err - b.repr_err)) < 1e-7
 
 
+@pytest.mark.parametrize("method", ["tft", "f", "optf"])
+def test_degenerate_problems_are_flagged_and_isolated(tvf, method):
+    """NaN / Inf coordinates, all points identical and a batch of zeros: MATLAB's svd raises on NaN/Inf input and the
+    reference dies; here such problems must come back (no hang, no CUDA error) with a non-zero status or non-finite
+    outputs, and must not disturb their neighbours in the batch (bitwise equal to a run without them)."""
+    from tft_vs_fund_b200 import scene
+    fn = {"tft": tvf.LinearTFTPoseEstimation, "f": tvf.LinearFPoseEstimation, "optf": tvf.OptimFPoseEstimation}[method]
+    d = scene.sweep_batch(64, 20, first_trial=13)
+    C, CalM = d["Corresp"].copy(), d["CalM"]
+    good = fn(C, CalM)
+    bad = {3: "nan", 10: "inf", 17: "same", 30: "zero", 41: "nan_one"}
+    Cb = C.copy()
+    Cb[3] = np.nan
+    Cb[10, :, 5] = np.inf
+    Cb[17] = Cb[17][:, :1]
+    Cb[30] = 0.0
+    Cb[41, 2, 7] = np.nan
+    res = fn(Cb, CalM)
+    keep = np.array([b for b in range(64) if b not in bad])
+    for k in range(4):
+        assert np.array_equal(res[k][keep], good[k][keep])
+    assert np.array_equal(res.repr_err[keep], good.repr_err[keep]) and np.array_equal(res.status[keep], good.status[keep])
+    for b, kind in bad.items():
+        finite = np.all(np.isfinite(res[0][b])) and np.all(np.isfinite(res[1][b])) and np.isfinite(res.repr_err[b])
+        assert res.status[b] != 0 or not finite, (method, kind)
+
+
 def test_device_scene_generator_small_image(tvf, hostcheck):
     """A small image makes most points fall outside: many refill passes per trial, refill passes with more than 32
     points (the chunked path of the warp-per-seed kernel), streams that run over dozens of MT19937 state blocks and

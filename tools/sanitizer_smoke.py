@@ -13,3 +13,4 @@ dev = scene.sweep_batch_device(100, 20, first_trial=7)
 host = scene.sweep_batch(100, 20, first_trial=7)
 print("gen equal", np.array_equal(dev["Corresp"], host["Corresp"]))
 t = experiments.run_sweep_device(13 * 4, 20, methods=(1, 7)); print("sweep ok", t[1][:2, 0])
+dev = scene.sweep_batch_device(30, 20, noise_levels=[0.0, 2.5], image=(1100.0, 800.0)); print("small image ok", dev["Corresp"].shape)
