@@ -1,6 +1,7 @@
 set -x
 T=${1:-r1g}
 mkdir -p gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/${T}_tests.log 2>&1; echo "tests exit $?"; tail -3 gpurun_out/${T}_tests.log | cut -c1-300
 # ncu --set full of one launch of every kernel of the TFT step (524 288 problems per launch), summarised on the box so
 # that the bench line below carries the counters of THIS build
