@@ -208,7 +208,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---- GPU arm -------------------------------------------------------------------------------------
@@ -498,7 +498,7 @@ def run_gpu(args, rank, local_rank, world):
         "flagged_problems": flagged,
         "input_generation": {"where": "device (tvf_generate_sweep_dev, TVF scene RNG v2)", "seconds": t_gen, "seconds_warm": t_gen2, "trials_per_s_warm": B / t_gen2, "check": gen_check},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -590,10 +590,31 @@ def run_large_n(args, local_rank):
         "flagged_problems": int(torch.count_nonzero(d_st).item()), "clocks": clocks,
         "gpu_launches": int(sum(v[1] for v in prof.values())),
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE line, the JSON result.  Libraries print there too (NCCL writes its version line to
+    stdout when the box exports NCCL_DEBUG=VERSION), so the real stdout is set aside for emit() and file descriptor 1
+    is pointed at stderr for everything else (this process and the libraries it loads)."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
