@@ -1,11 +1,10 @@
 import numpy as np, sys
 sys.path.insert(0, "/root/repo")
 import tft_vs_fund_b200 as tvf
-import oracle as o
 from tft_vs_fund_b200 import scene, experiments
 # large-n cluster kernel (small batch), GH kernel, per-seed generator, device sweep
-Cs = np.stack([o.generateSyntheticScene(1100, 1.0, s, 50, 0)[2] for s in (1, 2, 3)])
-CalM = o.generateSyntheticScene(20, 1.0, 1, 50, 0)[0]
+Cs = np.stack([scene.generateSyntheticScene(1100, 1.0, s, 50, 0)[2] for s in (1, 2, 3)])
+CalM = scene.generateSyntheticScene(20, 1.0, 1, 50, 0)[0]
 r = tvf.LinearTFTPoseEstimation(Cs, CalM); print("large ok", r.status)
 d = scene.sweep_batch(60, 20)
 r = tvf.OptimFPoseEstimation(d["Corresp"], d["CalM"]); print("optf ok", r[4][:8])
