@@ -26,6 +26,10 @@ constexpr int EIG_MAX_ITER = 80;
 #ifndef TVF_EIG_PIVOTNORM
 #define TVF_EIG_PIVOTNORM 1
 #endif
+// software-pipelined Gauss-Jordan sweeps: measured 4.6 % SLOWER in stage 1 (profiles/r01_variants.md), off
+#ifndef TVF_GJ_PIPE
+#define TVF_GJ_PIPE 0
+#endif
 #ifndef TVF_EIG_TOL
 #define TVF_EIG_TOL 4.0e-15
 #endif
@@ -100,6 +104,41 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
 
     __syncwarp();                              // sbuf may still be read by a previous phase
     if (lane >= N && lane < NP) { sbuf[lane] = 0.0; sbuf[32 + lane] = 0.0; }
+#if TVF_GJ_PIPE
+    // Software-pipelined sweeps (same operations, same results bit for bit; REJECTED by measurement, kept as a knob): the
+    // serial part of a sweep -- pivot
+    // broadcast, reciprocal (five dependent FP64 operations), scaled column, its publication and the barrier before
+    // the row can be read back -- is ~110 cycles in which a warp has nothing else to issue.  Sweep k therefore updates
+    // column k+1 FIRST and starts that chain for sweep k+1 at once (into the other row buffer), so it runs under the
+    // remaining 25 DFMAs of sweep k.
+    double colj = g[0];
+    double piv = fast_rcp(fmax(shfl_d(colj, 0), floor_piv));
+    double rk = colj * piv;
+    if (lane < N) sbuf[lane] = rk;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        __syncwarp();                          // row k is in sbuf[(k & 1) * 32 ..]; the other buffer is free again
+        const double2* b2 = reinterpret_cast<const double2*>(sbuf + (k & 1) * 32);
+        const double c = colj - ((lane == k) ? 1.0 : 0.0);
+        double colj_n = 0.0, piv_n = 0.0, rk_n = 0.0;
+        if (k + 1 < N) {
+            const double2 r = b2[(k + 1) >> 1];
+            g[k + 1] = fma(-c, ((k + 1) & 1) ? r.y : r.x, g[k + 1]);
+            colj_n = g[k + 1];
+            piv_n = fast_rcp(fmax(shfl_d(colj_n, k + 1), floor_piv));
+            rk_n = colj_n * piv_n;
+            if (lane < N) sbuf[((k + 1) & 1) * 32 + lane] = rk_n;
+        }
+#pragma unroll
+        for (int m2 = 0; m2 < NP / 2; ++m2) {
+            const double2 r = b2[m2];
+            if (2 * m2 != k && 2 * m2 != k + 1 && 2 * m2 < N) g[2 * m2] = fma(-c, r.x, g[2 * m2]);
+            if (2 * m2 + 1 != k && 2 * m2 + 1 != k + 1 && 2 * m2 + 1 < N) g[2 * m2 + 1] = fma(-c, r.y, g[2 * m2 + 1]);
+        }
+        g[k] = (lane == k) ? -piv : rk;
+        colj = colj_n; piv = piv_n; rk = rk_n;
+    }
+#else
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const double colj = g[k];
@@ -119,6 +158,7 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
         }
         g[k] = (lane == k) ? -piv : rk;
     }
+#endif
     __syncwarp();                              // last sweep's row buffer is reused below
     // g now holds -(G + delta I)^-1 (scaled).  Power iteration on its negative.
     bool ok = false;
@@ -227,6 +267,35 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
 
     __syncwarp();                              // sbuf may still be read by a previous phase
     if (r >= N) { sbuf[lane] = 0.0; sbuf[32 + lane] = 0.0; }
+#if TVF_GJ_PIPE
+    double colj = g[0];                          // software-pipelined as in smallest_eigvec_spd
+    double piv = fast_rcp(fmax(__shfl_sync(FULL, colj, 0, 16), floor_piv));
+    double rk = colj * piv;
+    if (r < N) sbuf[h16 + r] = rk;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        __syncwarp();
+        const double2* b2 = reinterpret_cast<const double2*>(sbuf + (k & 1) * 32 + h16);
+        const double c = colj - ((r == k) ? 1.0 : 0.0);
+        double colj_n = 0.0, piv_n = 0.0, rk_n = 0.0;
+        if (k + 1 < N) {
+            const double2 q = b2[(k + 1) >> 1];
+            g[k + 1] = fma(-c, ((k + 1) & 1) ? q.y : q.x, g[k + 1]);
+            colj_n = g[k + 1];
+            piv_n = fast_rcp(fmax(__shfl_sync(FULL, colj_n, k + 1, 16), floor_piv));
+            rk_n = colj_n * piv_n;
+            if (r < N) sbuf[((k + 1) & 1) * 32 + h16 + r] = rk_n;
+        }
+#pragma unroll
+        for (int m2 = 0; m2 < 8; ++m2) {
+            const double2 q = b2[m2];
+            if (2 * m2 != k && 2 * m2 != k + 1 && 2 * m2 < N) g[2 * m2] = fma(-c, q.x, g[2 * m2]);
+            if (2 * m2 + 1 != k && 2 * m2 + 1 != k + 1 && 2 * m2 + 1 < N) g[2 * m2 + 1] = fma(-c, q.y, g[2 * m2 + 1]);
+        }
+        g[k] = (r == k) ? -piv : rk;
+        colj = colj_n; piv = piv_n; rk = rk_n;
+    }
+#else
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const double colj = g[k];
@@ -246,6 +315,7 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
         }
         g[k] = (r == k) ? -piv : rk;
     }
+#endif
     __syncwarp();
     // g holds -(G + delta I)^-1.  Pivot-normalised power iteration (see smallest_eigvec_spd), per half.
     double x = (r < N) ? 1.0 : 0.0;

@@ -11,7 +11,7 @@ from tft_vs_fund_b200 import build as B   # noqa: E402
 
 VARIANTS = {
     "base": [],
-    "swminb12": ["-DTVF_SW_MINB=12"],
+    "nopipe": ["-DTVF_GJ_PIPE=0"],
 }
 
 
