@@ -64,7 +64,8 @@ int tvf_set_chunk(tvf_handle_t h, int64_t problems);
 int tvf_set_stream(tvf_handle_t h, void* cuda_stream);
 int tvf_use_own_stream(tvf_handle_t h);
 int tvf_synchronize(tvf_handle_t h);
-/* pinned host memory, so the host-pointer entry points overlap copies with compute */
+/* pinned host memory, so the host-pointer entry points overlap copies with compute; placed on the NUMA node of the
+ * calling thread's current CUDA device (the thread's CPU affinity is narrowed during the call and restored) */
 void* tvf_host_alloc(size_t bytes);
 void tvf_host_free(void* p);
 
