@@ -67,6 +67,7 @@ sweep_seeds_kernel(long long first_trial, long long B, int n, const double* __re
 #endif
 constexpr int SW_WARPS = 1;                     // warps (= seeds) per CTA
 constexpr int SW_CAP = 32;                      // points per chunk of a refill pass (one per lane)
+constexpr int SW_CAP2 = 8;                      // memoised second refill pass: up to this many points
 constexpr unsigned SW_FULL = 0xffffffffu;
 
 struct WarpMT {
@@ -233,7 +234,7 @@ __device__ __forceinline__ int sw_emit(bool have, const double* __restrict__ cl,
 }
 
 __host__ __device__ inline size_t sw_warp_bytes(int N) {
-    return 2 * 624 * 4 + (size_t)48 * N + (size_t)2 * 48 * SW_CAP + 2 * (size_t)((N + 15) & ~15);
+    return 2 * 624 * 4 + (size_t)48 * N + (size_t)2 * 48 * (SW_CAP + SW_CAP2) + 2 * (size_t)((N + 15) & ~15);
 }
 
 // SLOTS = ceil(N / 32): the noise-free projections of a lane's points (32 q + lane) stay in registers.
@@ -251,8 +252,10 @@ sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double*
     double* z = reinterpret_cast<double*>(base);                             // first pass: the Gaussian draws
     double* cc = z + 6 * N;                                                  // refill chunk: projections  (shuffle: tempered words)
     double* cz = cc + 6 * SW_CAP;                                            // refill chunk: Gaussian draws (shuffle: swap list)
+    double* cc2 = cz + 6 * SW_CAP;                                           // memoised second refill pass
+    double* cz2 = cc2 + 6 * SW_CAP2;
     WarpMT mt;
-    mt.raw = reinterpret_cast<uint32_t*>(cz + 6 * SW_CAP);
+    mt.raw = reinterpret_cast<uint32_t*>(cz2 + 6 * SW_CAP2);
     mt.lane = lane;
     unsigned char* arr = reinterpret_cast<unsigned char*>(mt.raw + 2 * 624);
     signed char* outpos = reinterpret_cast<signed char*>(arr + Npad);
@@ -323,8 +326,10 @@ sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double*
     const int snap_pos = sw_normals(mt, 6 * N, N, 0, N, z);
     // ---- per noise level: scale the draws, inside-image mask + compaction, refill passes (:95-110).
     // The first refill pass of a level starts at snap_pos for every level, and its points and draws do not depend on
-    // the noise level -- only their number M does.  Levels with the same M (the usual case) reuse them.
-    int memo_M = -1, memo_end = 0;
+    // the noise level -- only their number M does; the second pass likewise depends only on where it starts and on its
+    // size.  Levels that agree in those (the usual case) reuse them: memo slot 0 = first pass (<= SW_CAP points, in
+    // cc/cz), slot 1 = second pass (<= SW_CAP2 points, in cc2/cz2).  Anything else is generated into cc/cz in chunks.
+    int m0_M = -1, m0_end = 0, m1_M = -1, m1_pos = 0, m1_end = 0;
     for (int lv = lv_lo; lv < lv_hi; ++lv) {
         const double noise = noise_levels[lv];
         double* o = out0 + (size_t)(lv - lv_lo) * 6 * n;
@@ -337,25 +342,29 @@ sweep_seeds_warp_kernel(long long first_trial, long long B, int n, const double*
                 filled += sw_emit(i0 + lane < N, clean[q], z + 6 * i, noise, hi_x, hi_y, outpos, filled, lt, o);
             }
         }
-        int M = N - filled, pos = snap_pos;
-        bool first = true;
+        int M = N - filled, pos = snap_pos, npass = 0;
         while (M > 0) {
-            int end_pos = pos;
-            for (int c0 = 0; c0 < M; c0 += SW_CAP) {
+            const bool s0 = npass == 0 && M <= SW_CAP, s1 = npass == 1 && M <= SW_CAP2;
+            const bool reuse = (s0 && m0_M == M) || (s1 && m1_M == M && m1_pos == pos);
+            double* bc = s1 ? cc2 : cc;
+            double* bz = s1 ? cz2 : cz;
+            const int lb = s1 ? (lane & (SW_CAP2 - 1)) : lane;
+            int end_pos = s0 ? m0_end : m1_end;                 // valid when reuse
+            if (!s0 && !s1) m0_M = -1;                          // the big buffers are about to be overwritten
+            for (int c0 = 0; c0 < M; c0 += SW_CAP) {            // one chunk whenever a memo slot is involved
                 const int c1 = (c0 + SW_CAP < M) ? c0 + SW_CAP : M;
-                const bool memoable = first && M <= SW_CAP;
-                if (memoable && memo_M == M) end_pos = memo_end;
-                else {
+                if (!reuse) {
                     __syncwarp();
                     mt.prepare(pos + 6 * c0, pos + 6 * c1 - 1);
-                    if (c0 + lane < c1) sw_point(mt, pos + 6 * (c0 + lane), P, cc + 6 * lane);
+                    if (c0 + lane < c1) sw_point(mt, pos + 6 * (c0 + lane), P, bc + 6 * lb);
                     __syncwarp();
-                    end_pos = sw_normals(mt, pos + 6 * M, M, c0, c1, cz);
-                    memo_M = memoable ? M : -1; memo_end = end_pos;
+                    end_pos = sw_normals(mt, pos + 6 * M, M, c0, c1, bz);
                 }
-                filled += sw_emit(c0 + lane < c1, cc + 6 * lane, cz + 6 * lane, noise, hi_x, hi_y, outpos, filled, lt, o);
+                filled += sw_emit(c0 + lane < c1, bc + 6 * lb, bz + 6 * lb, noise, hi_x, hi_y, outpos, filled, lt, o);
             }
-            pos = end_pos; M = N - filled; first = false;
+            if (s0) { m0_M = M; m0_end = end_pos; }
+            if (s1) { m1_M = M; m1_pos = pos; m1_end = end_pos; }
+            pos = end_pos; M = N - filled; ++npass;
         }
     }
 }
