@@ -13,8 +13,10 @@
  *   - return value: < 0 argument/runtime error (tvf_last_error() has the text),
  *     0 success, > 0 number of problems whose status word is non-zero;
  *   - `status` (int32 per problem, may be NULL) is a bit set, see TVF_ST_*;
- *   - one handle per host thread and per GPU; calls on a handle are serialised
- *     by the caller (MATLAB calls MEX on its interpreter thread only);
+ *   - one handle per host thread; a handle drives one GPU (tvf_create) or several
+ *     (tvf_create_multi: the host-pointer pose entry points shard the batch over the
+ *     devices); calls on a handle are serialised by the caller (MATLAB calls MEX on
+ *     its interpreter thread only);
  *   - there is no CPU fallback: without a CUDA device tvf_create() fails.
  *
  * Results agree with the reference up to the sign/scale freedom the reference
@@ -54,6 +56,12 @@ typedef struct tvf_context* tvf_handle_t;
 int tvf_version(void);
 int tvf_device_count(void);
 int tvf_create(tvf_handle_t* out, int device);
+/* Group handle over n_dev devices (ids may repeat: two members on one GPU are legal).  Member 0 serves every entry
+ * point; the host-pointer pose entry points (tvf_pose, tvf_linear_tft_pose, tvf_linear_f_pose, tvf_optim_f_pose)
+ * split B into n_dev contiguous ranges, one host thread + one device per range, no exchange between them -- the batched
+ * form of the trial loop experiments.m:91-143 / experiments_real.m:75-163.  Results are bit-identical to a one-device call. */
+int tvf_create_multi(tvf_handle_t* out, const int* devices, int n_dev);
+int tvf_num_devices(tvf_handle_t h);
 void tvf_destroy(tvf_handle_t h);
 const char* tvf_last_error(tvf_handle_t h); /* h may be NULL: error of the last failed tvf_create */
 int tvf_device(tvf_handle_t h);
@@ -68,6 +76,10 @@ int tvf_synchronize(tvf_handle_t h);
  * calling thread's current CUDA device (the thread's CPU affinity is narrowed during the call and restored) */
 void* tvf_host_alloc(size_t bytes);
 void tvf_host_free(void* p);
+/* on != 0: caller buffers >= 1 MiB that are pageable (an mxArray's data) are page-locked with cudaHostRegister for the
+ * duration of each host-pointer pose call and released before it returns; off (default): pageable buffers take the
+ * CUDA runtime's staged copies */
+int tvf_set_host_register(tvf_handle_t h, int on);
 
 /* ---- method entry points (host pointers; copies are inside the call) ------------------- */
 
@@ -100,6 +112,30 @@ int tvf_optim_f_pose(tvf_handle_t h, const double* corresp, const double* calm, 
                      double* F21, double* F31, int32_t* iter, int32_t* status);
 int tvf_optim_f_max_n(void);
 
+/* Generic form of the three method entry points above, with every optional output in one place.
+ * method: 1 = LinearTFTPoseEstimation, 7 = LinearFPoseEstimation, 8 = OptimFPoseEstimation (numbering of
+ * experiments.m:51-59).  votes (10 x B int32): what recover_R_t computed at R_t_from_TFT.m:91-104 /
+ * LinearFPoseEstimation.m:94-107 -- per problem the four cheirality votes of view pair (1,2) in the reference's
+ * candidate order (R,t),(R,-t),(Rp,-t),(Rp,t), the four of pair (1,3), then one bit mask per pair of the candidates
+ * whose vote is NaN (bit k = candidate k; MATLAB's NaN >= x is false).  Any member may be NULL. */
+typedef struct tvf_pose_out {
+    double* Rt2;      /* 3 x 4 x B */
+    double* Rt3;      /* 3 x 4 x B */
+    double* reconst;  /* 3 x n x B */
+    double* T;        /* 3 x 3 x 3 x B */
+    double* repr_err; /* B */
+    double* F21;      /* 3 x 3 x B (methods 7, 8) */
+    double* F31;      /* 3 x 3 x B (methods 7, 8) */
+    int32_t* iter;    /* B (method 8) */
+    int32_t* votes;   /* 10 x B */
+    int32_t* status;  /* B */
+} tvf_pose_out;
+int tvf_pose(tvf_handle_t h, int method, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
+             const tvf_pose_out* out);
+/* same with device pointers (corresp, calm and every member of out), asynchronous like the other *_dev forms */
+int tvf_pose_dev(tvf_handle_t h, int method, const double* corresp, const double* calm, int calm_batched, int n,
+                 int64_t B, const tvf_pose_out* out);
+
 /* [F,iter] = optimF(p1,p2)   F_methods/optimF.m:1,34-78.  p1,p2 rows x n x B (rows = 2 or 3); F 3x3xB;
  * iter B (may be NULL).  n < 8 -> TVF_ERR_TOO_FEW_POINTS. */
 int tvf_optim_f(tvf_handle_t h, const double* p1, const double* p2, int rows, int n, int64_t B, double* F,
@@ -126,9 +162,10 @@ int tvf_normalize2d(tvf_handle_t h, const double* points, int n, int64_t B, doub
 int tvf_transform_tft(tvf_handle_t h, const double* T_old, const double* M1, const double* M2, const double* M3,
                       int mats_batched, int inverse, int64_t B, double* T_new);
 
-/* [R_t_2,R_t_3] = R_t_from_TFT(T,CalM,Corresp)   TFT_methods/R_t_from_TFT.m:1,40-106. */
+/* [R_t_2,R_t_3] = R_t_from_TFT(T,CalM,Corresp)   TFT_methods/R_t_from_TFT.m:1,40-106.
+ * votes (10 x B, may be NULL): the cheirality votes of the local recover_R_t (:91-104), layout as in tvf_pose_out. */
 int tvf_rt_from_tft(tvf_handle_t h, const double* T, const double* calm, int calm_batched, const double* corresp,
-                    int n, int64_t B, double* Rt2, double* Rt3, int32_t* status);
+                    int n, int64_t B, double* Rt2, double* Rt3, int32_t* votes, int32_t* status);
 
 /* T = TFT_from_P(P1,P2,P3)   TFT_methods/TFT_from_P.m:1,25-33.  P* 3x4xB. */
 int tvf_tft_from_p(tvf_handle_t h, const double* P1, const double* P2, const double* P3, int64_t B, double* T);

@@ -26,6 +26,8 @@ mxArray* mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c);
 mxArray* mxCreateNumericArray(mwSize ndim, const mwSize* dims, mxClassID cls, mxComplexity c);
 mxArray* mxCreateDoubleScalar(double v);
 void mxDestroyArray(mxArray* a);
+void* mxCalloc(size_t n, size_t size);       /* MATLAB frees these automatically when the MEX function leaves, also through an error */
+void mxFree(void* p);
 double* mxGetPr(const mxArray* a);
 mwSize mxGetM(const mxArray* a);
 mwSize mxGetN(const mxArray* a);            /* product of dims 2..end, as in MATLAB */

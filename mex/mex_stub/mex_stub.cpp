@@ -22,6 +22,8 @@ mxArray* mxCreateDoubleMatrix(mwSize m, mwSize n, mxComplexity c) {
     return mxCreateNumericArray(2, d, mxDOUBLE_CLASS, c);
 }
 mxArray* mxCreateDoubleScalar(double v) { mxArray* a = mxCreateDoubleMatrix(1, 1, mxREAL); a->data[0] = v; return a; }
+void* mxCalloc(size_t n, size_t size) { return std::calloc(n ? n : 1, size ? size : 1); }
+void mxFree(void* p) { std::free(p); }
 void mxDestroyArray(mxArray* a) { if (a) { std::free(a->data); std::free(a); } }
 double* mxGetPr(const mxArray* a) { return a->data; }
 mwSize mxGetM(const mxArray* a) { return a->dims[0]; }

@@ -12,12 +12,13 @@ void mexFunction(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prhs[]) {
         mexErrMsgIdAndTxt("TFT_vs_Fund:badInput", "p1,p2 must both be 2xN or 3xN");
     tvf_handle_t h = handle();
     mxArray* F = make(3, 3, a.B);
-    std::vector<int32_t> it(a.B, 0);
-    const int rc = tvf_optim_f(h, mxGetPr(prhs[0]), mxGetPr(prhs[1]), (int)a.rows, (int)a.n, (int64_t)a.B, mxGetPr(F), it.data(), nullptr);
+    int32_t* it = temp_i32(a.B);              // mxCalloc: released by MATLAB on the error paths below
+    const int rc = tvf_optim_f(h, mxGetPr(prhs[0]), mxGetPr(prhs[1]), (int)a.rows, (int)a.n, (int64_t)a.B, mxGetPr(F), it, nullptr);
     if (rc < 0) { mxDestroyArray(F); check(rc, h); }
     plhs[0] = F;
     if (nlhs > 1) {
         plhs[1] = (a.B == 1) ? mxCreateDoubleScalar((double)it[0]) : make(a.B, 1, 1);
         if (a.B != 1) for (mwSize k = 0; k < a.B; ++k) mxGetPr(plhs[1])[k] = (double)it[k];
     }
+    mxFree(it);
 }

@@ -7,11 +7,18 @@
 // on its interpreter thread only, so every mx* call happens on the calling thread; CUDA work runs on the
 // handle's private streams and is synchronised before the gateway returns.
 //
+// Devices: the environment variable TVF_DEVICES ("0", "0,1,2,3", "all"; default "0") selects the GPUs of the
+// persistent handle; with more than one the batched pose calls are sharded over them inside libtvf
+// (tvf_create_multi: one host thread per device, experiments.m:91-143 is the loop that fans out).
+// TVF_HOST_REGISTER=1 page-locks large mxArray buffers for the duration of a call (tvf_set_host_register).
+// Temporaries come from mxCalloc: MATLAB releases them itself when mexErrMsgIdAndTxt leaves the function.
+//
 // Batched superset: a trailing dimension B on the inputs (Corresp 6xNxB, p 2xNxB, CalM 9x3 or 9x3xB)
 // returns 3x4xB, 3xNxB, 3x3x3xB, ... ; B = 1 is exactly the reference signature.
 #pragma once
 #include <cstdint>
-#include <vector>
+#include <cstdlib>
+#include <cstring>
 
 #include "mex.h"
 #include "tvf.h"
@@ -27,13 +34,33 @@ inline void cleanup() {
 inline tvf_handle_t handle() {
     tvf_handle_t& h = handle_ref();
     if (!h) {
-        if (tvf_create(&h, 0) != TVF_OK)
+        int devs[64]; int nd = 0;
+        const char* env = std::getenv("TVF_DEVICES");
+        if (env && std::strcmp(env, "all") == 0) {
+            const int cnt = tvf_device_count();
+            for (int i = 0; i < cnt && i < 64; ++i) devs[nd++] = i;
+        } else if (env && *env) {
+            for (const char* c = env; *c && nd < 64;) {
+                char* end = nullptr;
+                const long v = std::strtol(c, &end, 10);
+                if (end == c) break;
+                devs[nd++] = (int)v;
+                c = end;
+                while (*c == ',' || *c == ' ') ++c;
+            }
+        }
+        if (nd == 0) devs[nd++] = 0;
+        if (tvf_create_multi(&h, devs, nd) != TVF_OK)
             mexErrMsgIdAndTxt("TFT_vs_Fund:noDevice", "libtvf: %s", tvf_last_error(nullptr));
+        const char* reg = std::getenv("TVF_HOST_REGISTER");
+        if (reg && *reg && *reg != '0') tvf_set_host_register(h, 1);
         mexLock();
         mexAtExit(cleanup);
     }
     return h;
 }
+
+inline int32_t* temp_i32(mwSize count) { return static_cast<int32_t*>(mxCalloc(count ? count : 1, sizeof(int32_t))); }
 
 inline void require_real_double(const mxArray* a, const char* name) {
     if (!mxIsDouble(a) || mxIsComplex(a) || mxIsSparse(a))
@@ -80,9 +107,10 @@ inline void pose_gateway(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prh
     tvf_handle_t h = handle();
     mxArray* Rt2 = make(3, 4, c.B); mxArray* Rt3 = make(3, 4, c.B);
     mxArray* Rec = make(3, c.n, c.B); mxArray* T = make_tensor(c.B);
-    std::vector<int32_t> status(c.B), iters(c.B, 0);
+    int32_t* status = temp_i32(c.B);          // mxCalloc: released by MATLAB even when an error leaves this function
+    int32_t* iters = temp_i32(c.B);
     const int rc = call(h, mxGetPr(prhs[0]), mxGetPr(prhs[1]), k.B != 1, (int)c.n, (int64_t)c.B, mxGetPr(Rt2),
-                        mxGetPr(Rt3), mxGetPr(Rec), mxGetPr(T), status.data(), iters.data());
+                        mxGetPr(Rt3), mxGetPr(Rec), mxGetPr(T), status, iters);
     mxArray* outs[5] = {Rt2, Rt3, Rec, T, nullptr};
     if (rc < 0 || (c.B == 1 && (status[0] & (TVF_ST_NO_POSE_2 | TVF_ST_NO_POSE_3)))) {
         for (int i = 0; i < 4; ++i) mxDestroyArray(outs[i]);
@@ -97,6 +125,7 @@ inline void pose_gateway(int nlhs, mxArray* plhs[], int nrhs, const mxArray* prh
     for (int i = 0; i < 5; ++i) {
         if (i < nout) plhs[i] = outs[i]; else mxDestroyArray(outs[i]);
     }
+    mxFree(status); mxFree(iters);
 }
 
 }  // namespace tvf_mex

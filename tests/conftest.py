@@ -88,3 +88,31 @@ def assert_pose_close(ref, got, n_label=""):
     # 1e-8 px; the relative term only matters for failed (hundreds-of-px) solutions whose own
     # sensitivity to a 1-ulp input change already exceeds 1e-8 px ("tolerances")
     assert abs(rep - grep) <= TOL_REPR + 1e-10 * abs(rep), n_label
+
+
+# ---- cheirality votes ---------------------------------------------------------------------------
+# The four candidates of recover_R_t are (R,t),(R,-t),(Rp,-t),(Rp,t) with R = U*W*V', Rp = U*W'*V', t = U(:,3)
+# (R_t_from_TFT.m:84-97).  svd(E) is defined only up to the signs of its singular-vector pairs (and E has two nearly
+# equal singular values); that freedom maps t -> -t and/or swaps R with Rp, i.e. it RELABELS the candidates by one of
+# these four permutations (ours[k] = theirs[p[k]]).  The set of (candidate, vote) pairs is invariant; the labels are
+# not even stable between two runs of the same LAPACK (thread count changes the last bits of T and with them the
+# labels -- observed while generating the goldens), let alone between NumPy and MATLAB.
+VOTE_RELABELINGS = ([0, 1, 2, 3], [1, 0, 3, 2], [3, 2, 1, 0], [2, 3, 0, 1])
+
+
+def votes8_equal(a8, b8):
+    """Two 4 + 4 vote vectors (floats, NaN = MATLAB's NaN sum) agree pair by pair under an admissible relabeling."""
+    a8 = np.asarray(a8, dtype=np.float64); b8 = np.asarray(b8, dtype=np.float64)
+    return all(any(np.array_equal(a8[4 * p:4 * p + 4], b8[4 * p:4 * p + 4][perm], equal_nan=True)
+                   for perm in VOTE_RELABELINGS) for p in range(2))
+
+
+def library_votes_as_float(v10):
+    """10 int32 of the library (4 + 4 votes, one NaN bit mask per pair) -> 8 floats with NaN where the mask says so."""
+    v10 = np.asarray(v10)
+    out = v10[:8].astype(np.float64)
+    for p in range(2):
+        for k in range(4):
+            if (int(v10[8 + p]) >> k) & 1:
+                out[4 * p + k] = np.nan
+    return out

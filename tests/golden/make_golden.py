@@ -152,7 +152,108 @@ def large_n(n=10000, seeds=(1, 2)):
     np.savez_compressed(os.path.join(HERE, "large_n10000.npz"), **{k: np.stack(v) for k, v in d.items()})
 
 
+def oracle_votes(C, CalM):
+    """The 4 + 4 cheirality votes of recover_R_t for both methods (R_t_from_TFT.m:91-104 with the tensor of
+    LinearTFTPoseEstimation; LinearFPoseEstimation.m:94-107 with its two F), as the oracle computes them:
+    candidate order (R,t),(R,-t),(Rp,-t),(Rp,t) per pair.  NaN sums are stored as NaN."""
+    K1, K2, K3 = CalM[0:3], CalM[3:6], CalM[6:9]
+    T = o.LinearTFTPoseEstimation(C, CalM)[3]
+    _, _, v2, v3 = o.R_t_from_TFT(T, CalM, C, return_votes=True)
+    F21, F31 = o.LinearFPoseEstimation(C, CalM, return_F=True)[5:7]
+    f2 = o.recover_R_t_F(K1, K2, F21, C[0:2], C[2:4], return_votes=True)[2]
+    f3 = o.recover_R_t_F(K1, K3, F31, C[0:2], C[4:6], return_votes=True)[2]
+    return np.array(list(v2) + list(v3), dtype=np.float64), np.array(list(f2) + list(f3), dtype=np.float64)
+
+
+def add_votes(name):
+    """Add tft_votes / f_votes (cases x 8) to an existing golden file (votes were never compared)."""
+    path = os.path.join(HERE, name)
+    d = dict(np.load(path))
+    tv, fv = [], []
+    for b in range(d["Corresp"].shape[0]):
+        a, c = oracle_votes(d["Corresp"][b], d["CalM"][b])
+        tv.append(a); fv.append(c)
+    d["tft_votes"] = np.stack(tv); d["f_votes"] = np.stack(fv)
+    np.savez_compressed(path, **d)
+
+
+DATASETS = (("fountain-P11", 70), ("Herz-Jesu-P8", 50))        # experiments_real.m:31-36
+
+
+def epfl_inputs():
+    """The raw inputs of experiments_real.m for every tested triplet (70 + 50): the match lists of
+    Corresp_triplets.mat, the calibration/orientation of every image and indexes_sorted -- data, not code; the GPU
+    box has no /root/reference, and tests/test_gpu_parity.py runs epfl.run_real on exactly these."""
+    d = {}
+    for ds, ntrip in DATASETS:
+        path = os.path.join(REFERENCE, "Data", ds)
+        idx, cor, names = o.load_corresp_triplets(path)
+        key = ds.replace("-", "_")
+        d[key + "_indexes_sorted"] = idx[:ntrip]
+        cams = [o.readCalibrationOrientation_EPFL(path, nm) for nm in names]
+        d[key + "_K"] = np.stack([c[0] for c in cams]); d[key + "_R"] = np.stack([c[1] for c in cams])
+        d[key + "_t"] = np.stack([c[2] for c in cams])
+        rows, offs = [], [0]
+        for it in range(1, ntrip + 1):
+            im = [int(v) for v in idx[it - 1, 0:3]]
+            rows.append(np.asarray(cor[im[0] - 1, im[1] - 1, im[2] - 1], dtype=np.float64))
+            offs.append(offs[-1] + rows[-1].shape[0])
+        d[key + "_matches"] = np.concatenate(rows); d[key + "_offsets"] = np.array(offs, dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, "epfl_inputs.npz"), **d)
+
+
+def epfl_all():
+    """experiments_real.m:75-138 for methods 1 and 7 on ALL tested triplets (70 of fountain-P11, 50 of Herz-Jesu-P8):
+    per triplet the sample (seeded with the loop index, :103), the poses, T, the cheirality votes, and the row
+    [ReprError over all inliers (:130-131), rot_err, t_err (:133-136)].  real_* from the oracle port, ref_real_* from
+    the reference's unmodified .m files run by oracle/mini_matlab.py."""
+    from oracle.mini_matlab import reference_interpreter, Cell
+    interp = reference_interpreter(REFERENCE, rng_factory=o.SceneRNG)
+    d = {}
+    def put(k, v):
+        d.setdefault(k, []).append(np.asarray(v))
+    for dsi, (ds, ntrip) in enumerate(DATASETS):
+        path = os.path.join(REFERENCE, "Data", ds)
+        idx, cor, names = o.load_corresp_triplets(path)
+        for it in range(1, ntrip + 1):
+            t = o.epfl_triplet(path, idx, cor, names, it)
+            inl, CalM, R_t0 = t["Corresp_inliers"], t["CalM"], t["R_t0"]
+            N = inl.shape[1]
+            sample = o.SceneRNG(it).randsample(N, min(100, N))
+            C = inl[:, sample]
+            Cpad = np.full((6, 100), np.nan); Cpad[:, :C.shape[1]] = C
+            K = [CalM[0:3], CalM[3:6], CalM[6:9]]
+            for k, v in (("dataset", dsi), ("it", it), ("triplet", t["triplet"]), ("n_inliers", N), ("n_sample", C.shape[1]),
+                         ("gt_repr", t["REr"]), ("Corresp", Cpad), ("CalM", CalM), ("Rt0_2", R_t0[0]), ("Rt0_3", R_t0[1]),
+                         ("sample", np.pad(sample, (0, 100 - sample.size), constant_values=-1))):
+                put(k, v)
+            tv, fv = oracle_votes(C, CalM)
+            put("tft_votes", tv); put("f_votes", fv)
+            for m, fn, mname in (("tft", o.LinearTFTPoseEstimation, "LinearTFTPoseEstimation"),
+                                 ("f", o.LinearFPoseEstimation, "LinearFPoseEstimation")):
+                R2, R3, _, T, _ = fn(C, CalM)
+                rep = o.ReprError([K[0] @ np.eye(3, 4), K[1] @ R2, K[2] @ R3], inl)
+                r2, t2 = o.AngError(R_t0[0], R2); r3, t3 = o.AngError(R_t0[1], R3)
+                put(m + "_Rt2", R2); put(m + "_Rt3", R3); put(m + "_T", T)
+                put("real_" + m, [rep, (r2 + r3) / 2, (t2 + t3) / 2])
+                q2, q3, _, qT, _ = interp.call(mname, [C.copy(), CalM.copy()], 5)
+                rrep = interp.call("ReprError", [Cell([K[0] @ np.eye(3, 4), K[1] @ q2, K[2] @ q3]), inl.copy()], 1)[0]
+                a2 = interp.call("AngError", [R_t0[0].copy(), q2], 2); a3 = interp.call("AngError", [R_t0[1].copy(), q3], 2)
+                put("ref_" + m + "_T", qT)
+                put("ref_real_" + m, [float(np.asarray(rrep).item()),
+                                      (float(np.asarray(a2[0]).item()) + float(np.asarray(a3[0]).item())) / 2,
+                                      (float(np.asarray(a2[1]).item()) + float(np.asarray(a3[1]).item())) / 2])
+            print(ds, it, N, flush=True)
+    np.savez_compressed(os.path.join(HERE, "epfl_all_triplets.npz"), **{k: np.stack(v) for k, v in d.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "votes":
+        for nm in ("sweep_n20.npz", "example_n100.npz", "epfl_triplets.npz"):
+            add_votes(nm)
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "epfl_all":
+        epfl_inputs(); epfl_all(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "large":
         large_n(); sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "optimf":

@@ -1,0 +1,302 @@
+"""Parity of the CUDA path, part 2 (the corners VERDICT round 1 found untested): the integer cheirality votes
+themselves, a random 10 000-trial sample of the 1 M-trial sweep against the live oracle, every EPFL triplet of
+experiments_real.m (70 + 50) including the real-data driver `epfl.run_real`, the 'focal' / 'points' / 'angle' scenes
+of experiments.m:38-47 (long focal lengths, minimal point counts, collinear centres), and shards == single call on the
+hardware.  Tolerances are BASELINE.json's (conftest.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as o
+import parity_workers as pw
+from conftest import ROOT, TOL_MODEL, assert_pose_close, library_votes_as_float, rel_frob_up_to_sign, votes8_equal
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+def votes_equal(got10, ref8):
+    """got10: 10 int32 from the library (4 + 4 votes, 2 NaN masks); ref8: the oracle's 8 votes (NaN where the sum is NaN).
+    True when both pairs agree exactly under an admissible relabeling of the candidates (conftest.VOTE_RELABELINGS)."""
+    return votes8_equal(library_votes_as_float(got10), ref8)
+
+
+def vote_tie(ref8):
+    ref8 = np.asarray(ref8, dtype=np.float64)
+    for p in range(2):
+        v = ref8[4 * p:4 * p + 4]
+        if np.any(np.isnan(v)) or np.sum(v == np.max(v)) > 1:
+            return True
+    return False
+
+
+def _golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+# ---------------------------------------------------------------------------------------------- (a) votes
+@pytest.mark.parametrize("name", ["sweep_n20.npz", "example_n100.npz", "epfl_triplets.npz"])
+@pytest.mark.parametrize("method", ["tft", "f"])
+def test_cheirality_votes_equal_the_oracles(tvf, name, method):
+    """R_t_from_TFT.m:91-104 / LinearFPoseEstimation.m:94-107: the vote of every candidate, integer for integer."""
+    g = _golden(name)
+    assert "tft_votes" in g.files, "regenerate with tests/golden/make_golden.py votes"
+    fn = tvf.LinearTFTPoseEstimation if method == "tft" else tvf.LinearFPoseEstimation
+    res = fn(g["Corresp"], g["CalM"])
+    ref = g["%s_votes" % method]
+    n = g["Corresp"].shape[2]
+    for b in range(ref.shape[0]):
+        assert votes_equal(res.votes[b], ref[b]), (name, method, b, res.votes[b], ref[b])
+        # every candidate sees all n points in front of both cameras, behind both, or split: |vote| <= 2n
+        assert np.max(np.abs(res.votes[b][:8])) <= 2 * n
+    # the stand-alone R_t_from_TFT on the oracle's tensor reports the same votes as the oracle's R_t_from_TFT
+    if method == "tft":
+        for b in range(0, ref.shape[0], 9):
+            T = g["tft_T"][b]
+            _, _, v2, v3 = o.R_t_from_TFT(T, g["CalM"][b], g["Corresp"][b], return_votes=True)
+            _, _, votes = tvf.R_t_from_TFT(T, g["CalM"][b], g["Corresp"][b], return_votes=True)
+            assert votes_equal(votes, list(v2) + list(v3)), (name, b)
+
+
+def test_votes_of_the_unfused_tail_and_nan_masks(tvf):
+    """n > 256 takes votes_kernel (not the fused tail); a point at infinity (X1(4) == 0) makes the vote NaN in MATLAB
+    and must be reported through the mask, not counted."""
+    CalM, R_t0, C, _ = o.generateSyntheticScene(300, 1.0, 3, 50, 0)
+    res = tvf.LinearTFTPoseEstimation(C[None], CalM)
+    T = o.LinearTFTPoseEstimation(C, CalM)[3]
+    _, _, v2, v3 = o.R_t_from_TFT(T, CalM, C, return_votes=True)
+    assert votes_equal(res.votes[0], list(v2) + list(v3))
+    g = _golden("sweep_n20.npz")
+    a = tvf.LinearTFTPoseEstimation(g["Corresp"][:16], g["CalM"][0])
+    assert np.all(a.votes[:, 8:] == 0)                      # no NaN votes on regular data
+
+
+# ------------------------------------------------------------------- (b) 10 k random sample of the 1 M sweep
+def test_random_10k_sample_of_the_1M_sweep_against_live_oracle(tvf):
+    """BASELINE config 3: 'parity checked on the first 13 x 20 trials plus a random 10 k sample'.  The
+    sample's inputs come from the oracle's own scene generator (by global trial index); the device generator's 1 M
+    trials are compared with them bit for bit at those indices, then both linear methods are solved on the GPU and
+    compared with the live oracle, votes included."""
+    from tft_vs_fund_b200 import scene
+    B, S, n = 1_000_000, 10_000, 20
+    levels = np.arange(0.0, 3.0 + 1e-9, 0.25)
+    idx = np.sort(np.random.RandomState(20260101).choice(B, S, replace=False))
+    with pw.pool() as pool:
+        ref = pool.map(pw.oracle_trial, [(int(j), n, levels, 50, 0) for j in idx], chunksize=16)
+    C = np.stack([r["Corresp"] for r in ref])
+    CalM = ref[0]["CalM"]
+    # the device-resident generator at the same global indices (whole 1 M trials generated, sample read back)
+    import torch
+    d_c = torch.empty((B, n, 6), dtype=torch.float64, device="cuda")
+    scene.sweep_batch_device(B, n, device=0, out_ptr=d_c.data_ptr(), meta=False)
+    torch.cuda.synchronize()
+    dev_sample = d_c[torch.from_numpy(idx).cuda()].cpu().numpy().transpose(0, 2, 1)
+    del d_c
+    assert np.array_equal(dev_sample, C), "device generator differs from the oracle's generator inside the 1 M sweep"
+    worst = {"tft": 0.0, "f": 0.0}
+    ties = 0
+    for method, fn in (("tft", tvf.LinearTFTPoseEstimation), ("f", tvf.LinearFPoseEstimation)):
+        res = fn(C, CalM)
+        assert np.count_nonzero(res.status) == 0
+        for b in range(S):
+            r = ref[b][method]
+            assert not isinstance(r, str), r
+            worst[method] = max(worst[method], rel_frob_up_to_sign(r[3], res[3][b]))
+            assert votes_equal(res.votes[b], r[5]), (method, int(idx[b]))
+            if vote_tie(r[5]):
+                ties += 1
+                continue
+            assert_pose_close(r[:5], (res[0][b], res[1][b], res[2][b], res[3][b], res.repr_err[b]),
+                              "%s trial %d" % (method, int(idx[b])))
+            if method == "f":
+                assert rel_frob_up_to_sign(r[6], res.F21[b]) < TOL_MODEL and rel_frob_up_to_sign(r[7], res.F31[b]) < TOL_MODEL
+    print("10k sample: worst rel. Frobenius difference of T: tft %.2e, f %.2e; vote ties skipped: %d" % (worst["tft"], worst["f"], ties))
+
+
+# ---------------------------------------------------------------------------------- (c) all EPFL triplets
+@pytest.mark.parametrize("method", ["tft", "f"])
+def test_epfl_all_120_triplets_golden(tvf, method):
+    """Config 2 in full: rows 1-70 of fountain-P11 and 1-50 of Herz-Jesu-P8 (experiments_real.m:31-36), the sampled
+    inliers of every triplet: T against the oracle AND against the reference's own .m files (ref_*), poses, votes."""
+    g = _golden("epfl_all_triplets.npz")
+    assert g["Corresp"].shape[0] == 120
+    fn = tvf.LinearTFTPoseEstimation if method == "tft" else tvf.LinearFPoseEstimation
+    for ns in np.unique(g["n_sample"]):
+        rows = np.flatnonzero(g["n_sample"] == ns)
+        res = fn(g["Corresp"][rows][:, :, :ns], g["CalM"][rows])
+        assert np.all(res.status == 0)
+        for k, b in enumerate(rows):
+            assert rel_frob_up_to_sign(g["%s_T" % method][b], res[3][k]) < TOL_MODEL, (method, b)
+            assert rel_frob_up_to_sign(g["ref_%s_T" % method][b], res[3][k]) < TOL_MODEL, (method, b)
+            assert votes_equal(res.votes[k], g["%s_votes" % method][b]), (method, b)
+            if vote_tie(g["%s_votes" % method][b]):
+                continue
+            from conftest import rot_angle, vec_angle, TOL_ANGLE
+            for a, c in ((g["%s_Rt2" % method][b], res[0][k]), (g["%s_Rt3" % method][b], res[1][k])):
+                assert rot_angle(a[:, :3], c[:, :3]) < TOL_ANGLE and vec_angle(a[:, 3], c[:, 3]) < TOL_ANGLE, (method, b)
+
+
+def test_run_real_executes_experiments_real_protocol(tvf):
+    """epfl.run_real (experiments_real.m:75-138, methods 1 and 7) on the committed raw inputs of all 120 triplets:
+    inlier counts and sample indices exact, ground-truth RMS, and the per-triplet [ReprError over all inliers, rot_err,
+    t_err] rows against the oracle's and against the reference's own .m files."""
+    from tft_vs_fund_b200 import epfl
+    g = _golden("epfl_all_triplets.npz")
+    inp = _golden("epfl_inputs.npz")
+    row0 = 0
+    for dsi, (key, ntrip) in enumerate((("fountain_P11", 70), ("Herz_Jesu_P8", 50))):
+        data = epfl.dataset_from_arrays(inp[key + "_indexes_sorted"], inp[key + "_matches"], inp[key + "_offsets"],
+                                        inp[key + "_K"], inp[key + "_R"], inp[key + "_t"])
+        details = []
+        table = epfl.run_real(data, range(1, ntrip + 1), details=details)
+        rows = slice(row0, row0 + ntrip)
+        assert np.all(g["dataset"][rows] == dsi)
+        assert [d["n_inliers"] for d in details] == list(g["n_inliers"][rows])              # integer indexing: exact
+        for k, d in enumerate(details):
+            ns = int(g["n_sample"][row0 + k])
+            assert np.array_equal(d["sample"], g["sample"][row0 + k][:ns])
+            assert abs(d["REr"] - float(g["gt_repr"][row0 + k])) < 1e-8
+        for m, name in ((1, "tft"), (7, "f")):
+            for src in ("real_", "ref_real_"):
+                ref = g[src + name][rows]
+                ok = np.array([not vote_tie(v) for v in g[name + "_votes"][rows]])
+                assert np.max(np.abs(table[m][ok, 0] - ref[ok, 0])) < 1e-8, (key, name, src)            # px
+                assert np.max(np.abs(table[m][ok, 1:] - ref[ok, 1:])) < 1e-4, (key, name, src)          # degrees
+        row0 += ntrip
+    # means_all of experiments_real.m:168-174 for the linear methods is then a plain column mean
+    assert np.all(np.isfinite(table[1].mean(axis=0)))
+
+
+# --------------------------------------------------- (d) the other three experiments of experiments.m:38-47
+EXPERIMENTS = {
+    "focal": [dict(focalL=f, angle=0, n=12) for f in range(20, 301, 20)],
+    "points": [dict(focalL=50, angle=0, n=n) for n in (7, 8, 9, 10, 15, 20, 25)],
+    "angle": [dict(focalL=50, angle=a, n=12) for a in (166, 168, 170, 172, 174, 175, 176, 177, 178, 179, 179.5, 180)],
+}
+
+
+@pytest.mark.parametrize("option", ["focal", "points", "angle"])
+def test_other_experiment_scenes_against_live_oracle(tvf, option):
+    """experiments.m with option = 'focal' (20:20:300 mm), 'points' (7:9, 10:5:25) and 'angle' (166 ... 180 degrees,
+    collinear centres), N = 12, noise = 1 px, n_sim = 20 seeds (experiments.m:30-34,38-47): the ill-conditioned
+    geometries every round-1 test avoided.  Trial by trial against the live oracle for methods 1 and 7; reports how many
+    trials end with TVF_ST_EIG_NOCONV."""
+    from tft_vs_fund_b200 import scene, _lib
+    n_sim = 20
+    jobs, meta = [], []
+    for lv, cfg in enumerate(EXPERIMENTS[option]):
+        for it in range(1, n_sim + 1):
+            jobs.append((it - 1, cfg["n"], [1.0], cfg["focalL"], cfg["angle"]))        # L = 1: seed = j + 1
+            meta.append((lv, it))
+    with pw.pool() as pool:
+        ref = pool.map(pw.oracle_trial, jobs, chunksize=4)
+    noconv = {"tft": 0, "f": 0}
+    compared = {"tft": 0, "f": 0}
+    worst = {"tft": 0.0, "f": 0.0}
+    for lv, cfg in enumerate(EXPERIMENTS[option]):
+        sel = [k for k, m in enumerate(meta) if m[0] == lv]
+        C = np.stack([ref[k]["Corresp"] for k in sel]); CalM = ref[sel[0]]["CalM"]
+        # the product-side generator (which feeds tvf_sweep_run's host twin) produces the same trials bit for bit
+        mine = scene.sweep_batch(n_sim, cfg["n"], noise_levels=[1.0], focalL=cfg["focalL"], angle=cfg["angle"])
+        assert np.array_equal(mine["Corresp"], C) and np.array_equal(mine["CalM"], CalM), (option, cfg)
+        for method, fn in (("tft", tvf.LinearTFTPoseEstimation), ("f", tvf.LinearFPoseEstimation)):
+            if method == "f" and cfg["n"] < 8:
+                with pytest.raises(ValueError, match="At least 8 correspondences"):     # experiments.m:99-104 skips these
+                    fn(C, CalM)
+                continue
+            res = fn(C, CalM)
+            noconv[method] += int(np.count_nonzero(res.status & _lib.ST_EIG_NOCONV))
+            for k, b in enumerate(sel):
+                r = ref[b][method]
+                if isinstance(r, str):          # the reference itself stops here (undefined R_f): we must flag it
+                    assert res.status[k] & (_lib.ST_NO_POSE_2 | _lib.ST_NO_POSE_3), (option, cfg, meta[b])
+                    continue
+                worst[method] = max(worst[method], rel_frob_up_to_sign(r[3], res[3][k])) if method == "tft" else worst[method]
+                assert votes_equal(res.votes[k], r[5]), (option, cfg, meta[b], res.votes[k], r[5])
+                if vote_tie(r[5]):
+                    continue
+                if method == "f":
+                    worst["f"] = max(worst["f"], rel_frob_up_to_sign(r[6], res.F21[k]), rel_frob_up_to_sign(r[7], res.F31[k]))
+                    assert rel_frob_up_to_sign(r[6], res.F21[k]) < TOL_MODEL and rel_frob_up_to_sign(r[7], res.F31[k]) < TOL_MODEL
+                assert_pose_close(r[:5], (res[0][k], res[1][k], res[2][k], res[3][k], res.repr_err[k]),
+                                  "%s %s %s trial %s" % (option, cfg, method, meta[b]))
+                compared[method] += 1
+    print("experiments.m option=%s: compared %s trials, EIG_NOCONV %s, worst rel. model difference %s"
+          % (option, compared, noconv, {k: "%.2e" % v for k, v in worst.items()}))
+    assert compared["tft"] >= 0.9 * len(jobs)
+
+
+def test_device_generator_bit_exact_on_collinear_and_long_focal_scenes(tvf):
+    """generateSyntheticScene.m:60-67 (p_coll for angle >= 70: centres pushed onto a line) and :53-57 (focal length
+    scaling K and the centres): the device generator against the host generator, bit for bit."""
+    from tft_vs_fund_b200 import scene
+    for focalL, angle, n in ((50, 70, 12), (50, 166, 12), (50, 179.5, 12), (50, 180, 20), (20, 0, 12), (300, 0, 12), (160, 175, 25)):
+        host = scene.sweep_batch(13 * 12, n, first_trial=26, focalL=focalL, angle=angle)
+        dev = scene.sweep_batch_device(13 * 12, n, first_trial=26, focalL=focalL, angle=angle)
+        assert np.array_equal(host["Corresp"], dev["Corresp"]), (focalL, angle, n)
+        CalM, R_t0, C, _ = o.experiments_subsample(n, 0.5, 3, focalL, angle)          # trial j = 26 + 2: level 2, seed 3
+        assert np.array_equal(C, host["Corresp"][2]) and np.array_equal(CalM, host["CalM"])
+        assert np.array_equal(R_t0[0], host["R_t0"][0]) and np.array_equal(R_t0[1], host["R_t0"][1])
+
+
+# ------------------------------------------------------------------------------ (e) shards == single call
+def _outputs(res):
+    return [np.asarray(x) for x in res[:4]] + [np.asarray(res.repr_err), np.asarray(res.status), np.asarray(res.votes)] + \
+           ([np.asarray(res.F21), np.asarray(res.F31)] if res.F21 is not None else [])
+
+
+@pytest.mark.parametrize("method", ["tft", "f", "optf"])
+def test_sharded_call_equals_single_call_bit_for_bit(tvf, method):
+    """contiguous trial ranges per device, no exchange.  A group handle (tvf_create_multi) with two members on
+    one GPU -- and with two and all GPUs when the box has them -- returns exactly the bits of the one-device call,
+    votes and statuses included; so do two explicit half-range calls (what two torchrun ranks do)."""
+    from tft_vs_fund_b200 import scene, _lib
+    fn = {"tft": tvf.LinearTFTPoseEstimation, "f": tvf.LinearFPoseEstimation, "optf": tvf.OptimFPoseEstimation}[method]
+    B = 13 * 701 + 5                                              # odd, does not divide by 2 or 3
+    d = scene.sweep_batch(B, 20, first_trial=13 * 77)
+    C, CalM = d["Corresp"], d["CalM"]
+    single = _outputs(fn(C, CalM, device=0))
+    ndev = _lib.load().tvf_device_count()
+    groups = [(0, 0), (0, 0, 0)]
+    if ndev >= 2:
+        groups += [(0, 1), tuple(range(ndev))]
+    for devs in groups:
+        h = _lib.handle(devs)
+        assert h.lib.tvf_num_devices(h._h) == len(devs)
+        got = _outputs(fn(C, CalM, device=devs))
+        for a, b in zip(single, got):
+            assert np.array_equal(a, b, equal_nan=True), (method, devs)
+    # two ranks, each solving its own contiguous range (sharding.shard_range), concatenated in rank order
+    from tft_vs_fund_b200.sharding import shard_range
+    parts = []
+    for rank in range(2):
+        lo, hi = shard_range(B, rank, 2)
+        parts.append(_outputs(fn(C[lo:hi], CalM, device=(rank % ndev))))
+    for a, p0, p1 in zip(single, parts[0], parts[1]):
+        assert np.array_equal(a, np.concatenate([p0, p1]), equal_nan=True), method
+    # per-problem CalM through the group handle
+    got = _outputs(fn(C[:999], np.broadcast_to(CalM, (999, 9, 3)).copy(), device=(0, 0)))
+    for a, b in zip(single, got):
+        assert np.array_equal(a[:999], b, equal_nan=True)
+
+
+def test_sharded_device_resident_sweep_equals_unsharded(tvf):
+    """tvf_sweep_run over [0, B) == the rank-ordered sum of its two halves: per-level counts exact, sums to rounding
+    (the per-trial values are bit-identical; only the order of the per-level additions differs)."""
+    from tft_vs_fund_b200 import _lib, scene
+    h = _lib.handle(0)
+    K, Ps, R_t0 = scene.scene_cameras(50, 0)
+    lv = np.ascontiguousarray(np.arange(0.0, 3.0 + 1e-9, 0.25)); P = np.ascontiguousarray(np.stack(Ps))
+    calm = np.ascontiguousarray(np.tile(K, (3, 1)).T); g2 = np.ascontiguousarray(R_t0[0].T); g3 = np.ascontiguousarray(R_t0[1].T)
+    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
+    B = 13 * 4000 + 7
+
+    def run(first, count):
+        t = np.zeros((13, 5))
+        h.call("tvf_sweep_run", 1, first, count, 20, dp(lv), 13, dp(P), 1800.0, 1200.0, dp(calm), dp(g2), dp(g3), dp(t))
+        return t
+    whole = run(0, B)
+    half = B // 2 + 3
+    parts = run(0, half) + run(half, B - half)
+    assert np.array_equal(whole[:, 3:], parts[:, 3:])
+    assert np.max(np.abs(whole[:, :3] - parts[:, :3]) / np.abs(whole[:, :3])) < 1e-12

@@ -29,6 +29,13 @@ ST_NONFINITE = 16
 LINEARF_ERRMSG = ("At least 8 correspondences are necessary to compute the "
                   "fundamental matrix linearly\\n")
 
+class PoseOut(C.Structure):
+    """tvf_pose_out of include/tvf.h: every optional output of a pose call (host or device pointers)."""
+    _fields_ = [(k, C.c_void_p) for k in ("Rt2", "Rt3", "reconst", "T", "repr_err", "F21", "F31", "iter", "votes", "status")]
+
+
+METHOD_IDS = {"tft": 1, "f": 7, "optf": 8}      # numbering of experiments.m:51-59
+
 # name -> (restype, argtypes); mirrors include/tvf.h one to one
 _H = C.c_void_p
 _D = c_double_p
@@ -39,6 +46,11 @@ SIGNATURES = {
     "tvf_version": (_I, []),
     "tvf_device_count": (_I, []),
     "tvf_create": (_I, [C.POINTER(_H), _I]),
+    "tvf_create_multi": (_I, [C.POINTER(_H), C.POINTER(C.c_int), _I]),
+    "tvf_num_devices": (_I, [_H]),
+    "tvf_set_host_register": (_I, [_H, _I]),
+    "tvf_pose": (_I, [_H, _I, _D, _D, _I, _I, _L, C.POINTER(PoseOut)]),
+    "tvf_pose_dev": (_I, [_H, _I, C.c_void_p, C.c_void_p, _I, _I, _L, C.POINTER(PoseOut)]),
     "tvf_destroy": (None, [_H]),
     "tvf_last_error": (C.c_char_p, [_H]),
     "tvf_device": (_I, [_H]),
@@ -58,7 +70,7 @@ SIGNATURES = {
     "tvf_linear_f": (_I, [_H, _D, _D, _I, _I, _L, _D, _S]),
     "tvf_normalize2d": (_I, [_H, _D, _I, _L, _D, _D]),
     "tvf_transform_tft": (_I, [_H, _D, _D, _D, _D, _I, _I, _L, _D]),
-    "tvf_rt_from_tft": (_I, [_H, _D, _D, _I, _D, _I, _L, _D, _D, _S]),
+    "tvf_rt_from_tft": (_I, [_H, _D, _D, _I, _D, _I, _L, _D, _D, _S, _S]),
     "tvf_tft_from_p": (_I, [_H, _D, _D, _D, _L, _D]),
     "tvf_triangulate": (_I, [_H, _D, _I, _I, _D, _I, _I, _L, _D]),
     "tvf_repr_error": (_I, [_H, _D, _I, _I, _D, _I, _I, _L, _D, _I, _D]),
@@ -109,11 +121,14 @@ _handles = {}
 
 
 def handle(device=None):
-    """Process-wide handle per device (created on first use)."""
+    """Process-wide handle per device (created on first use).  `device` may be a tuple/list of device ids: a group
+    handle (tvf_create_multi) whose host-pointer pose calls shard the batch over those GPUs."""
     lib = load()
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0")) if lib.tvf_device_count() > 1 else 0
         device = device % max(1, lib.tvf_device_count())
+    if isinstance(device, (list, tuple)):
+        device = tuple(int(d) for d in device)
     key = (threading.get_ident(), device)
     h = _handles.get(key)
     if h is None:
@@ -126,10 +141,14 @@ class Handle:
     def __init__(self, device=0):
         self.lib = load()
         self._h = C.c_void_p()
-        rc = self.lib.tvf_create(C.byref(self._h), int(device))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*[int(d) for d in device])
+            rc = self.lib.tvf_create_multi(C.byref(self._h), ids, len(device))
+        else:
+            rc = self.lib.tvf_create(C.byref(self._h), int(device))
         if rc != TVF_OK:
             msg = self.lib.tvf_last_error(None)
-            raise TvfError("tvf_create(device=%d) failed (%d): %s" % (device, rc, msg.decode() if msg else ""))
+            raise TvfError("tvf_create(device=%s) failed (%d): %s" % (device, rc, msg.decode() if msg else ""))
         self.device = device
 
     def close(self):

@@ -63,11 +63,18 @@ def _calm(CalM, B):
 
 
 class PoseResult(tuple):
-    """(R_t_2, R_t_3, Reconst, T, iter) like the reference, plus .repr_err, .status (and .F21/.F31)."""
+    """(R_t_2, R_t_3, Reconst, T, iter) like the reference, plus .repr_err, .status, .votes (and .F21/.F31).
+    votes: (B,10) int32 -- the cheirality votes of recover_R_t (R_t_from_TFT.m:91-104): 4 for pair (1,2), 4 for pair
+    (1,3) in the reference's candidate order, then the two NaN bit masks."""
     repr_err = None
     status = None
+    votes = None
     F21 = None
     F31 = None
+
+
+def _vp(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
 
 
 def _pose(method, Corresp, CalM, device):
@@ -78,19 +85,14 @@ def _pose(method, Corresp, CalM, device):
     n = c.shape[1]
     calm, cb = _calm(CalM, B)
     Rt2 = np.empty((B, 12)); Rt3 = np.empty((B, 12)); Rec = np.empty((B, 3 * n)); T = np.empty((B, 27))
-    rep = np.empty(B); st = np.zeros(B, dtype=np.int32)
-    F21 = F31 = None
-    if method == "tft":
-        h.call("tvf_linear_tft_pose", _p(c), _p(calm), cb, n, B, _p(Rt2), _p(Rt3), _p(Rec), _p(T), _p(rep),
-               st.ctypes.data_as(_ip))
-    elif method == "f":
+    rep = np.empty(B); st = np.zeros(B, dtype=np.int32); votes = np.zeros((B, 10), dtype=np.int32)
+    F21 = F31 = its = None
+    if method != "tft":
         F21 = np.empty((B, 9)); F31 = np.empty((B, 9))
-        h.call("tvf_linear_f_pose", _p(c), _p(calm), cb, n, B, _p(Rt2), _p(Rt3), _p(Rec), _p(T), _p(rep),
-               _p(F21), _p(F31), st.ctypes.data_as(_ip))
-    else:
-        F21 = np.empty((B, 9)); F31 = np.empty((B, 9)); its = np.zeros(B, dtype=np.int32)
-        h.call("tvf_optim_f_pose", _p(c), _p(calm), cb, n, B, _p(Rt2), _p(Rt3), _p(Rec), _p(T), _p(rep),
-               _p(F21), _p(F31), its.ctypes.data_as(_ip), st.ctypes.data_as(_ip))
+    if method == "optf":
+        its = np.zeros(B, dtype=np.int32)
+    out = _lib.PoseOut(_vp(Rt2), _vp(Rt3), _vp(Rec), _vp(T), _vp(rep), _vp(F21), _vp(F31), _vp(its), _vp(votes), _vp(st))
+    h.call("tvf_pose", _lib.METHOD_IDS[method], _p(c), _p(calm), cb, n, B, C.byref(out))
     it = np.zeros(B) if batched else 0                      # iter=0  (LinearTFTPoseEstimation.m:62)
     if method == "optf":
         it = its.astype(np.float64) if batched else int(its[0])      # iter=it1+it2 (OptimFPoseEstimation.m:49)
@@ -98,6 +100,7 @@ def _pose(method, Corresp, CalM, device):
                       _from_cm(Rec, B, (3, n), batched), _from_cm(T, B, (3, 3, 3), batched), it))
     out.repr_err = rep if batched else float(rep[0])
     out.status = st if batched else int(st[0])
+    out.votes = votes if batched else votes[0]
     if F21 is not None:
         out.F21 = _from_cm(F21, B, (3, 3), batched); out.F31 = _from_cm(F31, B, (3, 3), batched)
     if not batched and (out.status & (_lib.ST_NO_POSE_2 | _lib.ST_NO_POSE_3)):
@@ -189,16 +192,20 @@ def transform_TFT(T_old, M1, M2, M3, inverse=0, device=None):
     return _from_cm(out, B, (3, 3, 3), batched)
 
 
-def R_t_from_TFT(T, CalM, Corresp, device=None):
-    """[R_t_2,R_t_3]=R_t_from_TFT(T,CalM,Corresp) (TFT_methods/R_t_from_TFT.m:1,40-106)."""
+def R_t_from_TFT(T, CalM, Corresp, device=None, return_votes=False):
+    """[R_t_2,R_t_3]=R_t_from_TFT(T,CalM,Corresp) (TFT_methods/R_t_from_TFT.m:1,40-106).  return_votes=True appends
+    the (B,10) / (10,) int32 cheirality votes of the local recover_R_t (:91-104; layout: see PoseResult)."""
     h = _lib.handle(device)
     t, batched, B = _cm(T, 3)
     c, _, _ = _cm(Corresp, 2)
     n = c.shape[1]
     calm, cb = _calm(CalM, B)
     Rt2 = np.empty((B, 12)); Rt3 = np.empty((B, 12)); st = np.zeros(B, dtype=np.int32)
-    h.call("tvf_rt_from_tft", _p(t), _p(calm), cb, _p(c), n, B, _p(Rt2), _p(Rt3), st.ctypes.data_as(_ip))
-    return _from_cm(Rt2, B, (3, 4), batched), _from_cm(Rt3, B, (3, 4), batched)
+    votes = np.zeros((B, 10), dtype=np.int32)
+    h.call("tvf_rt_from_tft", _p(t), _p(calm), cb, _p(c), n, B, _p(Rt2), _p(Rt3), votes.ctypes.data_as(_ip),
+           st.ctypes.data_as(_ip))
+    out = (_from_cm(Rt2, B, (3, 4), batched), _from_cm(Rt3, B, (3, 4), batched))
+    return out + ((votes if batched else votes[0]),) if return_votes else out
 
 
 def TFT_from_P(P1, P2, P3, device=None):

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "tvf_kernels.h"
@@ -62,6 +63,11 @@ struct tvf_context {
     std::vector<cudaEvent_t> free_events;
     double prof_ms[TVF_NUM_KERNELS] = {};
     int64_t prof_n[TVF_NUM_KERNELS] = {};
+    // tvf_create_multi: further devices of a group handle (this context is member 0); the host-pointer pose entry points
+    // shard B over the members, one host thread per device (experiments.m:91-143 is the loop that fans out)
+    std::vector<tvf_context*> peers;
+    // tvf_set_host_register: pin caller buffers that are pageable for the duration of a host-pointer pose call
+    int host_register = 0;
 };
 
 namespace {
@@ -129,7 +135,7 @@ size_t carve(char* base, int n, int64_t C, bool host_io, bool calm_batched, Chun
     b.iter_sum = c.take<int>(C);
     if (host_io) {
         b.in = c.take<double>((size_t)6 * n * C);
-        b.calm = calm_batched ? c.take<double>(27 * C) : nullptr;
+        b.calm = c.take<double>(calm_batched ? 27 * C : 27);
         b.Rt2 = c.take<double>(12 * C);
         b.Rt3 = c.take<double>(12 * C);
         b.reconst = c.take<double>((size_t)3 * n * C);
@@ -251,30 +257,46 @@ int count_flagged(const int32_t* st, int64_t B) {
     return (int)(c > 0x7fffffff ? 0x7fffffff : c);
 }
 
-int pose_host(tvf_handle_t h, Method method, const double* corresp, const double* calm, int calm_batched, int n,
-              int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21,
-              double* F31, int32_t* status, int32_t* iter = nullptr) {
-    int rc = check_pose_args(h, corresp, calm, n, B, method);
-    if (rc != TVF_OK) return rc;
+// outputs of a pose call (any may be null); `votes` = 10 int32 per problem: the 4 + 4 cheirality votes of
+// R_t_from_TFT.m:91-104 in the reference's candidate order for the pairs (1,2) and (1,3), then the two NaN masks
+struct PoseOut {
+    double* Rt2; double* Rt3; double* reconst; double* T; double* repr_err; double* F21; double* F31;
+    int32_t* iter; int32_t* votes; int32_t* status;
+};
+
+// caller buffers that are pageable get pinned for the duration of a call (tvf_set_host_register); RAII
+struct HostPins {
+    std::vector<void*> pinned;
+    void add(const void* p, size_t bytes) {
+        if (!p || bytes < (1u << 20)) return;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return; }
+        if (at.type != cudaMemoryTypeUnregistered) return;
+        if (cudaHostRegister(const_cast<void*>(p), bytes, cudaHostRegisterPortable) == cudaSuccess) pinned.push_back(const_cast<void*>(p));
+        else cudaGetLastError();
+    }
+    ~HostPins() { for (void* p : pinned) cudaHostUnregister(p); }
+};
+
+int pose_host_one(tvf_handle_t h, Method method, const double* corresp, const double* calm, int calm_batched, int n,
+                  int64_t B, const PoseOut& o) {
     if (B == 0) return TVF_OK;
     TVF_CK(cudaSetDevice(h->device));
     const int64_t C = pick_chunk(h, n, B, true);
     const size_t need = carve(nullptr, n, C, true, calm_batched != 0, nullptr);
-    double* d_calm_shared = nullptr;
-    if (!calm_batched) {
-        void* p; rc = ensure_scratch(h, 0, 27 * sizeof(double), &p); if (rc) return rc;
-        d_calm_shared = (double*)p;
-        TVF_CK(cudaMemcpy(d_calm_shared, calm, 27 * sizeof(double), cudaMemcpyHostToDevice));
-    }
     std::vector<int32_t> st_tmp;
-    int32_t* st_host = status;
+    int32_t* st_host = o.status;
     if (!st_host) { st_tmp.resize((size_t)B); st_host = st_tmp.data(); }
+    // earlier asynchronous *_dev / sweep work of this handle may still be using slot 0's arena
+    TVF_CK(cudaStreamSynchronize(h->slot[0].stream));
+    if (h->use_user_stream) TVF_CK(cudaStreamSynchronize(h->user_stream));
 
     // Chunk schedule.  The call is bound by the host link (H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1
     // overlap).  Quarter- and half-size chunks at both ends, meant to shorten the pipeline's fill and drain, were
     // measured SLOWER (4.31e7 vs 4.56e7 solves/s end to end at 1 M problems, profiles/r01_variants.md) and are off.
     const bool ramp = TVF_RAMP && B >= 6 * C && C >= 4096;
     int64_t done = 0; int ci = 0;
+    int rc = TVF_OK;
     while (done < B) {
         const int64_t rem = B - done;
         int64_t Bc = (rem < C) ? rem : C;
@@ -295,26 +317,25 @@ int pose_host(tvf_handle_t h, Method method, const double* corresp, const double
         rc = ensure_arena(h, s, need); if (rc) return rc;
         ChunkBufs b; carve(s.arena, n, C, true, calm_batched != 0, &b);
         TVF_CK(cudaMemcpyAsync(b.in, corresp + done * 6 * n, (size_t)Bc * 6 * n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-        const double* d_calm = d_calm_shared;
-        if (calm_batched) {
-            TVF_CK(cudaMemcpyAsync(b.calm, calm + done * 27, (size_t)Bc * 27 * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-            d_calm = b.calm;
-        }
-        rc = run_pose_chunk(h, s.stream, method, b.in, d_calm, calm_batched, n, Bc,
-                            (method == METHOD_TFT || T) ? b.T : nullptr, b.F, b.core, b.cand, b.votes, b.scale, b.Rt2, b.Rt3,
+        // CalM travels on the chunk's own stream (ordered before the kernels that read it), shared 9x3 included
+        TVF_CK(cudaMemcpyAsync(b.calm, calm + (calm_batched ? done * 27 : 0), (size_t)(calm_batched ? Bc * 27 : 27) * sizeof(double),
+                               cudaMemcpyHostToDevice, s.stream));
+        rc = run_pose_chunk(h, s.stream, method, b.in, b.calm, calm_batched, n, Bc,
+                            (method == METHOD_TFT || o.T) ? b.T : nullptr, b.F, b.core, b.cand, b.votes, b.scale, b.Rt2, b.Rt3,
                             b.reconst, b.repr, b.status, b.iters, b.iter_sum);
         if (rc) return rc;
-        if (iter && method == METHOD_OPTF)
-            TVF_CK(cudaMemcpyAsync(iter + done, b.iter_sum, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-        if (Rt2) TVF_CK(cudaMemcpyAsync(Rt2 + done * 12, b.Rt2, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (Rt3) TVF_CK(cudaMemcpyAsync(Rt3 + done * 12, b.Rt3, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (reconst) TVF_CK(cudaMemcpyAsync(reconst + done * 3 * n, b.reconst, (size_t)Bc * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (T) TVF_CK(cudaMemcpyAsync(T + done * 27, b.T, (size_t)Bc * 27 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (repr_err) TVF_CK(cudaMemcpyAsync(repr_err + done, b.repr, (size_t)Bc * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (method != METHOD_TFT && F21)
-            TVF_CK(cudaMemcpy2DAsync(F21 + done * 9, 72, b.F, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
-        if (method != METHOD_TFT && F31)
-            TVF_CK(cudaMemcpy2DAsync(F31 + done * 9, 72, b.F + 9, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
+        if (o.iter && method == METHOD_OPTF)
+            TVF_CK(cudaMemcpyAsync(o.iter + done, b.iter_sum, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (o.Rt2) TVF_CK(cudaMemcpyAsync(o.Rt2 + done * 12, b.Rt2, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (o.Rt3) TVF_CK(cudaMemcpyAsync(o.Rt3 + done * 12, b.Rt3, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (o.reconst) TVF_CK(cudaMemcpyAsync(o.reconst + done * 3 * n, b.reconst, (size_t)Bc * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (o.T) TVF_CK(cudaMemcpyAsync(o.T + done * 27, b.T, (size_t)Bc * 27 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (o.repr_err) TVF_CK(cudaMemcpyAsync(o.repr_err + done, b.repr, (size_t)Bc * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+        if (o.votes) TVF_CK(cudaMemcpyAsync(o.votes + done * 10, b.votes, (size_t)Bc * 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        if (method != METHOD_TFT && o.F21)
+            TVF_CK(cudaMemcpy2DAsync(o.F21 + done * 9, 72, b.F, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
+        if (method != METHOD_TFT && o.F31)
+            TVF_CK(cudaMemcpy2DAsync(o.F31 + done * 9, 72, b.F + 9, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
         TVF_CK(cudaMemcpyAsync(st_host + done, b.status, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
         done += Bc; ++ci;
     }
@@ -322,9 +343,68 @@ int pose_host(tvf_handle_t h, Method method, const double* corresp, const double
     return count_flagged(st_host, B);
 }
 
+// contiguous [lo, hi) of B problems for member g of G (remainder to the first members; same rule as sharding.shard_range)
+inline void shard_of(int64_t B, int g, int G, int64_t* lo, int64_t* hi) {
+    const int64_t base = B / G, rem = B % G;
+    *lo = g * base + (g < rem ? g : rem);
+    *hi = *lo + base + (g < rem ? 1 : 0);
+}
+
+int pose_host(tvf_handle_t h, Method method, const double* corresp, const double* calm, int calm_batched, int n,
+              int64_t B, const PoseOut& o) {
+    int rc = check_pose_args(h, corresp, calm, n, B, method);
+    if (rc != TVF_OK) return rc;
+    if (B == 0) return TVF_OK;
+    HostPins pins;
+    if (h->host_register) {
+        TVF_CK(cudaSetDevice(h->device));
+        pins.add(corresp, (size_t)B * 6 * n * 8);
+        if (calm_batched) pins.add(calm, (size_t)B * 27 * 8);
+        pins.add(o.Rt2, (size_t)B * 96); pins.add(o.Rt3, (size_t)B * 96); pins.add(o.reconst, (size_t)B * 3 * n * 8);
+        pins.add(o.T, (size_t)B * 216); pins.add(o.repr_err, (size_t)B * 8); pins.add(o.votes, (size_t)B * 40);
+        pins.add(o.F21, (size_t)B * 72); pins.add(o.F31, (size_t)B * 72); pins.add(o.status, (size_t)B * 4);
+    }
+    const int G = 1 + (int)h->peers.size();
+    if (G == 1 || B < G) return pose_host_one(h, method, corresp, calm, calm_batched, n, B, o);
+    // group handle: member g solves the contiguous range shard_of(B, g, G) on its own device from its own host thread;
+    // problems are independent and a problem's result does not depend on its batch, so the outputs are bit-identical
+    // to a single-device call
+    std::vector<int> rcs((size_t)G, TVF_OK);
+    auto run = [&](int g) {
+        tvf_handle_t m = (g == 0) ? h : h->peers[(size_t)g - 1];
+        int64_t lo, hi; shard_of(B, g, G, &lo, &hi);
+        PoseOut s = o;
+        if (s.Rt2) s.Rt2 += lo * 12;
+        if (s.Rt3) s.Rt3 += lo * 12;
+        if (s.reconst) s.reconst += lo * 3 * n;
+        if (s.T) s.T += lo * 27;
+        if (s.repr_err) s.repr_err += lo;
+        if (s.F21) s.F21 += lo * 9;
+        if (s.F31) s.F31 += lo * 9;
+        if (s.iter) s.iter += lo;
+        if (s.votes) s.votes += lo * 10;
+        if (s.status) s.status += lo;
+        m->chunk_user = h->chunk_user;
+        rcs[(size_t)g] = pose_host_one(m, method, corresp + lo * 6 * n, calm + (calm_batched ? lo * 27 : 0), calm_batched, n, hi - lo, s);
+    };
+    std::vector<std::thread> th;
+    for (int g = 1; g < G; ++g) th.emplace_back(run, g);
+    run(0);
+    for (auto& t : th) t.join();
+    int64_t flagged = 0;
+    for (int g = 0; g < G; ++g) {
+        if (rcs[(size_t)g] < 0) {
+            if (g > 0) h->err = "device " + std::to_string(h->peers[(size_t)g - 1]->device) + ": " + h->peers[(size_t)g - 1]->err;
+            return rcs[(size_t)g];
+        }
+        flagged += rcs[(size_t)g];
+    }
+    cudaSetDevice(h->device);
+    return (int)(flagged > 0x7fffffff ? 0x7fffffff : flagged);
+}
+
 int pose_dev(tvf_handle_t h, Method method, const double* corresp, const double* calm, int calm_batched, int n,
-             int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21,
-             double* F31, int32_t* status, int32_t* iter = nullptr) {
+             int64_t B, const PoseOut& o) {
     int rc = check_pose_args(h, corresp, calm, n, B, method);
     if (rc != TVF_OK) return rc;
     if (B == 0) return TVF_OK;
@@ -340,18 +420,18 @@ int pose_dev(tvf_handle_t h, Method method, const double* corresp, const double*
     double* tmpRt3 = tmpRt2 + 12 * C;
     for (int64_t done = 0; done < B; done += C) {
         const int64_t Bc = (B - done < C) ? (B - done) : C;
-        double* dT = T ? T + done * 27 : (method == METHOD_TFT ? b.T : nullptr);
-        double* dRt2 = Rt2 ? Rt2 + done * 12 : tmpRt2;
-        double* dRt3 = Rt3 ? Rt3 + done * 12 : tmpRt3;
+        double* dT = o.T ? o.T + done * 27 : (method == METHOD_TFT ? b.T : nullptr);
+        double* dRt2 = o.Rt2 ? o.Rt2 + done * 12 : tmpRt2;
+        double* dRt3 = o.Rt3 ? o.Rt3 + done * 12 : tmpRt3;
         rc = run_pose_chunk(h, st, method, corresp + done * 6 * n, calm + (calm_batched ? done * 27 : 0), calm_batched, n,
-                            Bc, dT, b.F, b.core, b.cand, b.votes, b.scale, dRt2, dRt3, reconst ? reconst + done * 3 * n : nullptr,
-                            repr_err ? repr_err + done : nullptr, status ? status + done : b.status, b.iters,
-                            iter ? iter + done : nullptr);
+                            Bc, dT, b.F, b.core, b.cand, o.votes ? o.votes + done * 10 : b.votes, b.scale, dRt2, dRt3,
+                            o.reconst ? o.reconst + done * 3 * n : nullptr, o.repr_err ? o.repr_err + done : nullptr,
+                            o.status ? o.status + done : b.status, b.iters, o.iter ? o.iter + done : nullptr);
         if (rc) return rc;
-        if (method != METHOD_TFT && F21)
-            TVF_CK(cudaMemcpy2DAsync(F21 + done * 9, 72, b.F, 144, 72, (size_t)Bc, cudaMemcpyDeviceToDevice, st));
-        if (method != METHOD_TFT && F31)
-            TVF_CK(cudaMemcpy2DAsync(F31 + done * 9, 72, b.F + 9, 144, 72, (size_t)Bc, cudaMemcpyDeviceToDevice, st));
+        if (method != METHOD_TFT && o.F21)
+            TVF_CK(cudaMemcpy2DAsync(o.F21 + done * 9, 72, b.F, 144, 72, (size_t)Bc, cudaMemcpyDeviceToDevice, st));
+        if (method != METHOD_TFT && o.F31)
+            TVF_CK(cudaMemcpy2DAsync(o.F31 + done * 9, 72, b.F + 9, 144, 72, (size_t)Bc, cudaMemcpyDeviceToDevice, st));
     }
     return TVF_OK;
 }
@@ -402,7 +482,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, 
 // =========================================================================== C ABI
 extern "C" {
 
-int tvf_version(void) { return 100; }
+int tvf_version(void) { return 200; }
 
 int tvf_device_count(void) {
     int n = 0;
@@ -436,6 +516,8 @@ int tvf_create(tvf_handle_t* out, int device) {
 
 void tvf_destroy(tvf_handle_t h) {
     if (!h) return;
+    for (tvf_handle_t m : h->peers) tvf_destroy(m);
+    h->peers.clear();
     cudaSetDevice(h->device);
     for (int i = 0; i < NSLOT; ++i) {
         if (h->slot[i].stream) { cudaStreamSynchronize(h->slot[i].stream); cudaStreamDestroy(h->slot[i].stream); }
@@ -446,6 +528,32 @@ void tvf_destroy(tvf_handle_t h) {
     for (auto& ev : h->events) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
     for (auto e : h->free_events) cudaEventDestroy(e);
     delete h;
+}
+
+int tvf_create_multi(tvf_handle_t* out, const int* devices, int n_dev) {
+    if (!out) return fail(nullptr, TVF_ERR_ARG, "out must not be NULL");
+    *out = nullptr;
+    if (!devices || n_dev < 1) return fail(nullptr, TVF_ERR_ARG, "need at least one device");
+    tvf_handle_t h = nullptr;
+    int rc = tvf_create(&h, devices[0]);
+    if (rc != TVF_OK) return rc;
+    for (int i = 1; i < n_dev; ++i) {
+        tvf_handle_t m = nullptr;
+        rc = tvf_create(&m, devices[i]);
+        if (rc != TVF_OK) { tvf_destroy(h); return rc; }
+        h->peers.push_back(m);
+    }
+    cudaSetDevice(h->device);
+    *out = h;
+    return TVF_OK;
+}
+
+int tvf_num_devices(tvf_handle_t h) { return h ? 1 + (int)h->peers.size() : 0; }
+
+int tvf_set_host_register(tvf_handle_t h, int on) {
+    if (!h) return TVF_ERR_ARG;
+    h->host_register = on ? 1 : 0;
+    return TVF_OK;
 }
 
 const char* tvf_last_error(tvf_handle_t h) { return h ? h->err.c_str() : g_create_error.c_str(); }
@@ -531,7 +639,12 @@ void* tvf_host_alloc(size_t bytes) {
 
 void tvf_host_free(void* p) { if (p) cudaFreeHost(p); }
 
-int64_t tvf_launch_count(tvf_handle_t h) { return h ? h->launches : 0; }
+int64_t tvf_launch_count(tvf_handle_t h) {
+    if (!h) return 0;
+    int64_t n = h->launches;
+    for (tvf_handle_t m : h->peers) n += m->launches;
+    return n;
+}
 
 int tvf_profile_enable(tvf_handle_t h, int on) {
     if (!h) return TVF_ERR_ARG;
@@ -587,40 +700,70 @@ const char* tvf_kernel_name(int id) {
     return (id >= 0 && id < TVF_NUM_KERNELS) ? names[id] : "";
 }
 
+static bool method_of(int id, Method* m) {
+    if (id == 1) { *m = METHOD_TFT; return true; }
+    if (id == 7) { *m = METHOD_F; return true; }
+    if (id == 8) { *m = METHOD_OPTF; return true; }
+    return false;
+}
+
+static PoseOut pose_out_of(const tvf_pose_out* o) {
+    PoseOut p{};
+    if (o) { p.Rt2 = o->Rt2; p.Rt3 = o->Rt3; p.reconst = o->reconst; p.T = o->T; p.repr_err = o->repr_err; p.F21 = o->F21;
+             p.F31 = o->F31; p.iter = o->iter; p.votes = o->votes; p.status = o->status; }
+    return p;
+}
+
+int tvf_pose(tvf_handle_t h, int method, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
+             const tvf_pose_out* out) {
+    Method m;
+    if (!h) return TVF_ERR_ARG;
+    if (!method_of(method, &m)) return fail(h, TVF_ERR_ARG, "method must be 1 (linear TFT), 7 (linear F) or 8 (optimal F)");
+    return pose_host(h, m, corresp, calm, calm_batched, n, B, pose_out_of(out));
+}
+
+int tvf_pose_dev(tvf_handle_t h, int method, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
+                 const tvf_pose_out* out) {
+    Method m;
+    if (!h) return TVF_ERR_ARG;
+    if (!method_of(method, &m)) return fail(h, TVF_ERR_ARG, "method must be 1 (linear TFT), 7 (linear F) or 8 (optimal F)");
+    return pose_dev(h, m, corresp, calm, calm_batched, n, B, pose_out_of(out));
+}
+
 int tvf_linear_tft_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
                         double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, int32_t* status) {
-    return pose_host(h, METHOD_TFT, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, nullptr, nullptr, status);
+    return pose_host(h, METHOD_TFT, corresp, calm, calm_batched, n, B, PoseOut{Rt2, Rt3, reconst, T, repr_err, nullptr, nullptr, nullptr, nullptr, status});
 }
 
 int tvf_linear_f_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
                       double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21, double* F31,
                       int32_t* status) {
-    return pose_host(h, METHOD_F, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, F21, F31, status);
+    return pose_host(h, METHOD_F, corresp, calm, calm_batched, n, B, PoseOut{Rt2, Rt3, reconst, T, repr_err, F21, F31, nullptr, nullptr, status});
 }
 
 int tvf_optim_f_pose(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
                      double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21, double* F31,
                      int32_t* iter, int32_t* status) {
-    return pose_host(h, METHOD_OPTF, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, F21, F31, status, iter);
+    return pose_host(h, METHOD_OPTF, corresp, calm, calm_batched, n, B, PoseOut{Rt2, Rt3, reconst, T, repr_err, F21, F31, iter, nullptr, status});
 }
 
 int tvf_optim_f_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
                          double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21, double* F31,
                          int32_t* iter, int32_t* status) {
-    return pose_dev(h, METHOD_OPTF, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, F21, F31, status, iter);
+    return pose_dev(h, METHOD_OPTF, corresp, calm, calm_batched, n, B, PoseOut{Rt2, Rt3, reconst, T, repr_err, F21, F31, iter, nullptr, status});
 }
 
 int tvf_optim_f_max_n(void) { return optimf_max_n(); }
 
 int tvf_linear_tft_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
                             double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, int32_t* status) {
-    return pose_dev(h, METHOD_TFT, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, nullptr, nullptr, status);
+    return pose_dev(h, METHOD_TFT, corresp, calm, calm_batched, n, B, PoseOut{Rt2, Rt3, reconst, T, repr_err, nullptr, nullptr, nullptr, nullptr, status});
 }
 
 int tvf_linear_f_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n, int64_t B,
                           double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err, double* F21, double* F31,
                           int32_t* status) {
-    return pose_dev(h, METHOD_F, corresp, calm, calm_batched, n, B, Rt2, Rt3, reconst, T, repr_err, F21, F31, status);
+    return pose_dev(h, METHOD_F, corresp, calm, calm_batched, n, B, PoseOut{Rt2, Rt3, reconst, T, repr_err, F21, F31, nullptr, nullptr, status});
 }
 
 int tvf_linear_tft(tvf_handle_t h, const double* p1, const double* p2, const double* p3, int rows, int n, int64_t B,
@@ -757,7 +900,7 @@ int tvf_transform_tft(tvf_handle_t h, const double* T_old, const double* M1, con
 }
 
 int tvf_rt_from_tft(tvf_handle_t h, const double* T, const double* calm, int calm_batched, const double* corresp, int n,
-                    int64_t B, double* Rt2, double* Rt3, int32_t* status) {
+                    int64_t B, double* Rt2, double* Rt3, int32_t* votes, int32_t* status) {
     if (!h) return TVF_ERR_ARG;
     if (!T || !calm || !corresp || n < 1 || B < 0) return fail(h, TVF_ERR_ARG, "NULL argument or bad size");
     if (B == 0) return TVF_OK;
@@ -788,6 +931,7 @@ int tvf_rt_from_tft(tvf_handle_t h, const double* T, const double* calm, int cal
     std::vector<int32_t> tmp; int32_t* sth = status;
     if (!sth) { tmp.resize((size_t)B); sth = tmp.data(); }
     u.back(Rt2, a.Rt2, 12 * (size_t)B); u.back(Rt3, a.Rt3, 12 * (size_t)B);
+    u.back(votes, (const int32_t*)a.votes, 10 * (size_t)B);
     u.back(sth, (const int32_t*)a.status, (size_t)B);
     int rc = u.finish();
     return rc ? rc : count_flagged(sth, B);

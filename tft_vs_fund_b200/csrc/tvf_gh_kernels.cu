@@ -315,17 +315,18 @@ int launch_optimf_gh(const double* corresp, int n, long long B, const double* ws
     if (B <= 0) return 1;
     const size_t smem = (size_t)GH_WARPS * (12 * (size_t)n + 32 * GH_FEAT + 11 * 12 + 12) * sizeof(double);
     if (smem > 200 * 1024) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(optimf_gh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) return 0;
-        attr_set = true;
+    // the opt-in is a per-device (per-context) property of the function: set it on every launch (cheap), never cached
+    // in a process-wide static -- a handle on a second GPU would otherwise never get it
+    if (cudaFuncSetAttribute(optimf_gh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
     }
     optimf_init_kernel<<<(unsigned)((B + 127) / 128), 128, 0, stream>>>(ws, B, Fio);
     long long blocks = (2 * B + GH_WARPS - 1) / GH_WARPS;
     const long long cap = (long long)sm_count * 16;
     if (blocks > cap) blocks = cap;
     optimf_gh_kernel<<<(unsigned)blocks, GH_WARPS * 32, smem, stream>>>(corresp, n, B, ws, Fio, iters, status);
-    return 1;
+    return cudaPeekAtLastError() == cudaSuccess ? 1 : 0;
 }
 
 }  // namespace tvf

@@ -357,17 +357,19 @@ int launch_tft_moments_large(const double* corresp, int n, long long B, int norm
     const int slice_pts = (n + LG_CLUSTER - 1) / LG_CLUSTER;
     const size_t smem = (size_t)slice_pts * 48 + sizeof(LargeScratch) + 128;
     if (smem > 200 * 1024) return 0;
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(tft_moments_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess)
-            return 0;
-        attr_set = true;
+    // per-device function attribute: set on every launch (cheap), never cached process-wide
+    if (cudaFuncSetAttribute(tft_moments_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
     }
     // clusters that can be co-resident (8 CTAs of a cluster must share a GPC, so this is not sm_count*3/8 in
     // general); scenes are assigned statically, so launching more than fit would serialise whole clusters.
-    static int max_clusters = 0;
-    static size_t max_clusters_smem = 0;
-    if (max_clusters == 0 || max_clusters_smem != smem) {
+    // Cached per (device, shared-memory size) and per host thread.
+    static thread_local int max_clusters = 0, max_clusters_dev = -1;
+    static thread_local size_t max_clusters_smem = 0;
+    int cur_dev = 0;
+    cudaGetDevice(&cur_dev);
+    if (max_clusters == 0 || max_clusters_smem != smem || max_clusters_dev != cur_dev) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(sm_count * 3 / LG_CLUSTER * LG_CLUSTER)); cfg.blockDim = dim3(LG_THREADS);
         cfg.dynamicSmemBytes = smem;
@@ -380,14 +382,14 @@ int launch_tft_moments_large(const double* corresp, int n, long long B, int norm
             cudaGetLastError();
             nc = sm_count * 2 / LG_CLUSTER;
         }
-        max_clusters = nc; max_clusters_smem = smem;
+        max_clusters = nc; max_clusters_smem = smem; max_clusters_dev = cur_dev;
     }
     long long clusters = max_clusters;
     if (clusters > B) clusters = B;
     if (clusters < 1) clusters = 1;
     tft_moments_large_kernel<<<(unsigned)(clusters * LG_CLUSTER), LG_THREADS, smem, stream>>>(corresp, n, B, slice_pts,
                                                                                             normalize, ws);
-    return 1;
+    return cudaPeekAtLastError() == cudaSuccess ? 1 : 0;
 }
 
 }  // namespace tvf

@@ -34,6 +34,40 @@ def load_corresp_triplets(path_to_data):
     return (m["indexes_sorted"].astype(np.int64), m["Corresp"], [str(x[0]) for x in m["im_names"].ravel()])
 
 
+class Dataset:
+    """What experiments_real.m:45-48,86-88 reads for one EPFL dataset: `indexes_sorted` (K x 4), the match list of a
+    triplet (N x 6, by 1-based image numbers) and the calibration/orientation (K, R, t) of an image."""
+
+    def __init__(self, indexes_sorted, corresp, camera):
+        self.indexes_sorted = np.asarray(indexes_sorted, dtype=np.int64)
+        self._corresp, self._camera = corresp, camera
+
+    def corresp(self, im1, im2, im3):
+        return np.asarray(self._corresp(im1, im2, im3), dtype=np.float64)
+
+    def camera(self, im):
+        return self._camera(im)
+
+
+def load_dataset(path_to_data):
+    """Dataset from the reference's files: Corresp_triplets.mat (MAT v5) and the `.camera` text files."""
+    idx, cor, names = load_corresp_triplets(path_to_data)
+    return Dataset(idx, lambda a, b, c: cor[a - 1, b - 1, c - 1],
+                   lambda im: readCalibrationOrientation_EPFL(path_to_data, names[im - 1])[:3])
+
+
+def dataset_from_arrays(indexes_sorted, matches, offsets, K, R, t):
+    """Dataset from packed arrays (the committed fixture tests/golden/epfl_inputs.npz): row r of indexes_sorted owns
+    matches[offsets[r]:offsets[r+1]]; K, R, t are stacked per image."""
+    idx = np.asarray(indexes_sorted, dtype=np.int64)
+    rows = {tuple(int(v) for v in idx[r, :3]): r for r in range(idx.shape[0])}
+
+    def corresp(a, b, c):
+        r = rows[(a, b, c)]
+        return matches[offsets[r]:offsets[r + 1]]
+    return Dataset(idx, corresp, lambda im: (K[im - 1], R[im - 1], t[im - 1]))
+
+
 def relative_poses(cams):
     """experiments_real.m:89-91: CalM = [K1;K2;K3], R_t0 = {[R2*R1', t2-R2*R1'*t1], [R3*R1', t3-R3*R1'*t1]}."""
     (K1, R1, t1), (K2, R2, t2), (K3, R3, t3) = cams
@@ -57,40 +91,50 @@ def inlier_filter(Corresp, CalM, R_t0, repr_err_th=1.0, device=None):
     return inl, mask, REr
 
 
-def prepare_triplet(path_to_data, indexes_sorted, corresp_by_triplet, im_names, it, repr_err_th=1.0, device=None):
-    """experiments_real.m:78-101 for the 1-based triplet number `it`."""
-    im = [int(v) for v in indexes_sorted[it - 1, 0:3]]
-    Corresp = np.asarray(corresp_by_triplet[im[0] - 1, im[1] - 1, im[2] - 1], dtype=np.float64).T      # :80
-    cams = [readCalibrationOrientation_EPFL(path_to_data, im_names[i - 1])[:3] for i in im]             # :86-88
+def prepare_triplet(data, it, repr_err_th=1.0, device=None):
+    """experiments_real.m:78-101 for the 1-based row `it` of indexes_sorted.  data: a Dataset."""
+    im = [int(v) for v in data.indexes_sorted[it - 1, 0:3]]
+    Corresp = data.corresp(*im).T                                                                       # :80
+    cams = [data.camera(i) for i in im]                                                                 # :86-88
     CalM, R_t0 = relative_poses(cams)
     inl, mask, REr = inlier_filter(Corresp, CalM, R_t0, repr_err_th, device)
     return dict(triplet=tuple(im), CalM=CalM, R_t0=R_t0, Corresp=Corresp, Corresp_inliers=inl, inlier_mask=mask, REr=REr)
 
 
-def run_real(path_to_data, triplets, initial_sample_size=100, methods=(1, 7), device=None):
-    """The linear-method part of experiments_real.m:75-138: per triplet, sample min(100, N) inliers
-    (documented stand-in for MATLAB's randsample: scene.SceneRNG(it).randsample), run methods 1 / 7, evaluate
-    ReprError over ALL inliers (triangulating them, :130-131) and AngError against the ground truth.
-    Returns dict method -> array (len(triplets), 3) of [repr_err, rot_err, t_err]."""
+def run_real(data, triplets_to_test, initial_sample_size=100, methods=(1, 7), device=None, details=None):
+    """The linear-method part of experiments_real.m:75-138.  `data`: a Dataset or the path of a dataset directory;
+    `triplets_to_test`: rows of indexes_sorted (1-based; the reference uses 1:70 / 1:50, :31-36).  Per loop index `it`:
+    pre-filter (:94-101), sample min(100, N) inliers with rng(it) (:103-105; documented stand-in for MATLAB's
+    randsample: scene.SceneRNG(it).randsample), run methods 1 / 7 on the sample (:126), evaluate ReprError over ALL
+    inliers (triangulating them, :130-131) and AngError against the ground truth (:133-136).
+    Returns dict method -> array (len(triplets_to_test), 3) of [repr_err, rot_err, t_err]; `details` (a list) receives
+    one dict per triplet (inlier count, ground-truth RMS, sample, per-method poses / T / votes)."""
     from .scene import SceneRNG
     from .experiments import METHODS
-    idx, cor, names = load_corresp_triplets(path_to_data)
-    out = {m: np.zeros((len(triplets), 3)) for m in methods}
-    for row, it in enumerate(triplets):
-        d = prepare_triplet(path_to_data, idx, cor, names, it, device=device)
+    if not isinstance(data, Dataset):
+        data = load_dataset(data)
+    out = {m: np.zeros((len(triplets_to_test), 3)) for m in methods}
+    for row, trip in enumerate(triplets_to_test):
+        it = row + 1                                                                                    # :75 loop index
+        d = prepare_triplet(data, trip, device=device)
         inl = d["Corresp_inliers"]
         N = inl.shape[1]
-        sample = SceneRNG(it).randsample(N, min(initial_sample_size, N))                               # :104-105
+        sample = SceneRNG(it).randsample(N, min(initial_sample_size, N))                               # :103-105
         C0 = inl[:, sample]
         CalM = d["CalM"]
+        rec = dict(triplet=d["triplet"], n_inliers=N, REr=d["REr"], sample=sample, res={})
         for m in methods:
             if (m > 6 and N < 8) or N < 7:                                                              # :117-122
                 out[m][row] = np.inf
                 continue
-            R2, R3, _, _, _ = METHODS[m][1](C0, CalM, device=device)                                    # :126
+            res = METHODS[m][1](C0, CalM, device=device)                                                # :126
+            R2, R3 = res[0], res[1]
             Ps = [CalM[0:3] @ np.eye(3, 4), CalM[3:6] @ R2, CalM[6:9] @ R3]
             rep = api.ReprError(Ps, inl, device=device)                                                 # :130-131
             r2, t2 = api.AngError(d["R_t0"][0], R2, device=device)
             r3, t3 = api.AngError(d["R_t0"][1], R3, device=device)
             out[m][row] = [rep, (r2 + r3) / 2, (t2 + t3) / 2]                                           # :133-136
+            rec["res"][m] = res
+        if details is not None:
+            details.append(rec)
     return out

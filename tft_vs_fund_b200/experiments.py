@@ -7,7 +7,7 @@ loop collapses into one batched call per method and rank; the accumulation is a 
 gathered and added in rank order (tft_vs_fund_b200.sharding)."""
 import numpy as np
 
-from . import api, scene, sharding
+from . import _lib, api, scene, sharding
 
 NOISE_LEVELS = np.arange(0.0, 3.0 + 1e-9, 0.25)          # experiments.m:40  interval=0:0.25:3
 METHODS = {1: ("Linear TFT", api.LinearTFTPoseEstimation), 7: ("Linear F", api.LinearFPoseEstimation),
@@ -22,12 +22,18 @@ def evaluate(res, R_t0, device=None):
     return np.asarray(res.repr_err).reshape(B), (r2 + r3) / 2.0, (t2 + t3) / 2.0
 
 
-def level_sums(level_idx, n_levels, *columns):
-    """Sum each per-trial column per noise level -> (n_levels, len(columns)+1) with the count last."""
-    out = np.zeros((n_levels, len(columns) + 1))
+def level_sums(level_idx, n_levels, *columns, bad=None):
+    """Sum each per-trial column per level -> (n_levels, len(columns)+2): sums, trials counted, trials skipped.
+    `bad` (bool per trial): trials without a pose (status NO_POSE / NONFINITE) -- the reference would stop there on
+    the undefined R_f; both sweep drivers leave them out of the sums and report their number per level (the same
+    policy as sweep_eval_accumulate_kernel)."""
+    level_idx = np.asarray(level_idx)
+    good = np.ones(level_idx.shape, dtype=bool) if bad is None else ~np.asarray(bad, dtype=bool)
+    out = np.zeros((n_levels, len(columns) + 2))
     for k, col in enumerate(columns):
-        out[:, k] = np.bincount(level_idx, weights=col, minlength=n_levels)
-    out[:, -1] = np.bincount(level_idx, minlength=n_levels)
+        out[:, k] = np.bincount(level_idx[good], weights=np.asarray(col)[good], minlength=n_levels)
+    out[:, -2] = np.bincount(level_idx[good], minlength=n_levels)
+    out[:, -1] = np.bincount(level_idx[~good], minlength=n_levels)
     return out
 
 
@@ -43,22 +49,27 @@ def run_sweep(total_trials, n=20, methods=(1, 7), noise_levels=NOISE_LEVELS, foc
     L = len(noise_levels)
     level_idx = (np.arange(lo, hi) % L).astype(np.int64)
     out = {}
+    skipped = {}
     for m in methods:
+        bad = None
         if solver is not None:
             repr_err, rot_err, t_err = solver(m, d["Corresp"], d["CalM"], d["R_t0"])
         else:
             res = METHODS[m][1](d["Corresp"], d["CalM"], device=device)
             repr_err, rot_err, t_err = evaluate(res, d["R_t0"], device=device)
-        total = sharding.sum_in_rank_order(level_sums(level_idx, L, repr_err, rot_err, t_err))
+            bad = (np.asarray(res.status) & (_lib.ST_NO_POSE_2 | _lib.ST_NO_POSE_3 | _lib.ST_NONFINITE)) != 0
+        total = sharding.sum_in_rank_order(level_sums(level_idx, L, repr_err, rot_err, t_err, bad=bad))
         if total is not None:
             out[m] = total[:, :3] / total[:, 3:4]
+            skipped[m] = total[:, 4].astype(np.int64)
+    if rank == 0:
+        run_sweep.last_skipped = skipped        # trials without a pose per (method, level); all zero in the reference's sweeps
     return out if rank == 0 else None
 
 
 def run_sweep_device(total_trials, n=20, methods=(1, 7), noise_levels=NOISE_LEVELS, focalL=50, angle=0, device=None):
     """run_sweep with everything on the device (tvf_sweep_run): trials are generated, solved and reduced per
     noise level in HBM; each rank moves one L x 5 table.  Per-rank sums are added in rank order on rank 0."""
-    from . import _lib
     rank, size = sharding.world()
     lo, hi = sharding.shard_range(total_trials, rank, size)
     noise_levels = np.ascontiguousarray(noise_levels, dtype=np.float64)
@@ -70,6 +81,7 @@ def run_sweep_device(total_trials, n=20, methods=(1, 7), noise_levels=NOISE_LEVE
     h = _lib.handle(device)
     dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
     out = {}
+    skipped = {}
     for m in methods:
         table = np.zeros((L, 5))
         h.call("tvf_sweep_run", int(m), lo, hi - lo, n, dp(noise_levels), L, dp(P), 36 * scene.PIX, 24 * scene.PIX,
@@ -77,4 +89,7 @@ def run_sweep_device(total_trials, n=20, methods=(1, 7), noise_levels=NOISE_LEVE
         total = sharding.sum_in_rank_order(table)
         if total is not None:
             out[m] = total[:, :3] / total[:, 3:4]
+            skipped[m] = total[:, 4].astype(np.int64)
+    if rank == 0:
+        run_sweep_device.last_skipped = skipped
     return out if rank == 0 else None

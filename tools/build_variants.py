@@ -1,7 +1,9 @@
 """Development tool: build compile-time variants of libtvf.so into tools/_build/variants/ so that ONE GPU call can
-time them all (TVF_LIBPATH selects the library bench.py loads).  Not part of the product build."""
+time them all (TVF_LIBPATH selects the library bench.py loads).  Not part of the product build.
+
+    python tools/build_variants.py name=-DFLAG=1,-DOTHER=2 name2=...
+"""
 import os
-import subprocess
 import sys
 from concurrent.futures import ThreadPoolExecutor
 
@@ -9,23 +11,23 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from tft_vs_fund_b200 import build as B   # noqa: E402
 
-VARIANTS = {
-    "base": [],
-    "nopipe": ["-DTVF_GJ_PIPE=0"],
-}
+OUT = os.path.join(ROOT, "tools", "_build", "variants")
 
 
-def build_one(name):
-    out = os.path.join(ROOT, "tools", "_build", "variants", "libtvf_%s.so" % name)
-    os.makedirs(os.path.dirname(out), exist_ok=True)
-    cmd = [B._nvcc()] + [f for f in B.NVCC_FLAGS if f != "-Xptxas=-v"] + VARIANTS[name] + ["-I", B.CSRC, "-o", out] + \
-        [os.path.join(B.CSRC, f) for f in B.SOURCES]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    return name, res.returncode, (res.stdout + res.stderr)[-2000:]
+def build_one(spec):
+    name, _, flags = spec.partition("=")
+    defines = [f for f in flags.split(",") if f]
+    out = os.path.join(OUT, "libtvf_%s.so" % name)
+    os.makedirs(OUT, exist_ok=True)
+    try:
+        B.build(force=True, defines=defines, out=out)
+        return name, "ok"
+    except Exception as e:
+        return name, "FAILED: %s" % e
 
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(VARIANTS)
-    with ThreadPoolExecutor(4) as ex:
-        for name, rc, log in ex.map(build_one, names):
-            print(name, "ok" if rc == 0 else "FAILED\n" + log)
+    specs = sys.argv[1:] or ["base="]
+    with ThreadPoolExecutor(3) as ex:
+        for name, msg in ex.map(build_one, specs):
+            print(name, msg)
