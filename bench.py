@@ -46,7 +46,8 @@ def pose_bytes(n):
 def kernel_flops(n):
     """App. B.1 rows attributed to the kernels of the TFT method (sums to tft_flops(n))."""
     return {
-        "tft_stage1_kernel": 5909 * n + 216513,  # normalise x3, design matrix, null vector of A (4n x 27)
+        "tft_stage1_kernel": 77 * n,             # normalise x3 + design matrix (the moments half of the split stage 1)
+        "tft_stage1_solve_kernel": 5832 * n + 216513,  # null vector of A (4n x 27) (the solve half)
         "tft_epipoles_kernel": 2592,             # 8 svd3 (linearTFT.m:71-79)
         "tft_stage2_kernel": 5040 * n + 214000,  # svd(E), A*Up, its null vector, Up*tp, a; undo normalisation
         "candidates_kernel": 4922,               # de-calibrate, 8 svd3, E21/E31, 2 x svd(E) -> R, Rp, t
@@ -329,11 +330,16 @@ def run_gpu(args, rank, local_rank, world):
     launches = lib.tvf_launch_count(h._h) - l0
     clocks = sampler.stop() if sampler else None
     flagged = int(torch.count_nonzero(d_st).item())
+    flagged_detail = None
+    if flagged:
+        idxs = torch.nonzero(d_st).reshape(-1)[:8].cpu().numpy()
+        flagged_detail = [{"trial": int(rank * B + i), "status": int(d_st[int(i)].item())} for i in idxs]
     value = world * B * args.steps / (ms * 1e-3)
     rep_device_path = d_rep.cpu().numpy()
 
     full = args.legs == "all"
     f_value = ms_f = optf_value = ms_o = optf_iters = e2e_value = e2e_check = sweep_value = None
+    e2e_variants = link = shard_check = e2e_pageable_check = None
     optf_steps = e2e_steps = 0
     gh_ms = (float("nan"), 1)
     h2d = B * n * 6 * 8 + 27 * 8
@@ -355,7 +361,11 @@ def run_gpu(args, rank, local_rank, world):
         optf_iters = float(d_iter.double().mean().item())
         gh_ms = prof_o.get("optimf_gh_kernel", (float("nan"), 1)) if prof_o else (float("nan"), 1)
 
-        # 5. end to end through the host-pointer C ABI: pinned host buffers, H2D + kernels + D2H inside the timed region
+        # 5. end to end through the host-pointer C ABI: host buffers, H2D + kernels + D2H inside the timed region.
+        #    Headline `e2e`: pinned buffers (tvf_host_alloc), every output of the reference signature.  Beside it:
+        #    `lean` (Reconst and T not requested -- the ABI takes NULL; 204 B instead of 900 B back per solve),
+        #    `pageable` (plain malloc'ed buffers, what a MEX caller's mxArrays are) and `registered` (the same pageable
+        #    buffers page-locked by tvf_set_host_register for the duration of each call).
         lib.tvf_host_alloc.restype = C.c_void_p
 
         def pinned(shape, dtype=np.float64):
@@ -370,32 +380,110 @@ def run_gpu(args, rank, local_rank, world):
         h_calm = np.ascontiguousarray(CalM.T)
         h_Rt2, p1 = pinned((B, 12)); h_Rt3, p2 = pinned((B, 12)); h_rec, p3 = pinned((B, 3 * n))
         h_T, p4 = pinned((B, 27)); h_rep, p5 = pinned((B,)); h_st, p6 = pinned((B,), np.int32)
-        dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
+        dp = lambda a: a.ctypes.data_as(_lib.c_double_p) if a is not None else None
 
-        def step_e2e():
-            return h.call("tvf_linear_tft_pose", dp(h_in), dp(h_calm), 0, n, B, dp(h_Rt2), dp(h_Rt3), dp(h_rec), dp(h_T),
-                          dp(h_rep), h_st.ctypes.data_as(_lib.c_int32_p))
+        def make_step(bufs, lean):
+            i_, r2_, r3_, rec_, T_, rep_, st_ = bufs
+            def step():
+                return h.call("tvf_linear_tft_pose", dp(i_), dp(h_calm), 0, n, B, dp(r2_), dp(r3_), None if lean else dp(rec_),
+                              None if lean else dp(T_), dp(rep_), st_.ctypes.data_as(_lib.c_int32_p))
+            return step
 
-        for _ in range(2):
-            step_e2e()
+        def time_e2e(step, steps):
+            for _ in range(2):
+                step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                step()
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            barrier()
+            return world * B * steps / dt
+
+        pinned_bufs = (h_in, h_Rt2, h_Rt3, h_rec, h_T, h_rep, h_st)
         e2e_steps = max(3, min(args.steps, 10))
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            step_e2e()
-        torch.cuda.synchronize(dev)
-        dt = time.perf_counter() - t0
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
-        barrier()
-        e2e_value = world * B * e2e_steps / dt
+        e2e_value = time_e2e(make_step(pinned_bufs, False), e2e_steps)
         e2e_check = float(np.abs(h_rep - rep_device_path).max())       # host path and device path agree bit for bit
         h2d = B * n * 6 * 8 + 27 * 8
         d2h = B * (12 + 12 + 3 * n + 27 + 1) * 8 + B * 4
+        e2e_variants = {"pinned_all_outputs": {"value": e2e_value, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}}
+        e2e_variants["pinned_lean"] = {"value": time_e2e(make_step(pinned_bufs, True), e2e_steps), "h2d_bytes_per_step": h2d,
+                                       "d2h_bytes_per_step": B * (12 + 12 + 1) * 8 + B * 4,
+                                       "note": "Reconst and T not requested (NULL): R_t_2, R_t_3, repr_err, status only"}
+        # pageable buffers (np.empty): a MEX caller's situation
+        pg = (corresp_host.copy(), np.empty((B, 12)), np.empty((B, 12)), np.empty((B, 3 * n)), np.empty((B, 27)), np.empty(B),
+              np.zeros(B, dtype=np.int32))
+        steps_pg = max(2, min(args.steps, 4))
+        e2e_variants["pageable"] = {"value": time_e2e(make_step(pg, False), steps_pg), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                    "note": "np.empty buffers: the CUDA runtime stages every copy through its own pinned buffer"}
+        e2e_pageable_check = float(np.abs(pg[5] - rep_device_path).max())
+        h.call("tvf_set_host_register", 1)
+        e2e_variants["pageable_registered_per_call"] = {
+            "value": time_e2e(make_step(pg, False), steps_pg), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "note": "same buffers, page-locked by cudaHostRegister inside every call and released before it returns (TVF_HOST_REGISTER=1 in the MEX gateways)"}
+        h.call("tvf_set_host_register", 0)
+        del pg
+
+        # 5a. what the host link allows: pinned H2D of the input volume and D2H of the output volume at once, all ranks
+        #     together (the e2e path is bound by this, not by the kernels)
+        def link_ceiling(nin_bytes, nout_bytes):
+            d_i = torch.empty(nin_bytes // 8, dtype=torch.float64, device=dev); d_o = torch.ones(nout_bytes // 8, dtype=torch.float64, device=dev)
+            hin = torch.from_numpy(h_in.reshape(-1)[: nin_bytes // 8]); hout = torch.from_numpy(h_rec.reshape(-1)[: nout_bytes // 8])
+            s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            def once():
+                with torch.cuda.stream(s1):
+                    d_i.copy_(hin, non_blocking=True)
+                with torch.cuda.stream(s2):
+                    hout.copy_(d_o, non_blocking=True)
+                s1.synchronize(); s2.synchronize()
+            once(); barrier()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                once()
+            dt = (time.perf_counter() - t0) / 3
+            if world > 1:
+                t = torch.tensor([dt], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dt = float(t.item())
+            barrier()
+            return dt
+        # the copies use the pinned input buffer and the pinned Reconst buffer as host ends (sizes clipped to them)
+        nin_b = B * n * 48; nout_b = min(B * 3 * n * 8, d2h)
+        t_link = link_ceiling(nin_b, nout_b)
+        link = {"h2d_gbs_per_gpu": nin_b / t_link / 1e9, "d2h_gbs_per_gpu": nout_b / t_link / 1e9, "seconds": t_link,
+                "aggregate_bidirectional_gbs": world * (nin_b + nout_b) / t_link / 1e9,
+                "note": "pinned H2D of %d MB and D2H of %d MB issued together on every rank at once, wall clock, max over ranks" % (nin_b // 10**6, nout_b // 10**6)}
+        # time the link needs for one step's volumes at those rates -> ceiling of the e2e figures
+        for k_, v_ in e2e_variants.items():
+            t_need = max(v_["h2d_bytes_per_step"] / (link["h2d_gbs_per_gpu"] * 1e9), v_["d2h_bytes_per_step"] / (link["d2h_gbs_per_gpu"] * 1e9))
+            v_["link_ceiling"] = world * B / t_need
+            v_["frac_of_link_ceiling"] = v_["value"] / v_["link_ceiling"]
         for p in (p0, p1, p2, p3, p4, p5, p6):
             lib.tvf_host_free(C.c_void_p(p))
+
+        # 5c. N > 1: shards == single device, checked on the hardware.  Rank 0 re-solves the first K trials of rank 1's
+        #     shard on its own GPU and compares them bit for bit with what rank 1 computed.
+        if world > 1:
+            Kc = min(B, 65536)
+            mine = torch.cat([d_Rt2[:Kc].reshape(-1), d_Rt3[:Kc].reshape(-1), d_T[:Kc].reshape(-1), d_rep[:Kc]]).clone()
+            gathered = [torch.empty_like(mine) for _ in range(world)] if rank == 0 else None
+            dist.gather(mine, gathered, dst=0)
+            if rank == 0:
+                tmp_c = torch.empty((Kc, n, 6), dtype=torch.float64, device=dev)
+                scene.sweep_batch_device(Kc, n, first_trial=1 * B, device=local_rank, out_ptr=tmp_c.data_ptr(), meta=False)
+                r2 = torch.empty((Kc, 12), dtype=torch.float64, device=dev); r3 = torch.empty_like(r2)
+                tT = torch.empty((Kc, 27), dtype=torch.float64, device=dev); tr = torch.empty((Kc,), dtype=torch.float64, device=dev)
+                ts = torch.zeros((Kc,), dtype=torch.int32, device=dev)
+                h.call("tvf_linear_tft_pose_dev", ptr(tmp_c), ptr(d_calm), 0, n, Kc, ptr(r2), ptr(r3), None, ptr(tT), ptr(tr), ptr(ts))
+                h.call("tvf_synchronize"); torch.cuda.synchronize(dev)
+                ref = torch.cat([r2.reshape(-1), r3.reshape(-1), tT.reshape(-1), tr])
+                shard_check = {"trials": int(Kc), "of_rank": 1, "recomputed_on_rank": 0,
+                               "bitwise_equal": bool(torch.equal(ref.view(torch.int64), gathered[1].view(torch.int64)))}
 
         # 5b. the whole inner loop of experiments.m device-resident (generate + solve + per-level reduction; only a
         #     13 x 5 table crosses the bus): tvf_sweep_run
@@ -417,6 +505,14 @@ def run_gpu(args, rank, local_rank, world):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt_sweep = float(t.item())
         sweep_value = world * B * 3 / dt_sweep
+
+    # 5d. BASELINE config 5 inside the default line: 8 192 scenes x n = 10 000 (3.9 GB of input), single GPU
+    large_n_block = None
+    if full and rank == 0 and world == 1 and args.large_n_scenes > 0:
+        try:
+            large_n_block = large_n_measure(h, lib, local_rank, args.large_n_scenes, 10000, 3, 1)
+        except Exception as e:                                      # never lose the headline over the extra block
+            large_n_block = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -481,7 +577,11 @@ def run_gpu(args, rank, local_rank, world):
         "cpu_baseline": cpu_baseline,
         "e2e": ({"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                  "steps": e2e_steps, "max_abs_diff_vs_device_path": e2e_check,
-                 "api": "tvf_linear_tft_pose (host pointers, pinned; chunked H2D/compute/D2H over 3 streams)"} if full else None),
+                 "api": "tvf_linear_tft_pose (host pointers, pinned; chunked H2D/compute/D2H over 3 streams)",
+                 "link_ceiling": e2e_variants["pinned_all_outputs"]["link_ceiling"],
+                 "frac_of_link_ceiling": e2e_variants["pinned_all_outputs"]["frac_of_link_ceiling"]} if full else None),
+        "e2e_variants": e2e_variants, "host_link": link, "e2e_pageable_max_abs_diff_vs_device_path": e2e_pageable_check,
+        "shard_check": shard_check,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "f_method": ({"metric": "3-view linear F pose solves/sec (LinearFPoseEstimation + ReprError)", "value": f_value,
@@ -495,7 +595,8 @@ def run_gpu(args, rank, local_rank, world):
                                    "value": sweep_value, "unit": UNIT, "d2h_bytes_per_step": int(table.nbytes),
                                    "mean_repr_err_px_by_level": (table[:, 0] / np.maximum(table[:, 3], 1)).round(4).tolist()}
                                   if full else None),
-        "flagged_problems": flagged,
+        "flagged_problems": flagged, "flagged_detail": flagged_detail,
+        "large_n": large_n_block,
         "input_generation": {"where": "device (tvf_generate_sweep_dev, TVF scene RNG v2)", "seconds": t_gen, "seconds_warm": t_gen2, "trials_per_s_warm": B / t_gen2, "check": gen_check},
     }
     emit(line)
@@ -504,30 +605,42 @@ def run_gpu(args, rank, local_rank, world):
 
 
 # ---- BASELINE config 5: large-n triplets (HBM-oriented Gram formation) ------------------------------
-def run_large_n(args, local_rank):
-    """65 536 scenes x n = 10 000 correspondences (defaults: --trials 8192 to keep the default run short;
-    pass --trials 65536 for the full configuration).  Inputs are generated on the device with torch (scene
-    geometry of generateSyntheticScene, 1 px noise; no inside-image rejection) -- labelled in `data`."""
+def large_n_scenes(B, n, dev, seed=1):
+    """B scenes of generateSyntheticScene's geometry (f = 50, angle = 0), n points each, 1 px Gaussian noise, generated on
+    the device with torch.  Points whose noisy projections leave the 1800 x 1200 image in any view are re-drawn until every
+    point is inside (generateSyntheticScene.m:80-111 fills with fresh points in the same way; the random stream is
+    torch's, not the reference generator's -- labelled in `data`)."""
     import torch
-    from tft_vs_fund_b200 import scene, _lib
-    n, B = args.n, args.trials
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
+    from tft_vs_fund_b200 import scene
     K, Ps, R_t0 = scene.scene_cameras(50, 0)
-    CalM = np.tile(K, (3, 1))
-    g = torch.Generator(device=dev); g.manual_seed(1)
-    d_corresp = torch.empty((B, n, 6), dtype=torch.float64, device=dev)
+    g = torch.Generator(device=dev); g.manual_seed(seed)
     Pt = [torch.from_numpy(P).to(dev) for P in Ps]
-    step = max(1, (1 << 26) // n)
+    hi = torch.tensor([36 * scene.PIX, 24 * scene.PIX] * 3, dtype=torch.float64, device=dev)
+    out = torch.empty((B, n, 6), dtype=torch.float64, device=dev)
+    step = max(1, (1 << 25) // n)
     for lo in range(0, B, step):
-        hi = min(B, lo + step)
-        X = torch.rand((hi - lo, n, 3), dtype=torch.float64, device=dev, generator=g) * 400 - 200
-        for v in range(3):
-            x = X @ Pt[v][:, :3].T + Pt[v][:, 3]
-            d_corresp[lo:hi, :, 2 * v:2 * v + 2] = x[..., :2] / x[..., 2:3] + torch.randn((hi - lo, n, 2), dtype=torch.float64, device=dev, generator=g)
-        del X, x
-    h = _lib.Handle(local_rank)
-    lib = h.lib
+        hi_b = min(B, lo + step)
+        chunk = out[lo:hi_b].view(-1, 6)
+        todo = torch.arange(chunk.shape[0], device=dev)
+        while todo.numel() > 0:
+            X = torch.rand((todo.numel(), 3), dtype=torch.float64, device=dev, generator=g) * 400 - 200
+            c = torch.empty((todo.numel(), 6), dtype=torch.float64, device=dev)
+            for v in range(3):
+                x = X @ Pt[v][:, :3].T + Pt[v][:, 3]
+                c[:, 2 * v:2 * v + 2] = x[:, :2] / x[:, 2:3] + torch.randn((todo.numel(), 2), dtype=torch.float64, device=dev, generator=g)
+            ok = ((c >= 0) & (c <= hi)).all(dim=1)
+            chunk[todo[ok]] = c[ok]
+            todo = todo[~ok]
+    return out, np.tile(K, (3, 1))
+
+
+def large_n_measure(h, lib, local_rank, B, n, steps, warmup):
+    """Times LinearTFTPoseEstimation on B scenes of n points (device-resident) and returns the config-5 block: Gram
+    formation (tft_moments_large_kernel) against the HBM and FP64 roofs, and the full pipeline."""
+    import torch
+    from tft_vs_fund_b200 import _lib
+    dev = torch.device("cuda", local_rank)
+    d_corresp, CalM = large_n_scenes(B, n, dev)
     stream = torch.cuda.Stream(device=dev)
     h.call("tvf_set_stream", C.c_void_p(stream.cuda_stream))
     d_calm = torch.from_numpy(np.ascontiguousarray(CalM.T)).to(dev)
@@ -541,20 +654,17 @@ def run_large_n(args, local_rank):
         h.call("tvf_linear_tft_pose_dev", ptr(d_corresp), ptr(d_calm), 0, n, B, ptr(d_Rt2), ptr(d_Rt3), ptr(d_rec),
                ptr(d_T), ptr(d_rep), ptr(d_st))
 
-    for _ in range(max(1, args.warmup)):
+    for _ in range(max(1, warmup)):
         step_fn()
     torch.cuda.synchronize(dev)
     h.call("tvf_profile_reset"); h.call("tvf_profile_enable", 1)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    steps = max(1, min(args.steps, 5))
-    sampler = ClockSampler(local_rank)
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(steps):
             step_fn()
         e1.record(stream)
     torch.cuda.synchronize(dev)
-    clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     tot = (C.c_double * _lib.NUM_KERNELS)(); cnt = (C.c_int64 * _lib.NUM_KERNELS)()
     h.call("tvf_profile_read", tot, cnt); h.call("tvf_profile_enable", 0)
@@ -569,27 +679,51 @@ def run_large_n(args, local_rank):
     c5 = ncu_counters().get("tft_moments_large_kernel")
     gram_traffic = (c5["dram_bytes_per_launch"] * scenes_per_launch / c5["problems_per_launch"]
                     if c5 and c5.get("dram_bytes_per_launch") and n == 10000 else None)
-    line = {
+    flop_exec = (c5["fp64_flop_per_launch"] / c5["problems_per_launch"]) if c5 and c5.get("fp64_flop_per_launch") and n == 10000 else None
+    block = {
         "metric": "large-n linearTFT Gram formation (normalisation + 96 moments), scenes/s", "unit": "scenes/s",
-        "value": scenes_per_launch / gram_s, "n_gpus": 1, "steps": steps, "warmup": max(1, args.warmup),
-        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic (device-generated scenes of generateSyntheticScene's geometry, 1 px noise, no inside-image rejection)",
-        "config": {"workload": "large-n triplets: %d correspondences per scene x %d scenes (BASELINE config 5)" % (n, B),
+        "value": scenes_per_launch / gram_s, "steps": steps, "ms_per_step": ms / steps,
+        "data": "synthetic (device-generated scenes of generateSyntheticScene's geometry, 1 px noise, out-of-image points re-drawn; torch RNG)",
+        "config": {"workload": "large-n triplets: %d correspondences per scene x %d scenes (BASELINE config 5%s)"
+                               % (n, B, "" if B >= 65536 else "; 65536 scenes with --workload large-n --trials 65536"),
                    "n_points": n, "scenes": B, "cache": "%.1f GB of input per step, far beyond L2" % (B * n * 48 / 1e9)},
         "roofline": {"bound": "hbm", "kernel": "tft_moments_large_kernel", "achieved": gram_bytes / gram_s / 1e9,
                      "peak": hbm_peak, "unit": "GB/s", "frac": gram_bytes / gram_s / 1e9 / hbm_peak, "traffic": gram_traffic,
                      "traffic_note": "dram__bytes_read+write of this kernel from the committed ncu --set full capture (n = 10000), scaled to this launch size",
                      "fp64_pipe_active_pct_ncu": (c5["fp64_pipe_active_pct"] if c5 else None),
                      "work_model": "48*n+216 algorithmic bytes per scene (SURVEY.md 8d)"},
-        "roofline_fp64": {"bound": "fp64", "achieved": 624.0 * n * scenes_per_launch / gram_s / 1e12, "peak": fp64_peak,
-                          "unit": "TFLOP/s", "frac": 624.0 * n * scenes_per_launch / gram_s / 1e12 / fp64_peak,
-                          "work_model": "624*n algorithmic flop per scene (12-nnz rows, symmetric half; SURVEY.md B.3)"},
+        "roofline_fp64": {"bound": "fp64", "peak": fp64_peak, "unit": "TFLOP/s",
+                          "achieved_executed": (flop_exec * scenes_per_launch / gram_s / 1e12 if flop_exec else None),
+                          "frac_executed": (flop_exec * scenes_per_launch / gram_s / 1e12 / fp64_peak if flop_exec else None),
+                          "algorithmic": 624.0 * n * scenes_per_launch / gram_s / 1e12,
+                          "algorithmic_vs_peak": 624.0 * n * scenes_per_launch / gram_s / 1e12 / fp64_peak,
+                          "work_model": "executed = DFMA*2 + DMUL + DADD thread instructions of the ncu capture; algorithmic = 624*n flop per scene "
+                                        "(12-nnz rows, symmetric half; SURVEY.md B.3)"},
         "full_pipeline": {"metric": "LinearTFTPoseEstimation + ReprError solves/s at n=%d" % n, "value": B * steps / (ms * 1e-3),
-                          "unit": "solves/s", "fp64_frac_algorithmic": tft_flops(n) * B * steps / (ms * 1e-3) / 1e12 / fp64_peak},
+                          "unit": "solves/s"},
         "kernels": {k: {"ms_total": v[0], "launches": int(v[1])} for k, v in prof.items()},
-        "flagged_problems": int(torch.count_nonzero(d_st).item()), "clocks": clocks,
+        "flagged_problems": int(torch.count_nonzero(d_st).item()),
         "gpu_launches": int(sum(v[1] for v in prof.values())),
     }
+    del d_corresp, d_rec
+    torch.cuda.empty_cache()
+    return block
+
+
+def run_large_n(args, local_rank):
+    """65 536 scenes x n = 10 000 correspondences as its own bench line (`--workload large-n --n 10000 --trials 65536`);
+    the default run carries the same measurement on 8 192 scenes in its `large_n` block."""
+    import torch
+    from tft_vs_fund_b200 import _lib
+    torch.cuda.set_device(local_rank)
+    h = _lib.Handle(local_rank)
+    sampler = ClockSampler(local_rank)
+    blk = large_n_measure(h, h.lib, local_rank, args.trials, args.n, max(1, min(args.steps, 5)), max(1, args.warmup))
+    clocks = sampler.stop()
+    line = {"metric": blk["metric"], "unit": blk["unit"], "value": blk["value"], "n_gpus": 1, "steps": blk["steps"],
+            "warmup": max(1, args.warmup), "ms_per_step": blk["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "clocks": clocks}
+    line.update({k: v for k, v in blk.items() if k not in line})
     emit(line)
 
 
@@ -628,6 +762,8 @@ def main():
     ap.add_argument("--legs", default="all", choices=["all", "headline"],
                     help="headline = only the device-resident TFT step (what `value` times): used for the ncu launch list, so "
                          "that the list holds the kernels of the step and nothing else")
+    ap.add_argument("--large-n-scenes", type=int, default=8192,
+                    help="scenes of the config-5 block inside the default line (n = 10000; 0 = skip; N = 1 only)")
     ap.add_argument("--workload", default="sweep", choices=["sweep", "large-n"],
                     help="sweep = BASELINE config 3/4 (headline); large-n = config 5 (use with --n 10000 --trials 65536)")
     args = ap.parse_args()

@@ -215,6 +215,24 @@ int tvf_sweep_run(tvf_handle_t h, int method, int64_t first_trial, int64_t B, in
                   const double* P, double hi_x, double hi_y, const double* calm, const double* Rt0_2, const double* Rt0_3,
                   double* table);
 
+/* The same loop for any of the four experiments of experiments.m:23-47 ('noise', 'focal', 'points', 'angle'): level l of
+ * the swept variable has its own noise, point count N, cameras (focal length / collinearity change K, the centres and
+ * the ground truth: generateSyntheticScene.m:45-72,113), CalM and ground-truth poses.  Trial j of [first_trial,
+ * first_trial + B) is level j mod L with seed j div L + 1, exactly as in tvf_sweep_run.  table: L x 5 as above; a level
+ * the reference skips for lack of matches ((m > 6 && N < 8) || N < 7, experiments.m:99-104) gets +inf sums and count 0.
+ * P row-major (as tvf_generate_sweep); calm 9x3 and Rt0_* 3x4 column-major. */
+typedef struct tvf_sweep_level {
+    double noise;
+    int32_t n;
+    int32_t reserved;
+    double P[36];
+    double calm[27];
+    double Rt0_2[12];
+    double Rt0_3[12];
+} tvf_sweep_level;
+int tvf_sweep_run_levels(tvf_handle_t h, int method, int64_t first_trial, int64_t B, const tvf_sweep_level* levels, int L,
+                         double hi_x, double hi_y, double* table);
+
 /* ---- device-pointer forms (inputs/outputs already in HBM; asynchronous on the handle's stream,
  *      return 0 without synchronising -- read `status` after tvf_synchronize) ----------------- */
 int tvf_linear_tft_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,

@@ -300,3 +300,69 @@ def test_sharded_device_resident_sweep_equals_unsharded(tvf):
     parts = run(0, half) + run(half, B - half)
     assert np.array_equal(whole[:, 3:], parts[:, 3:])
     assert np.max(np.abs(whole[:, :3] - parts[:, :3]) / np.abs(whole[:, :3])) < 1e-12
+
+
+# -------------------------------------------------------- the other experiments, device-resident (tvf_sweep_run_levels)
+@pytest.mark.parametrize("option", ["noise", "focal", "points", "angle"])
+def test_device_resident_experiment_equals_host_driven_and_oracle(tvf, option):
+    """experiments.m:23-47 with every `option`, generated + solved + reduced on the device (tvf_sweep_run_levels: per
+    level its own noise, N, cameras, CalM, ground truth) == the host-driven twin (inputs from the host generator, one
+    batched call per level, NumPy reduction), and == the same loop written with the oracle on two levels."""
+    from tft_vs_fund_b200 import experiments
+    n_sim = 6
+    interval, dev = experiments.run_experiment(option, n_sim=n_sim, methods=(1, 7, 8))
+    interval_h, host = experiments.run_experiment_host(option, n_sim=n_sim, methods=(1, 7, 8))
+    assert list(interval) == list(interval_h) == list(experiments.INTERVALS[option])
+    for m in (1, 7, 8):
+        assert dev[m].shape == (len(interval), 3)
+        fin = np.isfinite(host[m][:, 0])
+        assert np.array_equal(fin, np.isfinite(dev[m][:, 0]))            # the same levels are skipped (N < 8 for methods 7, 8)
+        assert np.max(np.abs(dev[m][fin, 0] - host[m][fin, 0])) < 1e-7                                    # px
+        assert np.max(np.abs(dev[m][fin, 1:] - host[m][fin, 1:])) < 1e-5                                  # degrees
+    if option == "points":
+        assert np.all(np.isinf(dev[7][0])) and np.all(np.isinf(dev[8][0])) and np.all(np.isfinite(dev[1][0]))   # N = 7
+    assert all(int(v.sum()) == 0 for v in experiments.run_experiment.last_skipped.values())
+    # the oracle's version of the loop (experiments.m:91-124) on the first and the last level
+    _, params = experiments.experiment_levels(option)
+    for lv in (0, len(params) - 1):
+        p = params[lv]
+        acc = {1: np.zeros(3), 7: np.zeros(3)}
+        for it in range(1, n_sim + 1):
+            CalM, R_t0, C, _ = o.experiments_subsample(p["N"], p["noise"], it, p["f"], p["angle"])
+            K = CalM[:3]
+            for m, fn in ((1, o.LinearTFTPoseEstimation), (7, o.LinearFPoseEstimation)):
+                if m == 7 and p["N"] < 8:
+                    continue
+                R2, R3, Rec, _, _ = fn(C, CalM)
+                r2, t2 = o.AngError(R_t0[0], R2); r3, t3 = o.AngError(R_t0[1], R3)
+                acc[m] += np.array([o.ReprError([K @ np.eye(3, 4), K @ R2, K @ R3], C, Rec), (r2 + r3) / 2, (t2 + t3) / 2]) / n_sim
+        for m in (1, 7):
+            if m == 7 and p["N"] < 8:
+                continue
+            assert abs(dev[m][lv, 0] - acc[m][0]) < 1e-7 and np.max(np.abs(dev[m][lv, 1:] - acc[m][1:])) < 1e-4, (option, lv, m)
+
+
+def test_device_resident_experiment_sharded_ranges(tvf):
+    """tvf_sweep_run_levels over [0, B) == the sum of two ranges that cut through a seed's levels."""
+    from tft_vs_fund_b200 import experiments, _lib, scene
+    import ctypes as C
+    _, params = experiments.experiment_levels("focal")
+    L = len(params)
+    levels = (_lib.SweepLevel * L)()
+    for lv, p in zip(levels, params):
+        K, Ps, R_t0 = scene.scene_cameras(p["f"], p["angle"])
+        lv.noise, lv.n = p["noise"], p["N"]
+        lv.P[:] = np.ascontiguousarray(np.stack(Ps)).ravel(); lv.calm[:] = np.tile(K, (3, 1)).T.ravel()
+        lv.Rt0_2[:] = R_t0[0].T.ravel(); lv.Rt0_3[:] = R_t0[1].T.ravel()
+    h = _lib.handle(0)
+
+    def run(first, count):
+        t = np.zeros((L, 5))
+        h.call("tvf_sweep_run_levels", 1, first, count, levels, L, 1800.0, 1200.0, t.ctypes.data_as(_lib.c_double_p))
+        return t
+    B = L * 40 + 7
+    whole = run(0, B)
+    cut = L * 17 + 4
+    parts = run(0, cut) + run(cut, B - cut)
+    assert np.array_equal(whole[:, 3:], parts[:, 3:]) and int(whole[:, 3].sum()) == B
+    assert np.max(np.abs(whole[:, :3] - parts[:, :3]) / np.abs(whole[:, :3])) < 1e-12

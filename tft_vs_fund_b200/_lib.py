@@ -34,6 +34,12 @@ class PoseOut(C.Structure):
     _fields_ = [(k, C.c_void_p) for k in ("Rt2", "Rt3", "reconst", "T", "repr_err", "F21", "F31", "iter", "votes", "status")]
 
 
+class SweepLevel(C.Structure):
+    """tvf_sweep_level of include/tvf.h: one value of the swept variable of experiments.m:38-47."""
+    _fields_ = [("noise", C.c_double), ("n", C.c_int32), ("reserved", C.c_int32), ("P", C.c_double * 36),
+                ("calm", C.c_double * 27), ("Rt0_2", C.c_double * 12), ("Rt0_3", C.c_double * 12)]
+
+
 METHOD_IDS = {"tft": 1, "f": 7, "optf": 8}      # numbering of experiments.m:51-59
 
 # name -> (restype, argtypes); mirrors include/tvf.h one to one
@@ -78,6 +84,7 @@ SIGNATURES = {
     "tvf_project3d": (_I, [_H, _D, _D, _I, _I, _I, _L, _D]),
     "tvf_generate_sweep": (_I, [_H, _L, _L, _I, _D, _I, _D, C.c_double, C.c_double, _D]),
     "tvf_sweep_run": (_I, [_H, _I, _L, _L, _I, _D, _I, _D, C.c_double, C.c_double, _D, _D, _D, _D]),
+    "tvf_sweep_run_levels": (_I, [_H, _I, _L, _L, C.POINTER(SweepLevel), _I, C.c_double, C.c_double, _D]),
     "tvf_generate_sweep_dev": (_I, [_H, _L, _L, _I, _D, _I, _D, C.c_double, C.c_double, C.c_void_p]),
     "tvf_linear_tft_pose_dev": (_I, [_H, C.c_void_p, C.c_void_p, _I, _I, _L] + [C.c_void_p] * 6),
     "tvf_linear_f_pose_dev": (_I, [_H, C.c_void_p, C.c_void_p, _I, _I, _L] + [C.c_void_p] * 8),

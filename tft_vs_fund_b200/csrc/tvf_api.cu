@@ -28,7 +28,7 @@ namespace {
 #define TVF_RAMP 0
 #endif
 constexpr int NSLOT = TVF_NSLOT;
-constexpr int NSCRATCH = 16;
+constexpr int NSCRATCH = 24;
 constexpr int64_t DEFAULT_CHUNK = 65536;        // host-pointer entry points: chunks are the H2D / kernels / D2H pipeline stages
 constexpr int64_t DEFAULT_CHUNK_DEV = 524288;   // device-pointer entry points: fewer, larger launches (less launch and wave-tail
                                                 // overhead: +8 % at n = 20, profiles/r01_variants.md); the 1.2 GB of work space no
@@ -212,8 +212,12 @@ int run_pose_chunk(tvf_handle_t h, cudaStream_t st, Method method, const double*
             if (large_done)
                 timed_launch(h, TVF_K_TFT_STAGE1_SOLVE, st, [&] { launch_tft_stage1_solve(Bc, d_core, d_status, sm, st); });
         }
-        if (!large_done)
-            timed_launch(h, TVF_K_TFT_STAGE1, st, [&] { launch_tft_stage1(in, d_core, d_status, sm, st); });
+        if (!large_done) {
+            int need_solve = 0;
+            timed_launch(h, TVF_K_TFT_STAGE1, st, [&] { need_solve = launch_tft_stage1(in, d_core, d_status, sm, st); });
+            if (need_solve)
+                timed_launch(h, TVF_K_TFT_STAGE1_SOLVE, st, [&] { launch_tft_stage1_solve(Bc, d_core, d_status, sm, st); });
+        }
         timed_launch(h, TVF_K_TFT_EPIPOLES, st, [&] { launch_tft_epipoles(d_core, Bc, st); });
         timed_launch(h, TVF_K_TFT_STAGE2, st, [&] { launch_tft_stage2(in, d_core, d_T, nullptr, nullptr, d_status, sm, st); });
         timed_launch(h, TVF_K_CANDIDATES, st, [&] { launch_candidates(0, d_T, a, st); });
@@ -784,7 +788,7 @@ int tvf_linear_tft(tvf_handle_t h, const double* p1, const double* p2, const dou
     int* dst = u.out<int>((size_t)B);
     double* dws = u.out<double>((size_t)CORE_WS_TFT * B);
     if (u.rc) return u.rc;
-    launch_tft_stage1(in, dws, dst, h->sm_count, u.st);
+    if (launch_tft_stage1(in, dws, dst, h->sm_count, u.st)) { launch_tft_stage1_solve(B, dws, dst, h->sm_count, u.st); h->launches += 1; }
     launch_tft_epipoles(dws, B, u.st);
     launch_tft_stage2(in, dws, dT, dP2, dP3, dst, h->sm_count, u.st);
     h->launches += 3;
@@ -1103,6 +1107,81 @@ int tvf_sweep_run(tvf_handle_t h, int method, int64_t first_trial, int64_t B, in
     TVF_CK(cudaGetLastError());
     TVF_CK(cudaMemcpyAsync(table, pt, (size_t)L * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
     TVF_CK(cudaStreamSynchronize(st));
+    return TVF_OK;
+}
+
+// experiments.m:74-124 for any of its four options ('noise', 'focal', 'points', 'angle', :38-47): every level carries its
+// own noise, point count, cameras, calibration and ground truth.  Level by level: the level's trials (one per seed) are
+// generated with its cameras, solved with its n and CalM, and reduced into its row of the table -- all on the device.
+int tvf_sweep_run_levels(tvf_handle_t h, int method, int64_t first_trial, int64_t B, const tvf_sweep_level* levels, int L,
+                         double hi_x, double hi_y, double* table) {
+    if (!h) return TVF_ERR_ARG;
+    if (!levels || !table || L < 1 || B < 0 || first_trial < 0) return fail(h, TVF_ERR_ARG, "NULL argument or bad size");
+    if (method != 1 && method != 7 && method != 8) return fail(h, TVF_ERR_ARG, "method must be 1 (linear TFT), 7 (linear F) or 8 (optimal F)");
+    if ((first_trial + B) / L + 1 > 0xffffffffLL) return fail(h, TVF_ERR_ARG, "seed exceeds 32 bits");
+    int n_max = 1;
+    for (int l = 0; l < L; ++l) {
+        if (levels[l].n < 1 || levels[l].n > SWEEP_MAX_N) return fail(h, TVF_ERR_ARG, "device scene generator supports 1 <= n <= 60");
+        if (levels[l].n > n_max) n_max = levels[l].n;
+    }
+    TVF_CK(cudaSetDevice(h->device));
+    Slot& s = h->slot[0];
+    cudaStream_t st = s.stream;
+    const int Q = 512;
+    const Method m = method == 1 ? METHOD_TFT : (method == 7 ? METHOD_F : METHOD_OPTF);
+    const int64_t per_level = B / L + 1;
+    const int64_t C = pick_chunk(h, n_max, per_level, false);
+    const size_t need = carve(nullptr, n_max, C, true, false, nullptr);
+    int rc = ensure_arena(h, s, need); if (rc) return rc;
+    ChunkBufs b; carve(s.arena, n_max, C, true, false, &b);
+    void *pc, *pr, *pp, *pt, *pg;
+    rc = ensure_scratch(h, NSCRATCH - 8, (size_t)L * 27 * sizeof(double), &pc); if (rc) return rc;
+    rc = ensure_scratch(h, NSCRATCH - 9, (size_t)L * 24 * sizeof(double), &pr); if (rc) return rc;
+    rc = ensure_scratch(h, NSCRATCH - 5, (size_t)L * Q * 5 * sizeof(double), &pp); if (rc) return rc;
+    rc = ensure_scratch(h, NSCRATCH - 6, (size_t)L * 5 * sizeof(double), &pt); if (rc) return rc;
+    const int64_t G = (per_level < 4 * C) ? per_level : 4 * C;
+    rc = ensure_scratch(h, NSCRATCH - 7, (size_t)G * 6 * n_max * sizeof(double), &pg); if (rc) return rc;
+    std::vector<double> hc((size_t)L * 27), hr((size_t)L * 24);
+    for (int l = 0; l < L; ++l) {
+        memcpy(&hc[(size_t)l * 27], levels[l].calm, 27 * sizeof(double));
+        memcpy(&hr[(size_t)l * 24], levels[l].Rt0_2, 12 * sizeof(double));
+        memcpy(&hr[(size_t)l * 24 + 12], levels[l].Rt0_3, 12 * sizeof(double));
+    }
+    TVF_CK(cudaMemcpyAsync(pc, hc.data(), hc.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    TVF_CK(cudaMemcpyAsync(pr, hr.data(), hr.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    TVF_CK(cudaMemsetAsync(pp, 0, (size_t)L * Q * 5 * sizeof(double), st));
+    TVF_CK(cudaMemsetAsync(pt, 0, (size_t)L * 5 * sizeof(double), st));
+    std::vector<char> skipped((size_t)L, 0);
+    for (int l = 0; l < L; ++l) {
+        // trials j = l + L*q of [first_trial, first_trial + B): 0-based seed index q in [q_lo, q_hi), seed = q + 1
+        const int64_t q_lo = (first_trial > l) ? (first_trial - l + L - 1) / L : 0;
+        const int64_t q_hi = (first_trial + B > l) ? (first_trial + B - l + L - 1) / L : 0;
+        const int64_t Bl = q_hi - q_lo;
+        const int n = levels[l].n;
+        if ((method != 1 && n < 8) || n < 7) { skipped[(size_t)l] = 1; continue; }          // experiments.m:99-104: "not enough matches"
+        if (Bl <= 0) continue;
+        for (int64_t gdone = 0; gdone < Bl; gdone += G) {
+            const int64_t Gc = (Bl - gdone < G) ? (Bl - gdone) : G;
+            rc = sweep_common(h, q_lo + gdone, Gc, n, &levels[l].noise, 1, levels[l].P, hi_x, hi_y, (double*)pg, st); if (rc) return rc;
+            for (int64_t off = 0; off < Gc; off += C) {
+                const int64_t Bc = (Gc - off < C) ? (Gc - off) : C;
+                rc = run_pose_chunk(h, st, m, (const double*)pg + off * 6 * n, (const double*)pc + (size_t)l * 27, 0, n, Bc, b.T, b.F, b.core,
+                                    b.cand, b.votes, b.scale, b.Rt2, b.Rt3, b.reconst, b.repr, b.status, b.iters, nullptr);
+                if (rc) return rc;
+                launch_sweep_eval_accumulate(b.Rt2, b.Rt3, b.repr, b.status, q_lo + gdone + off, Bc, 1, Q, (const double*)pr + (size_t)l * 24,
+                                             (double*)pp + (size_t)l * Q * 5, st);
+                h->launches += 1;
+            }
+        }
+        launch_sweep_eval_finish((const double*)pp + (size_t)l * Q * 5, 1, Q, (double*)pt + (size_t)l * 5, st);
+        h->launches += 1;
+    }
+    TVF_CK(cudaGetLastError());
+    TVF_CK(cudaMemcpyAsync(table, pt, (size_t)L * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    TVF_CK(cudaStreamSynchronize(st));
+    const double inf = __builtin_huge_val();
+    for (int l = 0; l < L; ++l)
+        if (skipped[(size_t)l]) { table[5 * l] = inf; table[5 * l + 1] = inf; table[5 * l + 2] = inf; table[5 * l + 3] = 0.0; table[5 * l + 4] = 0.0; }
     return TVF_OK;
 }
 

@@ -213,6 +213,26 @@ __device__ __forceinline__ void build_gidx(unsigned char* gidx) {
     }
 }
 
+// trace of the 27 x 27 Gram from its moments: the diagonal entry of row (i,k,j) is moment sym6(i,i)*16 + m4(k,k)*4 +
+// m4(j,j) with sym6(i,i) in {0,3,5} and m4(k,k) in {0,0,3}: 12 moments, which occur nowhere else in the Gram
+__device__ __forceinline__ bool is_diag_moment(int idx) {
+    const int a = idx >> 4, bg = idx & 15;
+    return (a == 0 || a == 3 || a == 5) && (bg == 0 || bg == 3 || bg == 12 || bg == 15);
+}
+__device__ __forceinline__ double diag_moment_weight(int idx) {       // how many diagonal entries equal this moment
+    const int bg = idx & 15;
+    return (bg == 0) ? 4.0 : ((bg == 15) ? 1.0 : 2.0);
+}
+__device__ __forceinline__ double gram_trace_from_moments(const double* mom) {
+    double tr = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int o = (a == 0) ? 0 : ((a == 1) ? 48 : 80);
+        tr += 4.0 * mom[o] + 2.0 * (mom[o + 3] + mom[o + 12]) + mom[o + 15];
+    }
+    return tr;
+}
+
 // =========================================================================== TFT stage 1
 struct __align__(16) Stage1Scratch {
     double sbuf[64];                 // solver row/vector buffers
@@ -296,9 +316,240 @@ tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ statu
     }
 }
 
-// Large-n path: the moments were produced by tft_moments_large_kernel (tvf_large_kernels.cu); this is the
-// second half of stage 1 on its own (27x27 Gram from the 96 moments -> null vector).
-__global__ void __launch_bounds__(CORE_WARPS * 32, CORE_MINB)
+// =========================================================================== TFT stage 1, two problems per warp
+// n >= REFINE_N_MAX.  Half h of a warp owns problem 2*pair + h from the first load to the last store: the normalisation
+// statistics (points r, r + 16, ... of the problem on lane r; 4-step half-warp reductions), the 96 moments (lane r owns
+// the view-3 x view-2 product (beta, gamma) = (r >> 2, r & 3) and accumulates it against all six view-1 features: one
+// product, six DFMAs and five shared loads per point for BOTH problems), the unit-trace scaling and diagonal shift
+// applied to the moment table (the 12 moments that make up the diagonal of the Gram occur nowhere else in it, so the
+// shift is added to them), the gather of rows r and r + 14, and the two-rows-per-lane solver above.
+#ifndef TVF_STAGE1_DUAL
+#define TVF_STAGE1_DUAL 1
+#endif
+// solver of the split stage 1 (and of the large-n path): 1 = one problem per warp, one matrix row per lane (96
+// registers, 20 warps per SM), 2 = two problems per warp, two rows per lane (168 registers, 12 warps per SM: 22 % fewer
+// instructions but measured 18 % SLOWER -- the per-sweep reciprocal / publish / read-back chain is exposed with so few warps)
+#ifndef TVF_S1_SOLVER
+#define TVF_S1_SOLVER 1
+#endif
+#ifndef TVF_S1D_MINB
+#define TVF_S1D_MINB 3
+#endif
+constexpr int S1D_FEAT = 18;         // feature row stride (doubles): rows stay 16-byte aligned, lane-strided stores 2-way
+
+struct __align__(16) Stage1DualScratch {
+    double sbuf[128];                // solver row/vector buffers: [parity][half][32]
+    double feat[2][16 * S1D_FEAT];   // per half: features of 16 points
+    double mom[2][100];              // per half: 96 scaled + shifted moments, zero sentinel at 96
+};
+
+// moments in sc.mom[h] (raw) -> scaled to unit trace, shifted; then rows r and r + 14 -> null vector -> rec
+__device__ __forceinline__ void solve_pair_from_moments(Stage1DualScratch& sc, const unsigned char* gidx, int lane, bool live,
+                                                        double* rec, int* status, long long prob) {
+    const int h = lane >> 4, r = lane & 15;
+    double* mom = sc.mom[h];
+    const double tr = gram_trace_from_moments(mom);
+    const double scl = 1.0 / tr;
+    const double delta = 1.0e-13 / 27.0;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const int idx = q * 16 + r;
+        mom[idx] = fma(mom[idx], scl, is_diag_moment(idx) ? delta : 0.0);
+    }
+    __syncwarp();
+    const int row0 = (r < 14) ? r : 31, row1 = (r < 13) ? r + 14 : 31;          // rows >= 27 gather the zero sentinel
+    double g0[27], g1[27];
+#pragma unroll
+    for (int c = 0; c < 27; ++c) { g0[c] = mom[gidx[row0 * 27 + c]]; g1[c] = mom[gidx[row1 * 27 + c]]; }
+    double x0, x1;
+    bool conv;
+    smallest_eigvec_spd_half2<27>(g0, g1, lane, sc.sbuf, &x0, &x1, &conv);
+    if (live) {
+        if (r < 14) rec[CW_T1 + r] = x0;
+        if (r < 13) rec[CW_T1 + 14 + r] = x1;
+        if (status != nullptr && r == 0) status[prob] = conv ? 0 : ST_EIG_NOCONV;
+    }
+}
+
+// Normalisation statistics and the 96 moments of one problem on one half-warp (r = lane & 15).  feat: this half's
+// 16 x S1D_FEAT staging buffer.  acc[q] receives moment q*16 + r; (s, t): new = s*x + t per view.
+template <bool PACKED>
+__device__ __forceinline__ void half_stats_moments(const CoreInput& in, long long prob, int r, double* feat, double (&acc)[6],
+                                                   double (&s)[3], double (&t)[6]) {
+    const int n = in.n;
+    const int beta = r >> 2, gamma = r & 3;
+    const double invn = 1.0 / (double)n;
+    s[0] = s[1] = s[2] = 1.0;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) { t[q] = 0.0; acc[q] = 0.0; }
+    // ---- normalisation (LinearTFTPoseEstimation.m:45-47 -> Normalize2Ddata.m:34-37), three views at once -------
+    if (in.normalize) {
+        double sum[6] = {0, 0, 0, 0, 0, 0};
+        for (int i = r; i < n; i += 16) {
+            double p[6];
+            load_point<PACKED>(in, prob, i, p);
+#pragma unroll
+            for (int q = 0; q < 6; ++q) sum[q] += p[q];
+        }
+        double c[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) c[q] = half_sum(sum[q]) * invn;
+        double d[3] = {0, 0, 0};
+        for (int i = r; i < n; i += 16) {
+            double p[6];
+            load_point<PACKED>(in, prob, i, p);
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                const double dx = p[2 * v] - c[2 * v], dy = p[2 * v + 1] - c[2 * v + 1];
+#if TVF_FAST_STATS
+                d[v] += sqrt_(dx * dx + dy * dy);
+#else
+                d[v] += sqrt(dx * dx + dy * dy);
+#endif
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            const double norm0 = half_sum(d[v]) * invn;
+#if TVF_FAST_STATS
+            s[v] = 1.4142135623730951 * rcp_(norm0);
+#else
+            s[v] = 1.4142135623730951 / norm0;
+#endif
+            t[2 * v] = -s[v] * c[2 * v];
+            t[2 * v + 1] = -s[v] * c[2 * v + 1];
+        }
+    }
+    // ---- 96 moments: lane r owns (beta, gamma) and all six alpha ----------------------------------------------
+    for (int pbase = 0; pbase < n; pbase += 16) {
+        const int cnt = min(16, n - pbase);
+        __syncwarp();
+        if (r < cnt) {
+            double p[6];
+            load_point<PACKED>(in, prob, pbase + r, p);
+            const double x1 = s[0] * p[0] + t[0], y1 = s[0] * p[1] + t[1];
+            const double x2 = s[1] * p[2] + t[2], y2 = s[1] * p[3] + t[3];
+            const double x3 = s[2] * p[4] + t[4], y3 = s[2] * p[5] + t[5];
+            double2* f2 = reinterpret_cast<double2*>(feat + r * S1D_FEAT);
+            f2[0] = make_double2(x1 * x1, x1 * y1); f2[1] = make_double2(x1, y1 * y1); f2[2] = make_double2(y1, 1.0);
+            f2[3] = make_double2(1.0, -x3); f2[4] = make_double2(-y3, x3 * x3 + y3 * y3);
+            f2[5] = make_double2(1.0, -x2); f2[6] = make_double2(-y2, x2 * x2 + y2 * y2);
+        }
+        __syncwarp();
+        for (int p = 0; p < cnt; ++p) {
+            const double* f = feat + p * S1D_FEAT;
+            const double2* f2 = reinterpret_cast<const double2*>(f);
+            const double bc = f[6 + beta] * f[10 + gamma];
+            const double2 a01 = f2[0], a23 = f2[1], a45 = f2[2];
+            acc[0] = fma(a01.x, bc, acc[0]); acc[1] = fma(a01.y, bc, acc[1]); acc[2] = fma(a23.x, bc, acc[2]);
+            acc[3] = fma(a23.y, bc, acc[3]); acc[4] = fma(a45.x, bc, acc[4]); acc[5] = fma(a45.y, bc, acc[5]);
+        }
+    }
+    __syncwarp();
+}
+
+__device__ __forceinline__ void store_moments_stats(double* rec, int r, const double (&acc)[6], const double (&s)[3], const double (&t)[6]) {
+#pragma unroll
+    for (int q = 0; q < 6; ++q) rec[CW_MOM + q * 16 + r] = acc[q];
+    if (r < 3) rec[CW_STATS + r] = sel3(s, r);
+    if (r < 6) rec[CW_STATS + 3 + r] = (r < 3) ? sel3(t, r) : sel3(t + 3, r - 3);
+}
+
+template <bool PACKED>
+__global__ void __launch_bounds__(CORE_WARPS * 32, TVF_S1D_MINB)
+tft_stage1_dual_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ status) {
+    __shared__ Stage1DualScratch scratch[CORE_WARPS];
+    __shared__ unsigned char gidx[32 * 27];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    build_gidx(gidx);
+    __syncthreads();
+    Stage1DualScratch& sc = scratch[warp];
+    const int h = lane >> 4, r = lane & 15;
+    const long long npairs = (in.B + 1) / 2;
+
+    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < npairs; base += (long long)gridDim.x * CORE_WARPS) {
+        STEP_SYNC();
+        const long long pair = base + warp;
+        if (pair >= npairs) continue;
+        const bool live = 2 * pair + h < in.B;
+        const long long prob = live ? 2 * pair + h : in.B - 1;          // odd batch: the idle half repeats the last problem
+        double* rec = ws + prob * CORE_WS_TFT;
+        double acc[6], s[3], t[6];
+        half_stats_moments<PACKED>(in, prob, r, sc.feat[h], acc, s, t);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sc.mom[h][q * 16 + r] = acc[q];
+        if (r < 4) sc.mom[h][96 + r] = 0.0;
+        if (live) store_moments_stats(rec, r, acc, s, t);
+        __syncwarp();
+        solve_pair_from_moments(sc, gidx, lane, live, rec, status, prob);
+    }
+}
+
+// The first half on its own, compiled for many resident warps (it needs few registers and is latency bound: global
+// loads, shuffle reductions, square-root chains): statistics + moments -> work-space record.  The solve then runs as
+// tft_stage1_solve_dual_kernel.  (TVF_STAGE1_SPLIT; the fused kernel above holds 54 matrix doubles per lane, which
+// caps it at 12 warps per SM for its whole run.)
+#ifndef TVF_STAGE1_SPLIT
+#define TVF_STAGE1_SPLIT 1
+#endif
+#ifndef TVF_S1M_MINB
+#define TVF_S1M_MINB 10
+#endif
+struct __align__(16) MomentsScratch {
+    double feat[2][16 * S1D_FEAT];
+};
+
+template <bool PACKED>
+__global__ void __launch_bounds__(CORE_WARPS * 32, TVF_S1M_MINB)
+tft_moments_kernel(CoreInput in, double* __restrict__ ws) {
+    __shared__ MomentsScratch scratch[CORE_WARPS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = lane >> 4, r = lane & 15;
+    const long long npairs = (in.B + 1) / 2;
+    for (long long pair = (long long)blockIdx.x * CORE_WARPS + warp; pair < npairs; pair += (long long)gridDim.x * CORE_WARPS) {
+        const bool live = 2 * pair + h < in.B;
+        const long long prob = live ? 2 * pair + h : in.B - 1;
+        double acc[6], s[3], t[6];
+        half_stats_moments<PACKED>(in, prob, r, scratch[warp].feat[h], acc, s, t);
+        if (live) store_moments_stats(ws + prob * CORE_WS_TFT, r, acc, s, t);
+    }
+}
+
+// Large-n path, two problems per warp: the moments were produced by tft_moments_large_kernel.
+__global__ void __launch_bounds__(CORE_WARPS * 32, TVF_S1D_MINB)
+tft_stage1_solve_dual_kernel(long long B, double* __restrict__ ws, int* __restrict__ status) {
+    __shared__ Stage1DualScratch scratch[CORE_WARPS];
+    __shared__ unsigned char gidx[32 * 27];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    build_gidx(gidx);
+    __syncthreads();
+    Stage1DualScratch& sc = scratch[warp];
+    const int h = lane >> 4, r = lane & 15;
+    const long long npairs = (B + 1) / 2;
+    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < npairs; base += (long long)gridDim.x * CORE_WARPS) {
+        STEP_SYNC();
+        const long long pair = base + warp;
+        if (pair >= npairs) continue;
+        const bool live = 2 * pair + h < B;
+        const long long prob = live ? 2 * pair + h : B - 1;
+        double* rec = ws + prob * CORE_WS_TFT;
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sc.mom[h][q * 16 + r] = rec[CW_MOM + q * 16 + r];
+        if (r < 4) sc.mom[h][96 + r] = 0.0;
+        __syncwarp();
+        solve_pair_from_moments(sc, gidx, lane, live, rec, status, prob);
+    }
+}
+
+// The second half of stage 1 on its own, one problem per warp (27 x 27 Gram from the 96 moments -> null vector).  The
+// moments come from tft_moments_kernel (split stage 1) or from tft_moments_large_kernel (large n).  The unit-trace
+// scaling and the diagonal shift are applied to the moment table (see solve_pair_from_moments).
+#ifndef TVF_S1S_MINB
+#define TVF_S1S_MINB 4
+#endif
+__global__ void __launch_bounds__(CORE_WARPS * 32, TVF_S1S_MINB)
 tft_stage1_solve_kernel(long long B, double* __restrict__ ws, int* __restrict__ status) {
     __shared__ Stage1Scratch scratch[CORE_WARPS];
     __shared__ unsigned char gidx[32 * 27];
@@ -311,10 +562,30 @@ tft_stage1_solve_kernel(long long B, double* __restrict__ ws, int* __restrict__ 
         const long long prob = base + warp;
         if (prob >= B) continue;
         double* rec = ws + prob * CORE_WS_TFT;
-        sc.mom[lane] = rec[CW_MOM + lane]; sc.mom[lane + 32] = rec[CW_MOM + 32 + lane]; sc.mom[lane + 64] = rec[CW_MOM + 64 + lane];
+        const double m0 = rec[CW_MOM + lane], m1 = rec[CW_MOM + 32 + lane], m2 = rec[CW_MOM + 64 + lane];
+        // trace = sum of the 12 diagonal moments with multiplicities 4, 2, 2, 1 (gram_trace_from_moments), as one reduction
+        double part = 0.0;
+        {
+            const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
+            part += is_diag_moment(i0) ? diag_moment_weight(i0) * m0 : 0.0;
+            part += is_diag_moment(i1) ? diag_moment_weight(i1) * m1 : 0.0;
+            part += is_diag_moment(i2) ? diag_moment_weight(i2) * m2 : 0.0;
+        }
+        const double scl = 1.0 / warp_sum(part);
+        const double delta = 1.0e-13 / 27.0;
+        __syncwarp();
+        sc.mom[lane] = fma(m0, scl, is_diag_moment(lane) ? delta : 0.0);
+        sc.mom[lane + 32] = fma(m1, scl, is_diag_moment(lane + 32) ? delta : 0.0);
+        sc.mom[lane + 64] = fma(m2, scl, is_diag_moment(lane + 64) ? delta : 0.0);
         if (lane == 0) { sc.mom[96] = 0.0; sc.mom[97] = 0.0; }
         __syncwarp();
-        solve_from_moments(sc, gidx, rec, lane, status, prob, NoRefine(), 0);
+        double g[27];
+#pragma unroll
+        for (int c = 0; c < 27; ++c) g[c] = sc.mom[gidx[lane * 27 + c]];
+        bool conv;
+        const double tl = smallest_eigvec_spd<27, NoRefine, true>(g, lane, sc.sbuf, &conv);
+        if (lane < 27) rec[CW_T1 + lane] = tl;
+        if (status != nullptr && lane == 0) status[prob] = conv ? 0 : ST_EIG_NOCONV;
     }
 }
 
@@ -842,19 +1113,46 @@ static inline unsigned core_grid(long long B, int sm_count) {
     return (unsigned)(blocks < 1 ? 1 : blocks);
 }
 
-void launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream) {
-    if (in.B <= 0) return;
+static inline unsigned core_grid_minb(long long units, int sm_count, int minb) {
+    long long blocks = (units + CORE_WARPS - 1) / CORE_WARPS;
+    const long long cap = (long long)sm_count * minb * 4;
+    if (blocks > cap) blocks = cap;
+    return (unsigned)(blocks < 1 ? 1 : blocks);
+}
+
+int launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream) {
+    if (in.B <= 0) return 0;
     const unsigned g = core_grid(in.B, sm_count);
     const bool refine = in.n < REFINE_N_MAX;       // barely determined systems: polish with the un-squared rows
+#if TVF_STAGE1_DUAL
+    if (!refine) {
+#if TVF_STAGE1_SPLIT
+        const unsigned gm = core_grid_minb((in.B + 1) / 2, sm_count, TVF_S1M_MINB);
+        if (in.packed) tft_moments_kernel<true><<<gm, CORE_WARPS * 32, 0, stream>>>(in, ws);
+        else tft_moments_kernel<false><<<gm, CORE_WARPS * 32, 0, stream>>>(in, ws);
+        return 1;                 // the caller follows up with launch_tft_stage1_solve
+#else
+        const unsigned gd = core_grid_minb((in.B + 1) / 2, sm_count, TVF_S1D_MINB);
+        if (in.packed) tft_stage1_dual_kernel<true><<<gd, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+        else tft_stage1_dual_kernel<false><<<gd, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+        return 0;
+#endif
+    }
+#endif
     if (in.packed && refine) tft_stage1_kernel<true, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
     else if (in.packed) tft_stage1_kernel<true, false><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
     else if (refine) tft_stage1_kernel<false, true><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
     else tft_stage1_kernel<false, false><<<g, CORE_WARPS * 32, 0, stream>>>(in, ws, status);
+    return 0;
 }
 
 void launch_tft_stage1_solve(long long B, double* ws, int* status, int sm_count, cudaStream_t stream) {
     if (B <= 0) return;
-    tft_stage1_solve_kernel<<<core_grid(B, sm_count), CORE_WARPS * 32, 0, stream>>>(B, ws, status);
+#if TVF_S1_SOLVER == 2
+    tft_stage1_solve_dual_kernel<<<core_grid_minb((B + 1) / 2, sm_count, TVF_S1D_MINB), CORE_WARPS * 32, 0, stream>>>(B, ws, status);
+#else
+    tft_stage1_solve_kernel<<<core_grid_minb(B, sm_count, TVF_S1S_MINB), CORE_WARPS * 32, 0, stream>>>(B, ws, status);
+#endif
 }
 
 void launch_tft_epipoles(double* ws, long long B, cudaStream_t stream) {

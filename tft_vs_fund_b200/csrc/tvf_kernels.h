@@ -23,7 +23,8 @@ struct CoreInput {
 constexpr int CORE_WS_TFT = 140;   // 96 moments | 9 normalisation stats (+1) | t1 27 (+1) | e21,e31
 constexpr int CORE_WS_F = 36;      // raw f (2 x 9) | outer stats 9 | inner stats 9
 
-void launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream);
+// returns 1 when only the moments half ran (split stage 1): the caller then launches launch_tft_stage1_solve
+int launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count, cudaStream_t stream);
 // large-n stage 1: cluster/TMA moments kernel (returns 0 if the shape is unsupported -> use launch_tft_stage1)
 // followed by the solve-only half of stage 1
 constexpr int LARGE_N_MIN = 1024;

@@ -130,6 +130,9 @@ struct __align__(16) LargeScratch {
     unsigned long long bar3;        // this CTA finalises the scene: the 8 x 99 sums have landed in in3
     double wpart1[LG_WARPS][8];     // per-warp partials, pass 1: 6 coordinate sums
     double wpart2[LG_WARPS][56];    // per-warp partials, pass 2: 48 moments + 2 distance sums
+#if TVF_LARGE_DMMA
+    double wpartD[LG_WARPS][100];   // tensor-core variant: per-warp partials of all 96 moments + 3 distance sums
+#endif
     double in1[2][LG_CLUSTER][8];   // [scene parity][source rank][6 coordinate sums]   (written by st.async from every rank)
     double in3[LG_CLUSTER][104];    // [source rank][96 centred raw moments + 3 distance sums]
     double cen[2][8];               // cluster-wide centroids by scene parity
@@ -194,6 +197,54 @@ __device__ __forceinline__ void moments_pass(const double* __restrict__ pts, int
         }
         if (!more) break;
         a = na; b = nb; c = nc; i = nx;
+    }
+}
+
+// ---- tensor-core variant of the fused pass (TVF_LARGE_DMMA=1; north star: "tensor cores ... for Gram formation on
+// large-n triplets, where that step really is a dense contraction") -------------------------------------------------
+// The 96 moments are the 6 x 16 x n contraction M = sum_i A6_i (x) U16_i (A6 = view-1 features, U16 = the 16 view-3 x
+// view-2 products).  Padded to 8 x 16 it is two DMMA.8x8x4 accumulator tiles per warp; a k-step consumes 4 points.
+// Fragment layout of mma.sync.m8n8k4.f64: lane l supplies A[l>>2][l&3] and B[l&3][l>>2], i.e. for point (l & 3) of
+// the k-step the ONE view-1 feature m = l >> 2 and the ONE product n = l >> 2 (+ 8 for the second tile) -- every
+// point's coordinates are therefore centred by 8 lanes, and each lane builds its three operands with lane-constant
+// selects.  Per 4 points that is ~24 FP64 instructions + 2 DMMA (= 16 DFMA issue slots on the shared FP64 pipe) against
+// ~19 for the DFMA form: the tensor-core form spends MORE pipe time, and is kept as measured evidence only.
+#ifndef TVF_LARGE_DMMA
+#define TVF_LARGE_DMMA 0
+#endif
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+// warp `warp` of LG_WARPS takes k-steps warp, warp + LG_WARPS, ...; c0/c1: accumulator tiles (products 0..7 / 8..15);
+// ds: this lane's share of the three distance sums (lanes with m = 0,1,2 own view 1,2,3)
+__device__ __forceinline__ void moments_pass_dmma(const double* __restrict__ pts, int npts, int warp, int lane,
+                                                  const double (&cen)[6], double (&c0)[2], double (&c1)[2], double& ds) {
+    const int m = lane >> 2, kp = lane & 3;
+    const int gam = m & 3, bhi = m >> 2;
+    for (int base = warp * 4; base < npts; base += LG_WARPS * 4) {
+        const int p = base + kp;
+        const bool valid = p < npts;
+        const double2* q = reinterpret_cast<const double2*>(pts + 6 * (valid ? p : base));
+        const double2 a = q[0], b = q[1], c = q[2];
+        const double x1 = a.x - cen[0], y1 = a.y - cen[1];
+        const double x2 = b.x - cen[2], y2 = b.y - cen[3];
+        const double x3 = c.x - cen[4], y3 = c.y - cen[5];
+        const double r2 = fma(x2, x2, y2 * y2), r3 = fma(x3, x3, y3 * y3);
+        // A operand: view-1 feature m of [x^2, xy, x, y^2, y, 1, 0, 0]
+        const double ua = (m < 3) ? x1 : ((m < 5) ? y1 : ((m == 5) ? 1.0 : 0.0));
+        const double ub = (m == 0) ? x1 : ((m == 1 || m == 3) ? y1 : 1.0);
+        const double av = valid ? ua * ub : 0.0;
+        // B operands: product n = 4*beta + gamma of m4(view 3)[beta] * m4(view 2)[gamma], m4 = [1, x, y, x^2+y^2]
+        const double g = (gam == 0) ? 1.0 : ((gam == 1) ? x2 : ((gam == 2) ? y2 : r2));
+        const double b0 = bhi ? x3 : 1.0, b1 = bhi ? r3 : y3;
+        dmma_8x8x4(c0, av, g * b0);
+        dmma_8x8x4(c1, av, g * b1);
+        // distance sums of Normalize2Ddata.m:35: lanes m = 0, 1, 2 take views 1, 2, 3 of their point
+        const double dd = (m == 0) ? fma(x1, x1, y1 * y1) : ((m == 1) ? r2 : r3);
+        const double sq = sqrt_fast(dd);
+        ds += (valid && m < 3) ? sq : 0.0;
     }
 }
 
@@ -288,6 +339,21 @@ tft_moments_large_kernel(const double* __restrict__ corresp, int n, long long B,
             for (int k = 0; k < 6; ++k) cen[k] = sc.cen[par][k];
         }
         // ---- pass 2 (fused): distance sums (:35) + the 96 centred raw moments ----------------------------
+#if TVF_LARGE_DMMA
+        {
+            double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0}, dsl = 0.0;
+            moments_pass_dmma(pts, npts, warp, lane, cen, c0, c1, dsl);
+            const int m = lane >> 2, kp = lane & 3;
+            if (m < 6) {                                   // rows 6, 7 of the accumulator tiles are padding
+                sc.wpartD[warp][m * 16 + 2 * kp] = c0[0]; sc.wpartD[warp][m * 16 + 2 * kp + 1] = c0[1];
+                sc.wpartD[warp][m * 16 + 8 + 2 * kp] = c1[0]; sc.wpartD[warp][m * 16 + 8 + 2 * kp + 1] = c1[1];
+            }
+            // lanes with the same m hold the partial distance sum of view m + 1: add over kp (xor 1, 2), then lane m*4 stores
+            dsl += __shfl_xor_sync(0xffffffffu, dsl, 1);
+            dsl += __shfl_xor_sync(0xffffffffu, dsl, 2);
+            if (kp == 0 && m < 3) sc.wpartD[warp][96 + m] = dsl;
+        }
+#else
         double acc[48], ds[2] = {0.0, 0.0};
 #pragma unroll
         for (int k = 0; k < 48; ++k) acc[k] = 0.0;
@@ -300,6 +366,7 @@ tft_moments_large_kernel(const double* __restrict__ corresp, int n, long long B,
         sc.wpart2[warp][lane] = t32;
         if (lane < 16) sc.wpart2[warp][32 + lane] = t16;
         if (lane == 0) { sc.wpart2[warp][48] = d0; sc.wpart2[warp][49] = d1; }
+#endif
         __syncthreads();                                  // every thread is done with the slice
         {
             const long long next = scene + ncl;
@@ -311,6 +378,12 @@ tft_moments_large_kernel(const double* __restrict__ corresp, int n, long long B,
         const unsigned fin = it % LG_CLUSTER;              // the rank that finalises this scene
         if (tid < 99) {
             double v;
+#if TVF_LARGE_DMMA
+            v = 0.0;
+#pragma unroll
+            for (int w = 0; w < LG_WARPS; ++w) v += sc.wpartD[w][tid];          // index = alpha*16 + beta*4 + gamma | 96 + view
+            if (tid == 80) v = (double)npts;
+#else
             if (tid < 96) {
                 const int al = tid >> 4, be = (tid >> 2) & 3, ga = tid & 3;     // moment index = alpha*16 + beta*4 + gamma
                 const int g = be >> 1, k = al * 8 + (be & 1) * 4 + ga;
@@ -319,6 +392,7 @@ tft_moments_large_kernel(const double* __restrict__ corresp, int n, long long B,
                 const int w = tid - 96, g = (w == 2) ? 1 : 0, k = (w == 1) ? 49 : 48;
                 v = sc.wpart2[g][k] + sc.wpart2[g + 2][k];
             }
+#endif
             st_async_f64(mapa_u32(smem_u32(&sc.in3[rank][tid]), fin), v, mapa_u32(smem_u32(&sc.bar3), fin));
         }
         if (rank == fin) {                                 // CTA-uniform branch

@@ -30,22 +30,57 @@ constexpr int EIG_MAX_ITER = 80;
 #ifndef TVF_GJ_PIPE
 #define TVF_GJ_PIPE 0
 #endif
+// Gauss-Jordan sweeps publish the RAW pivot column (one STS straight from the register, before the pivot's reciprocal
+// chain starts) and scale the per-lane multiplier instead of the published row: the shared-memory round trip
+// (STS -> barrier -> LDS.128) then runs under the shuffle + MUFU + Newton chain instead of after it.
+#ifndef TVF_GJ_RAWCOL
+#define TVF_GJ_RAWCOL 0
+#endif
 #ifndef TVF_EIG_TOL
 #define TVF_EIG_TOL 4.0e-15
 #endif
-constexpr double EIG_TOL = TVF_EIG_TOL;      // largest component change of the unit eigenvector between two steps
+// Largest change of a component's MAGNITUDE between two steps.  Magnitudes, not signed values: the iterate is normalised
+// by its largest component, and when two components of opposite sign tie for that role to within rounding the pivot can
+// alternate between them from step to step, flipping the sign of the whole (otherwise converged) vector each time.  The
+// sign of the eigenvector is arbitrary anyway (T, F are defined up to sign).
+constexpr double EIG_TOL = TVF_EIG_TOL;
 
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(FULL, v, src); }
 
 // 1/d for a normal, positive d: MUFU.RCP64H seed (>= 20 bits) + two Newton steps (full double precision,
 // not correctly rounded) -- 7 instructions instead of the ~20 of the IEEE division with its slow path.
+// TVF_RCP_CUBIC: one third-order step r (1 + e + e^2), e = 1 - d r, instead of two Newton steps: the seed's 2^-20 becomes
+// 2^-60 in THREE dependent DFMAs instead of four (the reciprocal sits on the serial chain of every Gauss-Jordan sweep).
+#ifndef TVF_RCP_CUBIC
+#define TVF_RCP_CUBIC 0
+#endif
 __device__ __forceinline__ double fast_rcp(double d) {
     double r;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+#if TVF_RCP_CUBIC
+    const double e = fma(-d, r, 1.0);
+    const double t = fma(e, e, e);
+    return fma(r, t, r);
+#else
     double e = fma(-d, r, 1.0);
     r = fma(r, e, r);
     e = fma(-d, r, 1.0);
     return fma(r, e, r);
+#endif
+}
+
+// max(d, floor) for the Gauss-Jordan pivots, decided on the high word with one integer compare (negative, zero and
+// tiny pivots all compare below; a NaN pivot passes through and poisons the problem, which is then flagged NONFINITE)
+// instead of fmax()'s DSETP.MAX + selects + NaN-quieting sequence.  Identical to fmax for every regular pivot.
+#ifndef TVF_PIVOT_INTFLOOR
+#define TVF_PIVOT_INTFLOOR 1
+#endif
+__device__ __forceinline__ double pivot_floor(double d, double floor_piv) {
+#if TVF_PIVOT_INTFLOOR
+    return (__double2hiint(d) < __double2hiint(floor_piv)) ? floor_piv : d;
+#else
+    return fmax(d, floor_piv);
+#endif
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -87,20 +122,25 @@ __device__ __forceinline__ double warp_reduce_transposed32(double (&v)[32], int 
 // polished by iterative refinement, x <- x - (G+dI)^-1 (A'(A x) - rho x): the residual carries an error of
 // eps*|A|*|Ax| instead of the eps*|A|^2 of the Gram route, which matters for barely determined systems
 // (n = 7..11) where sigma_{N-1} is tiny.  nrefine is warp-uniform.
-template <int N, class Resid = NoRefine>
+// PRESCALED: the caller passes G/trace + delta*I already (the Gram is gathered from a moment table, and scaling that
+// table costs 3 multiplications per lane instead of N per lane plus the diagonal-extraction select chain); no refinement.
+template <int N, class Resid = NoRefine, bool PRESCALED = false>
 __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int lane, double* sbuf, bool* converged,
                                                       Resid resid = Resid(), int nrefine = 0) {
     static_assert(N <= 32 && N >= 2, "one matrix row per lane");
     constexpr int NP = (N + 1) & ~1;          // row length padded to a whole number of 128-bit loads
-    double diag = 0.0;
-#pragma unroll
-    for (int m = 0; m < N; ++m) diag = (lane == m) ? g[m] : diag;
-    const double tr = warp_sum(diag);
-    const double sc = 1.0 / tr;
     const double delta = 1.0e-13 / N;         // relative to the unit trace
     const double floor_piv = 1.0e-3 * delta;
+    double sc = 1.0;
+    if (!PRESCALED) {
+        double diag = 0.0;
 #pragma unroll
-    for (int m = 0; m < N; ++m) g[m] = g[m] * sc + ((lane == m) ? delta : 0.0);
+        for (int m = 0; m < N; ++m) diag = (lane == m) ? g[m] : diag;
+        const double tr = warp_sum(diag);
+        sc = 1.0 / tr;
+#pragma unroll
+        for (int m = 0; m < N; ++m) g[m] = g[m] * sc + ((lane == m) ? delta : 0.0);
+    }
 
     __syncwarp();                              // sbuf may still be read by a previous phase
     if (lane >= N && lane < NP) { sbuf[lane] = 0.0; sbuf[32 + lane] = 0.0; }
@@ -112,7 +152,7 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
     // column k+1 FIRST and starts that chain for sweep k+1 at once (into the other row buffer), so it runs under the
     // remaining 25 DFMAs of sweep k.
     double colj = g[0];
-    double piv = fast_rcp(fmax(shfl_d(colj, 0), floor_piv));
+    double piv = fast_rcp(pivot_floor(shfl_d(colj, 0), floor_piv));
     double rk = colj * piv;
     if (lane < N) sbuf[lane] = rk;
 #pragma unroll
@@ -125,7 +165,7 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
             const double2 r = b2[(k + 1) >> 1];
             g[k + 1] = fma(-c, ((k + 1) & 1) ? r.y : r.x, g[k + 1]);
             colj_n = g[k + 1];
-            piv_n = fast_rcp(fmax(shfl_d(colj_n, k + 1), floor_piv));
+            piv_n = fast_rcp(pivot_floor(shfl_d(colj_n, k + 1), floor_piv));
             rk_n = colj_n * piv_n;
             if (lane < N) sbuf[((k + 1) & 1) * 32 + lane] = rk_n;
         }
@@ -138,11 +178,30 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
         g[k] = (lane == k) ? -piv : rk;
         colj = colj_n; piv = piv_n; rk = rk_n;
     }
+#elif TVF_GJ_RAWCOL
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double colj = g[k];
+        double* buf = sbuf + (k & 1) * 32;
+        if (lane < N) buf[lane] = colj;        // raw column k == raw row k (symmetry)
+        const double d = pivot_floor(shfl_d(colj, k), floor_piv);
+        const double piv = fast_rcp(d);
+        __syncwarp();
+        const double cs = (colj - ((lane == k) ? 1.0 : 0.0)) * piv;
+        const double2* b2 = reinterpret_cast<const double2*>(buf);
+#pragma unroll
+        for (int m2 = 0; m2 < NP / 2; ++m2) {
+            const double2 r = b2[m2];
+            if (2 * m2 != k && 2 * m2 < N) g[2 * m2] = fma(-cs, r.x, g[2 * m2]);
+            if (2 * m2 + 1 != k && 2 * m2 + 1 < N) g[2 * m2 + 1] = fma(-cs, r.y, g[2 * m2 + 1]);
+        }
+        g[k] = (lane == k) ? -piv : colj * piv;
+    }
 #else
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const double colj = g[k];
-        const double d = fmax(shfl_d(colj, k), floor_piv);
+        const double d = pivot_floor(shfl_d(colj, k), floor_piv);
         const double piv = fast_rcp(d);
         const double rk = colj * piv;
         double* buf = sbuf + (k & 1) * 32;
@@ -174,19 +233,20 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
         if (lane < NP) buf[lane] = x;
         __syncwarp();
         const double2* b2 = reinterpret_cast<const double2*>(buf);
-        double z0 = 0.0, z1 = 0.0;
+        double za[4] = {0.0, 0.0, 0.0, 0.0};               // four independent accumulation chains
 #pragma unroll
         for (int m2 = 0; m2 < NP / 2; ++m2) {
             const double2 r = b2[m2];
-            if (2 * m2 < N) z0 = fma(g[2 * m2], r.x, z0);
-            if (2 * m2 + 1 < N) z1 = fma(g[2 * m2 + 1], r.y, z1);
+            const int c = (m2 & 1) * 2;
+            if (2 * m2 < N) za[c] = fma(g[2 * m2], r.x, za[c]);
+            if (2 * m2 + 1 < N) za[c + 1] = fma(g[2 * m2 + 1], r.y, za[c + 1]);
         }
-        double z = z0 + z1;
+        double z = (za[0] + za[1]) + (za[2] + za[3]);
         const unsigned hz = (unsigned)__double2hiint(z) & 0x7fffffffu;
         const unsigned hmax = __reduce_max_sync(FULL, hz);
         const int piv = __ffs(__ballot_sync(FULL, hz == hmax)) - 1;
         z *= fast_rcp(shfl_d(z, piv));
-        const bool moving = fabs(z - x) > EIG_TOL;            // max_lane |z - x| > tol, as one warp vote
+        const bool moving = fabs(fabs(z) - fabs(x)) > EIG_TOL;            // max_lane |z - x| > tol, as one warp vote
         x = z;
         if (!__any_sync(FULL, moving)) { ok = true; break; }
     }
@@ -208,7 +268,7 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
         }
         double z = -(z0 + z1);
         z *= rsqrt_(warp_sum(z * z));
-        const bool moving = fabs(z - x) > EIG_TOL;            // max_lane |z - x| > tol, as one warp vote
+        const bool moving = fabs(fabs(z) - fabs(x)) > EIG_TOL;            // max_lane |z - x| > tol, as one warp vote
         x = z;
         if (!__any_sync(FULL, moving)) { ok = true; break; }
     }
@@ -269,7 +329,7 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
     if (r >= N) { sbuf[lane] = 0.0; sbuf[32 + lane] = 0.0; }
 #if TVF_GJ_PIPE
     double colj = g[0];                          // software-pipelined as in smallest_eigvec_spd
-    double piv = fast_rcp(fmax(__shfl_sync(FULL, colj, 0, 16), floor_piv));
+    double piv = fast_rcp(pivot_floor(__shfl_sync(FULL, colj, 0, 16), floor_piv));
     double rk = colj * piv;
     if (r < N) sbuf[h16 + r] = rk;
 #pragma unroll
@@ -282,7 +342,7 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
             const double2 q = b2[(k + 1) >> 1];
             g[k + 1] = fma(-c, ((k + 1) & 1) ? q.y : q.x, g[k + 1]);
             colj_n = g[k + 1];
-            piv_n = fast_rcp(fmax(__shfl_sync(FULL, colj_n, k + 1, 16), floor_piv));
+            piv_n = fast_rcp(pivot_floor(__shfl_sync(FULL, colj_n, k + 1, 16), floor_piv));
             rk_n = colj_n * piv_n;
             if (r < N) sbuf[((k + 1) & 1) * 32 + h16 + r] = rk_n;
         }
@@ -295,11 +355,30 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
         g[k] = (r == k) ? -piv : rk;
         colj = colj_n; piv = piv_n; rk = rk_n;
     }
+#elif TVF_GJ_RAWCOL
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const double colj = g[k];
+        double* buf = sbuf + (k & 1) * 32 + h16;
+        if (r < N) buf[r] = colj;
+        const double d = pivot_floor(__shfl_sync(FULL, colj, k, 16), floor_piv);
+        const double piv = fast_rcp(d);
+        __syncwarp();
+        const double cs = (colj - ((r == k) ? 1.0 : 0.0)) * piv;
+        const double2* b2 = reinterpret_cast<const double2*>(buf);
+#pragma unroll
+        for (int m2 = 0; m2 < 8; ++m2) {
+            const double2 q = b2[m2];
+            if (2 * m2 != k && 2 * m2 < N) g[2 * m2] = fma(-cs, q.x, g[2 * m2]);
+            if (2 * m2 + 1 != k && 2 * m2 + 1 < N) g[2 * m2 + 1] = fma(-cs, q.y, g[2 * m2 + 1]);
+        }
+        g[k] = (r == k) ? -piv : colj * piv;
+    }
 #else
 #pragma unroll
     for (int k = 0; k < N; ++k) {
         const double colj = g[k];
-        const double d = fmax(__shfl_sync(FULL, colj, k, 16), floor_piv);
+        const double d = pivot_floor(__shfl_sync(FULL, colj, k, 16), floor_piv);
         const double piv = fast_rcp(d);
         const double rk = colj * piv;
         double* buf = sbuf + (k & 1) * 32 + h16;
@@ -338,7 +417,7 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
         const unsigned hmax = __reduce_max_sync(hmask, hz);
         const int piv = __ffs(__ballot_sync(hmask, hz == hmax)) - 1;
         z *= fast_rcp(shfl_d(z, piv));
-        const bool moving = !done && (fabs(z - x) > EIG_TOL);
+        const bool moving = !done && (fabs(fabs(z) - fabs(x)) > EIG_TOL);
         if (!done) x = z;
         const unsigned bal = __ballot_sync(FULL, moving);
         done = done || ((bal & hmask) == 0u);
@@ -347,6 +426,143 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
     x *= rsqrt_(half_sum(x * x));
     *converged = done;
     return x;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Two problems per warp for systems of up to 32 unknowns: half h of the warp owns problem h and lane r of a half owns
+// the TWO rows r and r + NR of its matrix (NR = ceil(N/2) <= 16; N = 27: rows r and r + 14, lanes 14 and 15 idle).
+// Compared with one row per lane on a full warp, a Gauss-Jordan sweep still costs one DFMA per matrix element, but the
+// pivot-row read-back (N/2 broadcast 128-bit shared loads), the pivot's reciprocal chain, the publication and the
+// barrier are issued once per TWO problems: 31 FP64 + 13 other instructions per problem and sweep instead of 34 + 30.
+//
+// The caller passes a matrix that is ALREADY scaled to unit trace and shifted (G/tr + delta*I): the 27 x 27 Gram is
+// gathered from a moment table, so scaling the table (96 multiplications) replaces scaling the matrix (729) and the
+// diagonal-extraction select chain.  Rows >= N (the second row of the last lanes) must be passed as zeros: they are
+// never pivots and stay zero.  sbuf: 128 doubles, 16-byte aligned; half h uses [32 h, 32 h + 32) of each 64-double
+// parity buffer.  Nothing crosses between the halves except the loop-exit vote (each half freezes its iterate when IT
+// has converged), so a problem's result does not depend on its neighbour.
+#ifndef TVF_GJ2_PIPE
+#define TVF_GJ2_PIPE 1
+#endif
+template <int N>
+__device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], double (&g1)[N], const int lane, double* sbuf,
+                                                          double* x0_out, double* x1_out, bool* converged) {
+    static_assert(N <= 32 && N >= 4, "two matrix rows per lane of a half-warp");
+    constexpr int NR = (N + 1) / 2;
+    constexpr int NP = (N + 1) & ~1;
+    const int r = lane & 15, h32 = (lane & 16) * 2;          // offset of this half's 32-double segment
+    const unsigned hmask = 0xffffu << (lane & 16);
+    const double floor_piv = 1.0e-3 * (1.0e-13 / N);
+    const bool own0 = r < NR, own1 = r + NR < N;
+    __syncwarp();                              // sbuf may still be read by a previous phase
+    if (r == 0) {                              // padding entry of the row buffers (odd N)
+        if (NP > N) { sbuf[h32 + N] = 0.0; sbuf[64 + h32 + N] = 0.0; }
+    }
+#if TVF_GJ2_PIPE
+    // Software-pipelined sweeps, written for ONE or TWO resident warps per scheduler (255 registers): every warp has to keep
+    // the FP64 pipe busy on its own.  (1) All N/2 broadcast loads of pivot row k are issued at once, right behind the
+    // barrier, so the DFMAs never wait for shared memory one load at a time.  (2) Sweep k updates column k+1 FIRST and
+    // then starts sweep k+1's serial chain -- pivot shuffle, reciprocal, scaled column, publication into the other
+    // parity buffer -- which completes under the remaining 2(N-2) DFMAs of sweep k.  Same operations on the same
+    // operands as the plain loop below: bit-identical results.
+    const int dst0 = own0 ? r : 30, dst1 = own1 ? NR + r : 31;      // idle lanes write two unused slots of the segment
+    double c0j = g0[0], c1j = g1[0];
+    double piv = fast_rcp(pivot_floor(__shfl_sync(FULL, c0j, 0, 16), floor_piv));
+    double r0 = c0j * piv, r1 = c1j * piv;
+    sbuf[h32 + dst0] = r0; sbuf[h32 + dst1] = r1;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int a = (k >= NR) ? 1 : 0, rk = k - a * NR;     // pivot row k lives on lane rk of each half, array a
+        __syncwarp();                          // row k is in parity buffer k & 1; the other one is free again
+        const double2* b2 = reinterpret_cast<const double2*>(sbuf + (k & 1) * 64 + h32);
+        double2 q[NP / 2];
+#pragma unroll
+        for (int m2 = 0; m2 < NP / 2; ++m2) q[m2] = b2[m2];
+        const double c0 = c0j - ((a == 0 && r == rk) ? 1.0 : 0.0);
+        const double c1 = c1j - ((a == 1 && r == rk) ? 1.0 : 0.0);
+        double n0j = 0.0, n1j = 0.0, npiv = 0.0, nr0 = 0.0, nr1 = 0.0;
+        if (k + 1 < N) {
+            const int an = (k + 1 >= NR) ? 1 : 0, rkn = k + 1 - an * NR;
+            const double v = ((k + 1) & 1) ? q[(k + 1) >> 1].y : q[(k + 1) >> 1].x;
+            g0[k + 1] = fma(-c0, v, g0[k + 1]); g1[k + 1] = fma(-c1, v, g1[k + 1]);
+            n0j = g0[k + 1]; n1j = g1[k + 1];
+            npiv = fast_rcp(pivot_floor(__shfl_sync(FULL, an ? n1j : n0j, rkn, 16), floor_piv));
+            nr0 = n0j * npiv; nr1 = n1j * npiv;
+            double* bn = sbuf + ((k + 1) & 1) * 64 + h32;
+            bn[dst0] = nr0; bn[dst1] = nr1;
+        }
+#pragma unroll
+        for (int m2 = 0; m2 < NP / 2; ++m2) {
+            if (2 * m2 != k && 2 * m2 != k + 1 && 2 * m2 < N) { g0[2 * m2] = fma(-c0, q[m2].x, g0[2 * m2]); g1[2 * m2] = fma(-c1, q[m2].x, g1[2 * m2]); }
+            if (2 * m2 + 1 != k && 2 * m2 + 1 != k + 1 && 2 * m2 + 1 < N) { g0[2 * m2 + 1] = fma(-c0, q[m2].y, g0[2 * m2 + 1]); g1[2 * m2 + 1] = fma(-c1, q[m2].y, g1[2 * m2 + 1]); }
+        }
+        g0[k] = (a == 0 && r == rk) ? -piv : r0;
+        g1[k] = (a == 1 && r == rk) ? -piv : r1;
+        c0j = n0j; c1j = n1j; piv = npiv; r0 = nr0; r1 = nr1;
+    }
+#else
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int a = (k >= NR) ? 1 : 0, rk = k - a * NR;     // pivot row k lives on lane rk of each half, array a
+        const double c0j = g0[k], c1j = g1[k];
+        const double d = pivot_floor(__shfl_sync(FULL, a ? c1j : c0j, rk, 16), floor_piv);
+        const double piv = fast_rcp(d);
+        const double r0 = c0j * piv, r1 = c1j * piv;
+        double* buf = sbuf + (k & 1) * 64 + h32;
+        if (own0) buf[r] = r0;
+        if (own1) buf[NR + r] = r1;
+        __syncwarp();
+        const double c0 = c0j - ((a == 0 && r == rk) ? 1.0 : 0.0);
+        const double c1 = c1j - ((a == 1 && r == rk) ? 1.0 : 0.0);
+        const double2* b2 = reinterpret_cast<const double2*>(buf);
+#pragma unroll
+        for (int m2 = 0; m2 < NP / 2; ++m2) {
+            const double2 q = b2[m2];
+            if (2 * m2 != k && 2 * m2 < N) { g0[2 * m2] = fma(-c0, q.x, g0[2 * m2]); g1[2 * m2] = fma(-c1, q.x, g1[2 * m2]); }
+            if (2 * m2 + 1 != k && 2 * m2 + 1 < N) { g0[2 * m2 + 1] = fma(-c0, q.y, g0[2 * m2 + 1]); g1[2 * m2 + 1] = fma(-c1, q.y, g1[2 * m2 + 1]); }
+        }
+        g0[k] = (a == 0 && r == rk) ? -piv : r0;
+        g1[k] = (a == 1 && r == rk) ? -piv : r1;
+    }
+#endif
+    __syncwarp();
+    // g holds -(G + delta I)^-1.  Pivot-normalised power iteration (see smallest_eigvec_spd), per half.
+    double x0 = own0 ? 1.0 : 0.0, x1 = own1 ? 1.0 : 0.0;
+    bool done = false;                          // uniform within a half
+#pragma unroll 1
+    for (int it = 0; it < EIG_MAX_ITER; ++it) {
+        double* buf = sbuf + (it & 1) * 64 + h32;
+        if (own0) buf[r] = x0;
+        if (own1) buf[NR + r] = x1;
+        __syncwarp();
+        const double2* b2 = reinterpret_cast<const double2*>(buf);
+        // four independent accumulation chains per row (the mat-vec is latency bound: 3 resident warps per scheduler)
+        double a0[4] = {0.0, 0.0, 0.0, 0.0}, a1[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int m2 = 0; m2 < NP / 2; ++m2) {
+            const double2 q = b2[m2];
+            const int c = (m2 & 1) * 2;
+            if (2 * m2 < N) { a0[c] = fma(g0[2 * m2], q.x, a0[c]); a1[c] = fma(g1[2 * m2], q.x, a1[c]); }
+            if (2 * m2 + 1 < N) { a0[c + 1] = fma(g0[2 * m2 + 1], q.y, a0[c + 1]); a1[c + 1] = fma(g1[2 * m2 + 1], q.y, a1[c + 1]); }
+        }
+        double z0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), z1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+        const unsigned h0 = (unsigned)__double2hiint(z0) & 0x7fffffffu, h1 = (unsigned)__double2hiint(z1) & 0x7fffffffu;
+        const unsigned hmax = __reduce_max_sync(hmask, max(h0, h1));
+        const unsigned bal0 = __ballot_sync(hmask, h0 == hmax) & hmask;
+        const unsigned bal1 = __ballot_sync(hmask, h1 == hmax) & hmask;
+        const int src = __ffs(bal0 ? bal0 : bal1) - 1;
+        const double pv = shfl_d(bal0 ? z0 : z1, src);
+        const double ip = fast_rcp(pv);
+        z0 *= ip; z1 *= ip;
+        const bool moving = !done && ((fabs(fabs(z0) - fabs(x0)) > EIG_TOL) || (fabs(fabs(z1) - fabs(x1)) > EIG_TOL));
+        if (!done) { x0 = z0; x1 = z1; }
+        const unsigned bal = __ballot_sync(FULL, moving);
+        done = done || ((bal & hmask) == 0u);
+        if (bal == 0u) break;
+    }
+    const double nn = rsqrt_(half_sum(x0 * x0 + x1 * x1));
+    *x0_out = x0 * nn; *x1_out = x1 * nn;
+    *converged = done;
 }
 
 }  // namespace tvf

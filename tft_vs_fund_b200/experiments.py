@@ -93,3 +93,78 @@ def run_sweep_device(total_trials, n=20, methods=(1, 7), noise_levels=NOISE_LEVE
     if rank == 0:
         run_sweep_device.last_skipped = skipped
     return out if rank == 0 else None
+
+
+# ---- the four experiments of experiments.m:23-47 -------------------------------------------------------------
+INTERVALS = {                                                                     # experiments.m:38-47
+    "noise": [0.25 * k for k in range(13)],                                      # 0:0.25:3
+    "focal": list(range(20, 301, 20)),                                           # 20:20:300
+    "points": [7, 8, 9, 10, 15, 20, 25],                                         # [7:9,10:5:25]
+    "angle": [166, 168, 170, 172, 174, 175, 176, 177, 178, 179, 179.5, 180],     # [166:2:174,175:179,179.5,180]
+}
+
+
+def experiment_levels(option, N=12, noise=1.0, f=50, angle=0, interval=None):
+    """The per-level parameters (N, noise, f, angle) of experiments.m:74-89 for `option`; defaults are :30-33."""
+    interval = INTERVALS[option] if interval is None else list(interval)
+    out = []
+    for v in interval:
+        p = dict(N=int(N), noise=float(noise), f=f, angle=angle)
+        p[{"noise": "noise", "focal": "f", "points": "N", "angle": "angle"}[option]] = int(v) if option == "points" else v
+        out.append(p)
+    return interval, out
+
+
+def run_experiment(option, n_sim=20, methods=(1, 7), N=12, noise=1.0, f=50, angle=0, interval=None, device=None):
+    """experiments.m for one `option`, device-resident (tvf_sweep_run_levels): level i x seeds 1..n_sim x methods.  Sharded
+    like run_sweep (contiguous ranges of the global trial index j = (seed-1)*L + level).  Returns on rank 0
+    (interval, dict method -> (L, 3) mean [repr_err, rot_err, t_err]; inf where the reference skips the method for lack
+    of matches, experiments.m:99-104), None elsewhere."""
+    import ctypes as C
+    interval, params = experiment_levels(option, N, noise, f, angle, interval)
+    L = len(params)
+    levels = (_lib.SweepLevel * L)()
+    for lv, p in zip(levels, params):
+        K, Ps, R_t0 = scene.scene_cameras(p["f"], p["angle"])
+        lv.noise, lv.n = p["noise"], p["N"]
+        lv.P[:] = np.ascontiguousarray(np.stack(Ps)).ravel()
+        lv.calm[:] = np.tile(K, (3, 1)).T.ravel()
+        lv.Rt0_2[:] = R_t0[0].T.ravel(); lv.Rt0_3[:] = R_t0[1].T.ravel()
+    rank, size = sharding.world()
+    lo, hi = sharding.shard_range(L * n_sim, rank, size)
+    h = _lib.handle(device)
+    out, skipped = {}, {}
+    for m in methods:
+        table = np.zeros((L, 5))
+        h.call("tvf_sweep_run_levels", int(m), lo, hi - lo, levels, L, 36 * scene.PIX, 24 * scene.PIX,
+               table.ctypes.data_as(_lib.c_double_p))
+        unavailable = np.isinf(table[:, 0])
+        table[unavailable, :3] = 0.0
+        total = sharding.sum_in_rank_order(table)
+        if total is not None:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                out[m] = total[:, :3] / total[:, 3:4]
+            out[m][unavailable] = np.inf
+            skipped[m] = total[:, 4].astype(np.int64)
+    if rank == 0:
+        run_experiment.last_skipped = skipped
+    return (interval, out) if rank == 0 else None
+
+
+def run_experiment_host(option, n_sim=20, methods=(1, 7), N=12, noise=1.0, f=50, angle=0, interval=None, device=None):
+    """The same experiment driven from the host (inputs from scene.sweep_batch, one batched solver call per level and
+    method, NumPy reduction): the twin the tests hold run_experiment against."""
+    interval, params = experiment_levels(option, N, noise, f, angle, interval)
+    out = {m: np.zeros((len(params), 3)) for m in methods}
+    for i, p in enumerate(params):
+        d = scene.sweep_batch(n_sim, p["N"], noise_levels=[p["noise"]], focalL=p["f"], angle=p["angle"])
+        for m in methods:
+            if (m > 6 and p["N"] < 8) or p["N"] < 7:                                                 # experiments.m:99-104
+                out[m][i] = np.inf
+                continue
+            res = METHODS[m][1](d["Corresp"], d["CalM"], device=device)
+            repr_err, rot_err, t_err = evaluate(res, d["R_t0"], device=device)
+            bad = (np.asarray(res.status) & (_lib.ST_NO_POSE_2 | _lib.ST_NO_POSE_3 | _lib.ST_NONFINITE)) != 0
+            sums = level_sums(np.zeros(n_sim, dtype=np.int64), 1, repr_err, rot_err, t_err, bad=bad)
+            out[m][i] = sums[0, :3] / sums[0, 3]
+    return interval, out

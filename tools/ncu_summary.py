@@ -109,6 +109,17 @@ def counters_json(rep, out, problems_per_launch):
             "registers": num(r, "launch__registers_per_thread"),
             "launched_as": launched,
         }
+        # executed FP64 thread-instructions of this launch: <op>.sum.per_cycle_elapsed x smsp__cycles_elapsed.avg
+        cyc = num(r, "smsp__cycles_elapsed.avg")
+        ops = {}
+        for op in ("dfma", "dmul", "dadd"):
+            v = num(r, "smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed" % op)
+            ops[op] = v * cyc if (v is not None and cyc is not None) else None
+        k = out_d["kernels"][name]
+        k["fp64_thread_inst_per_launch"] = ops
+        if all(v is not None for v in ops.values()):
+            k["fp64_flop_per_launch"] = 2.0 * ops["dfma"] + ops["dmul"] + ops["dadd"]
+            k["achieved_occupancy_pct"] = num(r, "sm__warps_active.avg.pct_of_peak_sustained_active")
     json.dump(out_d, open(out, "w"), indent=1)
 
 
