@@ -80,6 +80,10 @@ void tvf_host_free(void* p);
  * duration of each host-pointer pose call and released before it returns; off (default): pageable buffers take the
  * CUDA runtime's staged copies */
 int tvf_set_host_register(tvf_handle_t h, int on);
+/* Pageable caller buffers are otherwise staged chunk by chunk through pinned per-slot buffers, filled and drained by
+ * `threads` host threads (0 = automatic: hardware threads / devices of the handle, clamped to 2..8), so the copies still
+ * overlap the kernels.  Pinned buffers (tvf_host_alloc, cudaHostRegister) are used in place. */
+int tvf_set_host_threads(tvf_handle_t h, int threads);
 
 /* ---- method entry points (host pointers; copies are inside the call) ------------------- */
 

@@ -50,6 +50,40 @@ int hc_dlt(const double* rows, int M, double* x) {
     return it;
 }
 
+// Certified depth signs (dlt4_depth_signs) against the accurate route on every point and candidate of a problem:
+// counts[0] = DLTs examined, counts[1] = answered by the shortcut, counts[2] = shortcut answers that DIFFER from the
+// accurate route's signs (must stay 0).
+void hc_vote_signs_check(int mode, const double* model, const double* CalM, const double* corresp, int n, long long* counts) {
+    double cand[CAND_SIZE];
+    if (mode == 0) candidates_from_tft(model, CalM, cand); else candidates_from_f(model, model + 9, CalM, cand);
+    double P1[12];
+    load_K1_as_P1(CalM, P1);
+    for (int i = 0; i < n; ++i) {
+        const double* p = corresp + 6 * i;
+        double ra[4], rb[4];
+        dlt_rows(P1, p[0], p[1], ra, rb);
+        for (int pair = 0; pair < 2; ++pair)
+            for (int q = 0; q < 2; ++q) {
+                double P[12], r3[3], tz;
+                candidate_camera(cand + pair * CAND_PAIR, q == 0 ? 0 : 3, P, r3, &tz);
+                double a[4][4], b[4][4];
+                for (int e = 0; e < 4; ++e) { a[0][e] = ra[e]; a[1][e] = rb[e]; }
+                dlt_rows(P, p[2 + 2 * pair], p[3 + 2 * pair], a[2], a[3]);
+                for (int r = 0; r < 4; ++r) for (int e = 0; e < 4; ++e) b[r][e] = a[r][e];
+                counts[0] += 1;
+                int sx, sz;
+                if (!dlt4_depth_signs(a, r3, tz, &sx, &sz)) continue;
+                counts[1] += 1;
+                double X[4];
+                dlt_null<4>(b, X);
+                const double iw = 1.0 / X[3];
+                const double X0 = X[0] * iw, X1 = X[1] * iw, X2 = X[2] * iw, X3 = X[3] * iw;
+                const double z2 = r3[0] * X0 + r3[1] * X1 + r3[2] * X2 + tz * X3;
+                if ((int)sign_(X2) != sx || (int)sign_(z2) != sz) counts[2] += 1;
+            }
+    }
+}
+
 // Whole pose tail on one problem, stage by stage exactly as the kernels chain them.
 // mode 0: `model` is T (27, pixel coordinates); mode 1: `model` is [F21(9) F31(9)].
 int hc_pose_tail(int mode, const double* model, const double* CalM, const double* corresp, int n,

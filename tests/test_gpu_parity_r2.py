@@ -366,3 +366,45 @@ def test_device_resident_experiment_sharded_ranges(tvf):
     parts = run(0, cut) + run(cut, B - cut)
     assert np.array_equal(whole[:, 3:], parts[:, 3:]) and int(whole[:, 3].sum()) == B
     assert np.max(np.abs(whole[:, :3] - parts[:, :3]) / np.abs(whole[:, :3])) < 1e-12
+
+
+def test_pageable_staged_path_equals_pinned_path(tvf):
+    """Pageable caller buffers (NumPy arrays, an mxArray's data) go through pinned per-slot staging buffers filled and
+    drained by host threads; pinned buffers (tvf_host_alloc) are used in place.  Same bits either way, for any thread
+    count, also through a group handle."""
+    import ctypes as C
+    from tft_vs_fund_b200 import scene, _lib
+    B, n = 150_001, 20                                        # > 4 MB of input: staged; not a multiple of the chunk
+    d = scene.sweep_batch(B, n, first_trial=7, workers=min(16, os.cpu_count() or 1))
+    ref = _outputs(tvf.LinearTFTPoseEstimation(d["Corresp"], d["CalM"]))
+    h = _lib.handle(0)
+    lib = h.lib
+    c = np.ascontiguousarray(d["Corresp"].transpose(0, 2, 1))
+    calm = np.ascontiguousarray(d["CalM"].T)
+    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
+
+    def pinned(shape, dtype=np.float64):
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = lib.tvf_host_alloc(nbytes)
+        assert p
+        return np.frombuffer((C.c_char * nbytes).from_address(p), dtype=dtype).reshape(shape), p
+    bufs = [pinned((B, n, 6)), pinned((B, 12)), pinned((B, 12)), pinned((B, 3 * n)), pinned((B, 27)), pinned((B,)), pinned((B,), np.int32)]
+    try:
+        bufs[0][0][...] = c
+        h.call("tvf_linear_tft_pose", dp(bufs[0][0]), dp(calm), 0, n, B, dp(bufs[1][0]), dp(bufs[2][0]), dp(bufs[3][0]), dp(bufs[4][0]),
+               dp(bufs[5][0]), bufs[6][0].ctypes.data_as(_lib.c_int32_p))
+        assert np.array_equal(bufs[5][0], ref[4]) and np.array_equal(bufs[6][0], ref[5])
+        assert np.array_equal(bufs[4][0].reshape(B, 3, 3, 3).transpose(0, 3, 2, 1), ref[3])
+        for threads in (1, 3):
+            h.call("tvf_set_host_threads", threads)
+            got = _outputs(tvf.LinearTFTPoseEstimation(d["Corresp"], d["CalM"]))
+            for a, b in zip(ref, got):
+                assert np.array_equal(a, b, equal_nan=True), threads
+    finally:
+        h.call("tvf_set_host_threads", 0)
+        for _, p in bufs:
+            lib.tvf_host_free(C.c_void_p(p))
+    got = _outputs(tvf.LinearFPoseEstimation(d["Corresp"][:120_000], d["CalM"], device=(0, 0)))
+    one = _outputs(tvf.LinearFPoseEstimation(d["Corresp"][:120_000], d["CalM"], device=0))
+    for a, b in zip(one, got):
+        assert np.array_equal(a, b, equal_nan=True)

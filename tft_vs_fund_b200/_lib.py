@@ -55,6 +55,7 @@ SIGNATURES = {
     "tvf_create_multi": (_I, [C.POINTER(_H), C.POINTER(C.c_int), _I]),
     "tvf_num_devices": (_I, [_H]),
     "tvf_set_host_register": (_I, [_H, _I]),
+    "tvf_set_host_threads": (_I, [_H, _I]),
     "tvf_pose": (_I, [_H, _I, _D, _D, _I, _I, _L, C.POINTER(PoseOut)]),
     "tvf_pose_dev": (_I, [_H, _I, C.c_void_p, C.c_void_p, _I, _I, _L, C.POINTER(PoseOut)]),
     "tvf_destroy": (None, [_H]),

@@ -68,6 +68,12 @@ struct tvf_context {
     std::vector<tvf_context*> peers;
     // tvf_set_host_register: pin caller buffers that are pageable for the duration of a host-pointer pose call
     int host_register = 0;
+    // pageable caller buffers (an mxArray's data): chunks travel through per-slot pinned staging buffers filled / drained by
+    // a few host threads, so the DMA engines see pinned memory and the three-slot pipeline keeps overlapping
+    int host_threads = 0;                 // 0 = automatic
+    int group_size = 1;                   // members of the group handle this context belongs to
+    void* stage[NSLOT] = {};
+    size_t stage_cap[NSLOT] = {};
 };
 
 namespace {
@@ -261,6 +267,38 @@ int count_flagged(const int32_t* st, int64_t B) {
     return (int)(c > 0x7fffffff ? 0x7fffffff : c);
 }
 
+// copy `bytes` with `nthreads` host threads (a single memcpy stream reaches ~10 GB/s, far below what the PCIe link moves)
+void par_memcpy(void* dst, const void* src, size_t bytes, int nthreads) {
+    if (bytes == 0) return;
+    if (nthreads <= 1 || bytes < (4u << 20)) { memcpy(dst, src, bytes); return; }
+    const size_t part = ((bytes / (size_t)nthreads) + 4095) & ~size_t(4095);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nthreads; ++t) {
+        const size_t lo = (size_t)t * part;
+        if (lo >= bytes) break;
+        const size_t len = (lo + part <= bytes) ? part : bytes - lo;
+        th.emplace_back([=] { memcpy((char*)dst + lo, (const char*)src + lo, len); });
+    }
+    memcpy(dst, src, part < bytes ? part : bytes);
+    for (auto& t : th) t.join();
+}
+
+bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+int ensure_stage(tvf_handle_t h, int slot, size_t bytes) {
+    if (h->stage_cap[slot] >= bytes) return TVF_OK;
+    if (h->stage[slot]) { cudaFreeHost(h->stage[slot]); h->stage[slot] = nullptr; h->stage_cap[slot] = 0; }
+    cudaError_t e = cudaHostAlloc(&h->stage[slot], bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(h, TVF_ERR_NOMEM, std::string("cudaHostAlloc(staging): ") + cudaGetErrorString(e)); }
+    h->stage_cap[slot] = bytes;
+    return TVF_OK;
+}
+
 // outputs of a pose call (any may be null); `votes` = 10 int32 per problem: the 4 + 4 cheirality votes of
 // R_t_from_TFT.m:91-104 in the reference's candidate order for the pairs (1,2) and (1,3), then the two NaN masks
 struct PoseOut {
@@ -295,6 +333,26 @@ int pose_host_one(tvf_handle_t h, Method method, const double* corresp, const do
     TVF_CK(cudaStreamSynchronize(h->slot[0].stream));
     if (h->use_user_stream) TVF_CK(cudaStreamSynchronize(h->user_stream));
 
+    // Pageable caller memory (what a MEX gateway receives): cudaMemcpyAsync would fall back to synchronous copies through
+    // the runtime's own bounce buffer and serialise the pipeline (measured 6.6e6 solves/s against 4.5e7 with pinned
+    // buffers).  Instead every chunk goes through a pinned per-slot staging buffer that a few host threads fill and drain.
+    const bool staged = !h->host_register && (size_t)B * 6 * n * sizeof(double) >= (size_t(4) << 20) &&
+                        (is_pageable(corresp) || is_pageable(o.Rt2) || is_pageable(o.reconst) || is_pageable(o.T) || is_pageable(o.repr_err));
+    int nthreads = h->host_threads;
+    if (nthreads <= 0) {
+        const int hw = (int)std::thread::hardware_concurrency();
+        nthreads = hw / (h->group_size > 0 ? h->group_size : 1);
+        nthreads = nthreads < 2 ? 2 : (nthreads > 8 ? 8 : nthreads);
+    }
+    struct Drain { void* dst; const void* src; size_t bytes; };
+    std::vector<Drain> pending[NSLOT];
+    auto drain = [&](int slot) {
+        for (const Drain& d : pending[slot]) par_memcpy(d.dst, d.src, d.bytes, nthreads);
+        pending[slot].clear();
+    };
+    const size_t in_bytes_max = (size_t)C * 6 * n * sizeof(double) + (calm_batched ? (size_t)C * 27 * sizeof(double) : 0);
+    const size_t out_bytes_max = (size_t)C * ((24 + 3 * n + 27 + 1 + 18) * sizeof(double) + 12 * sizeof(int32_t));
+
     // Chunk schedule.  The call is bound by the host link (H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1
     // overlap).  Quarter- and half-size chunks at both ends, meant to shorten the pipeline's fill and drain, were
     // measured SLOWER (4.31e7 vs 4.56e7 solves/s end to end at 1 M problems, profiles/r01_variants.md) and are off.
@@ -316,34 +374,67 @@ int pose_host_one(tvf_handle_t h, Method method, const double* corresp, const do
             } else if (rem > C / 4) Bc = rem - C / 4;
             else Bc = rem;
         }
-        Slot& s = h->slot[ci % NSLOT];
+        const int si = ci % NSLOT;
+        Slot& s = h->slot[si];
         TVF_CK(cudaStreamSynchronize(s.stream));        // slot reuse: its previous chunk (incl. D2H) is finished
         rc = ensure_arena(h, s, need); if (rc) return rc;
         ChunkBufs b; carve(s.arena, n, C, true, calm_batched != 0, &b);
-        TVF_CK(cudaMemcpyAsync(b.in, corresp + done * 6 * n, (size_t)Bc * 6 * n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+        const double* src_in = corresp + done * 6 * n;
+        const double* src_calm = calm + (calm_batched ? done * 27 : 0);
+        char* stage_out = nullptr;
+        if (staged) {
+            drain(si);                                   // the slot's previous outputs leave the staging buffer first
+            rc = ensure_stage(h, si, in_bytes_max + out_bytes_max); if (rc) return rc;
+            char* st_in = (char*)h->stage[si];
+            par_memcpy(st_in, src_in, (size_t)Bc * 6 * n * sizeof(double), nthreads);
+            src_in = (const double*)st_in;
+            if (calm_batched) {
+                char* st_calm = st_in + (size_t)C * 6 * n * sizeof(double);
+                memcpy(st_calm, src_calm, (size_t)Bc * 27 * sizeof(double));
+                src_calm = (const double*)st_calm;
+            }
+            stage_out = st_in + in_bytes_max;
+        }
+        TVF_CK(cudaMemcpyAsync(b.in, src_in, (size_t)Bc * 6 * n * sizeof(double), cudaMemcpyHostToDevice, s.stream));
         // CalM travels on the chunk's own stream (ordered before the kernels that read it), shared 9x3 included
-        TVF_CK(cudaMemcpyAsync(b.calm, calm + (calm_batched ? done * 27 : 0), (size_t)(calm_batched ? Bc * 27 : 27) * sizeof(double),
-                               cudaMemcpyHostToDevice, s.stream));
+        TVF_CK(cudaMemcpyAsync(b.calm, src_calm, (size_t)(calm_batched ? Bc * 27 : 27) * sizeof(double), cudaMemcpyHostToDevice, s.stream));
         rc = run_pose_chunk(h, s.stream, method, b.in, b.calm, calm_batched, n, Bc,
                             (method == METHOD_TFT || o.T) ? b.T : nullptr, b.F, b.core, b.cand, b.votes, b.scale, b.Rt2, b.Rt3,
                             b.reconst, b.repr, b.status, b.iters, b.iter_sum);
         if (rc) return rc;
-        if (o.iter && method == METHOD_OPTF)
-            TVF_CK(cudaMemcpyAsync(o.iter + done, b.iter_sum, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-        if (o.Rt2) TVF_CK(cudaMemcpyAsync(o.Rt2 + done * 12, b.Rt2, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (o.Rt3) TVF_CK(cudaMemcpyAsync(o.Rt3 + done * 12, b.Rt3, (size_t)Bc * 12 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (o.reconst) TVF_CK(cudaMemcpyAsync(o.reconst + done * 3 * n, b.reconst, (size_t)Bc * 3 * n * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (o.T) TVF_CK(cudaMemcpyAsync(o.T + done * 27, b.T, (size_t)Bc * 27 * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (o.repr_err) TVF_CK(cudaMemcpyAsync(o.repr_err + done, b.repr, (size_t)Bc * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
-        if (o.votes) TVF_CK(cudaMemcpyAsync(o.votes + done * 10, b.votes, (size_t)Bc * 10 * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
-        if (method != METHOD_TFT && o.F21)
-            TVF_CK(cudaMemcpy2DAsync(o.F21 + done * 9, 72, b.F, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
-        if (method != METHOD_TFT && o.F31)
-            TVF_CK(cudaMemcpy2DAsync(o.F31 + done * 9, 72, b.F + 9, 144, 72, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream));
-        TVF_CK(cudaMemcpyAsync(st_host + done, b.status, (size_t)Bc * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+        // device -> host: straight into the caller's array, or into the staging buffer with a drain entry
+        size_t soff = 0;
+        auto back = [&](void* host_base, size_t per, const void* dev, size_t dev_pitch) -> cudaError_t {
+            if (!host_base) return cudaSuccess;
+            char* dst = (char*)host_base + (size_t)done * per;
+            if (staged) {
+                char* stg = stage_out + soff;
+                soff += ((size_t)C * per + 255) & ~size_t(255);
+                pending[si].push_back(Drain{dst, stg, (size_t)Bc * per});
+                dst = stg;
+            }
+            if (dev_pitch == per) return cudaMemcpyAsync(dst, dev, (size_t)Bc * per, cudaMemcpyDeviceToHost, s.stream);
+            return cudaMemcpy2DAsync(dst, per, dev, dev_pitch, per, (size_t)Bc, cudaMemcpyDeviceToHost, s.stream);
+        };
+        if (method == METHOD_OPTF) TVF_CK(back(o.iter, sizeof(int32_t), b.iter_sum, sizeof(int32_t)));
+        TVF_CK(back(o.Rt2, 12 * sizeof(double), b.Rt2, 12 * sizeof(double)));
+        TVF_CK(back(o.Rt3, 12 * sizeof(double), b.Rt3, 12 * sizeof(double)));
+        TVF_CK(back(o.reconst, (size_t)3 * n * sizeof(double), b.reconst, (size_t)3 * n * sizeof(double)));
+        TVF_CK(back(o.T, 27 * sizeof(double), b.T, 27 * sizeof(double)));
+        TVF_CK(back(o.repr_err, sizeof(double), b.repr, sizeof(double)));
+        TVF_CK(back(o.votes, 10 * sizeof(int32_t), b.votes, 10 * sizeof(int32_t)));
+        if (method != METHOD_TFT) {
+            TVF_CK(back(o.F21, 72, b.F, 144));
+            TVF_CK(back(o.F31, 72, b.F + 9, 144));
+        }
+        TVF_CK(back(st_host, sizeof(int32_t), b.status, sizeof(int32_t)));
         done += Bc; ++ci;
     }
-    for (int i = 0; i < NSLOT; ++i) TVF_CK(cudaStreamSynchronize(h->slot[i].stream));
+    for (int i = 0; i < NSLOT; ++i) {
+        const int si = (ci + i) % NSLOT;                 // oldest chunk first
+        TVF_CK(cudaStreamSynchronize(h->slot[si].stream));
+        if (staged) drain(si);
+    }
     return count_flagged(st_host, B);
 }
 
@@ -388,7 +479,7 @@ int pose_host(tvf_handle_t h, Method method, const double* corresp, const double
         if (s.iter) s.iter += lo;
         if (s.votes) s.votes += lo * 10;
         if (s.status) s.status += lo;
-        m->chunk_user = h->chunk_user;
+        m->chunk_user = h->chunk_user; m->host_threads = h->host_threads;
         rcs[(size_t)g] = pose_host_one(m, method, corresp + lo * 6 * n, calm + (calm_batched ? lo * 27 : 0), calm_batched, n, hi - lo, s);
     };
     std::vector<std::thread> th;
@@ -526,6 +617,7 @@ void tvf_destroy(tvf_handle_t h) {
     for (int i = 0; i < NSLOT; ++i) {
         if (h->slot[i].stream) { cudaStreamSynchronize(h->slot[i].stream); cudaStreamDestroy(h->slot[i].stream); }
         if (h->slot[i].arena) cudaFree(h->slot[i].arena);
+        if (h->stage[i]) cudaFreeHost(h->stage[i]);
     }
     for (int i = 0; i < NSCRATCH; ++i)
         if (h->scratch[i]) cudaFree(h->scratch[i]);
@@ -547,12 +639,20 @@ int tvf_create_multi(tvf_handle_t* out, const int* devices, int n_dev) {
         if (rc != TVF_OK) { tvf_destroy(h); return rc; }
         h->peers.push_back(m);
     }
+    h->group_size = n_dev;
+    for (tvf_handle_t m : h->peers) m->group_size = n_dev;
     cudaSetDevice(h->device);
     *out = h;
     return TVF_OK;
 }
 
 int tvf_num_devices(tvf_handle_t h) { return h ? 1 + (int)h->peers.size() : 0; }
+
+int tvf_set_host_threads(tvf_handle_t h, int threads) {
+    if (!h || threads < 0) return TVF_ERR_ARG;
+    h->host_threads = threads;
+    return TVF_OK;
+}
 
 int tvf_set_host_register(tvf_handle_t h, int on) {
     if (!h) return TVF_ERR_ARG;

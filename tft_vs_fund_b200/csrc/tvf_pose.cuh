@@ -8,6 +8,10 @@
 #ifndef TVF_CHEIR_UNROLL
 #define TVF_CHEIR_UNROLL 1
 #endif
+// votes from certified depth signs (dlt4_depth_signs) wherever the DLT solution itself is not needed
+#ifndef TVF_VOTE_FAST_SIGNS
+#define TVF_VOTE_FAST_SIGNS 1
+#endif
 
 namespace tvf {
 
@@ -143,6 +147,13 @@ TVF_HD void cheirality_point(const double* ra, const double* rb, const double* c
 #pragma unroll
         for (int e = 0; e < 4; ++e) { a[0][e] = ra[e]; a[1][e] = rb[e]; }
         dlt_rows(P, x2, y2, a[2], a[3]);
+        double* dst = (q == 0) ? Xa : Xb;
+#if TVF_VOTE_FAST_SIGNS
+        if (dst == nullptr) {          // only the two depth signs are needed: certified shortcut, else the accurate route below
+            int sx, sz;
+            if (dlt4_depth_signs(a, r3, tz, &sx, &sz)) { v[q] += sx + sz; continue; }
+        }
+#endif
         double X[4];
         dlt_null<4>(a, X);
         // X1./X1(4): one reciprocal, same inf/NaN outcomes as the division (x*inf = +-inf, 0*inf = NaN)
@@ -154,7 +165,6 @@ TVF_HD void cheirality_point(const double* ra, const double* rb, const double* c
         } else {
             v[q] += (int)sign_(X2) + (int)sign_(z2);
         }
-        double* dst = (q == 0) ? Xa : Xb;
         if (dst != nullptr) { dst[0] = X[0]; dst[1] = X[1]; dst[2] = X[2]; dst[3] = X[3]; }
     }
 }

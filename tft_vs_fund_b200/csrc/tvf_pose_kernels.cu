@@ -117,7 +117,7 @@ candidates_kernel(int mode, const double* __restrict__ model, PoseTailArgs a) {
 }
 
 // ------------------------------------------------------------------------ votes
-__global__ void __launch_bounds__(PT_THREADS)
+__global__ void __launch_bounds__(PT_THREADS, 2)
 votes_kernel(PoseTailArgs a) {
     __shared__ int sv[PT_THREADS * 10];
     const PointMap m(a.n);
@@ -176,6 +176,9 @@ __device__ __forceinline__ void load_selected(const PoseTailArgs& a, long long b
 }
 
 // ------------------------------------------------------------------------ scale
+#ifndef TVF_TAIL3_MINB
+#define TVF_TAIL3_MINB 2          // scale / final kernels of the n > 256 tail: 2 CTAs per SM (128 registers) instead of 1 (216)
+#endif
 __global__ void __launch_bounds__(PT_THREADS)
 scale_kernel(PoseTailArgs a) {
     __shared__ double rnum[PT_THREADS], rden[PT_THREADS];
@@ -255,6 +258,97 @@ final_kernel(PoseTailArgs a) {
                 for (int i = 0; i < 12; ++i) a.Rt3[b * 12 + i] = ok ? s.Rt3[i] : qnan;
             if (a.repr_err != nullptr) a.repr_err[b] = ok ? err : qnan;
             if (a.status != nullptr && st != 0) a.status[b] |= st;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- n > 128: one problem per CTA iteration.  The selected cameras (36 doubles) are computed once per problem by one
+// thread and published in shared memory instead of being rebuilt and held in 60 registers by every thread (216 -> 128
+// registers for the final pass: two CTAs per SM instead of one).
+__global__ void __launch_bounds__(PT_THREADS, 2)
+scale_large_kernel(PoseTailArgs a) {
+    __shared__ double rnum[PT_THREADS], rden[PT_THREADS];
+    __shared__ double sP[36];            // P1 | P2 | [K3*R3 | K3*t3]
+    const PointMap m(a.n);               // ppb == 1
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        if (threadIdx.x == 0) {
+            Selected s;
+            load_selected(a, b, s);
+#pragma unroll
+            for (int i = 0; i < 12; ++i) { sP[i] = s.P1[i]; sP[12 + i] = s.P2[i]; sP[24 + i] = s.KR3u3[i]; }
+        }
+        __syncthreads();
+        double num = 0.0, den = 0.0;
+        for (int pt = threadIdx.x; pt < a.n; pt += PT_THREADS) {
+            const double2* q = reinterpret_cast<const double2*>(a.corresp + (b * a.n + pt) * 6);
+            const double2 p1 = __ldg(q), p2 = __ldg(q + 1), p3 = __ldg(q + 2);
+            const double p6[6] = {p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+            double cn, cd;
+            scale_point(sP, sP + 12, sP + 24, sP + 33, p6, &cn, &cd);
+            num += cn; den += cd;
+        }
+        rnum[threadIdx.x] = num; rden[threadIdx.x] = den;
+        seg_reduce(rnum, m);
+        seg_reduce(rden, m);
+        if (threadIdx.x == 0) { a.scale[2 * b] = rnum[0]; a.scale[2 * b + 1] = rden[0]; }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(PT_THREADS, 2)
+final_large_kernel(PoseTailArgs a) {
+    __shared__ double rsq[PT_THREADS];
+    __shared__ double sP[36];
+    __shared__ int sok;
+    const PointMap m(a.n);               // ppb == 1
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        if (threadIdx.x == 0) {
+            Selected s;
+            load_selected(a, b, s);
+            const bool ok = (s.k2 >= 0 && s.k3 >= 0);
+            const double lam = -a.scale[2 * b] / a.scale[2 * b + 1];          // R_t_from_TFT.m:72-74
+#pragma unroll
+            for (int i = 0; i < 3; ++i) { s.Rt3[9 + i] *= lam; s.KR3u3[9 + i] *= lam; }
+#pragma unroll
+            for (int i = 0; i < 12; ++i) { sP[i] = s.P1[i]; sP[12 + i] = s.P2[i]; sP[24 + i] = s.KR3u3[i]; }
+            int st = 0;
+            if (s.k2 < 0) st |= ST_NO_POSE_2;
+            if (s.k3 < 0) st |= ST_NO_POSE_3;
+            bool fin = true;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) fin = fin && isfinite(s.Rt2[i]) && isfinite(s.Rt3[i]);
+            if (!fin) st |= ST_NONFINITE;
+            if (a.Rt2 != nullptr)
+#pragma unroll
+                for (int i = 0; i < 12; ++i) a.Rt2[b * 12 + i] = ok ? s.Rt2[i] : qnan;
+            if (a.Rt3 != nullptr)
+#pragma unroll
+                for (int i = 0; i < 12; ++i) a.Rt3[b * 12 + i] = ok ? s.Rt3[i] : qnan;
+            if (a.status != nullptr && st != 0) a.status[b] |= st;
+            sok = ok ? 1 : 0;
+        }
+        __syncthreads();
+        const bool ok = sok != 0;
+        double sq = 0.0;
+        for (int pt = threadIdx.x; pt < a.n; pt += PT_THREADS) {
+            const double2* q = reinterpret_cast<const double2*>(a.corresp + (b * a.n + pt) * 6);
+            const double2 p1 = __ldg(q), p2 = __ldg(q + 1), p3 = __ldg(q + 2);
+            const double p6[6] = {p1.x, p1.y, p2.x, p2.y, p3.x, p3.y};
+            double X[3];
+            sq += final_point(sP, sP + 12, sP + 24, p6, X);
+            if (a.reconst != nullptr) {
+                double* dst = a.reconst + (b * a.n + pt) * 3;
+                dst[0] = ok ? X[0] : qnan; dst[1] = ok ? X[1] : qnan; dst[2] = ok ? X[2] : qnan;
+            }
+        }
+        rsq[threadIdx.x] = sq;
+        seg_reduce(rsq, m);
+        if (threadIdx.x == 0) {
+            const double err = sqrt(rsq[0] / (3.0 * (double)a.n));                // ReprError.m:65
+            if (a.repr_err != nullptr) a.repr_err[b] = ok ? err : qnan;
+            if (a.status != nullptr && !isfinite(err)) a.status[b] |= ST_NONFINITE;
         }
         __syncthreads();
     }
@@ -664,12 +758,14 @@ void launch_votes(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
 
 void launch_scale(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
     if (a.B <= 0) return;
-    scale_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
+    if (a.n > PT_THREADS / 2) scale_large_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
+    else scale_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
 }
 
 void launch_final(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
     if (a.B <= 0) return;
-    final_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
+    if (a.n > PT_THREADS / 2) final_large_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
+    else final_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
 }
 
 void launch_tft_from_pose(const double* calm, int calm_batched, const double* Rt2, const double* Rt3, long long B,
