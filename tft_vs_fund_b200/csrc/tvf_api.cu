@@ -351,7 +351,7 @@ int pose_host_one(tvf_handle_t h, Method method, const double* corresp, const do
         pending[slot].clear();
     };
     const size_t in_bytes_max = (size_t)C * 6 * n * sizeof(double) + (calm_batched ? (size_t)C * 27 * sizeof(double) : 0);
-    const size_t out_bytes_max = (size_t)C * ((24 + 3 * n + 27 + 1 + 18) * sizeof(double) + 12 * sizeof(int32_t));
+    const size_t out_bytes_max = (size_t)C * ((24 + 3 * n + 27 + 1 + 18) * sizeof(double) + 12 * sizeof(int32_t)) + 16 * 256;   // + region alignment
 
     // Chunk schedule.  The call is bound by the host link (H2D of chunk i+1, kernels of chunk i and D2H of chunk i-1
     // overlap).  Quarter- and half-size chunks at both ends, meant to shorten the pipeline's fill and drain, were

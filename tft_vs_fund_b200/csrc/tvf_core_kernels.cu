@@ -903,6 +903,12 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
             const double* rec = ws + prob * CORE_WS_TFT;
             const double e21[3] = {rec[CW_EPI], rec[CW_EPI + 1], rec[CW_EPI + 2]};
             const double e31[3] = {rec[CW_EPI + 3], rec[CW_EPI + 4], rec[CW_EPI + 5]};
+            // normalisation statistics early: their latency hides under the arithmetic below
+            double st9[9];
+            if (normalize) {
+#pragma unroll
+                for (int q = 0; q < 9; ++q) st9[q] = rec[CW_STATS + q];
+            }
             double u1[3], u2[3], v1[3], v2[3];
             onb3(e21, u1, u2);
             onb3(e31, v1, v2);
@@ -935,33 +941,32 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
                 }
             }
             double tout = tl2;
-            if (normalize) {                                                     // LinearTFTPoseEstimation.m:53 -> transform_TFT.m:43-49
-                const double s0 = rec[CW_STATS], s1 = rec[CW_STATS + 1], s2 = rec[CW_STATS + 2];
-                const double N1[9] = {s0, 0, 0, 0, s0, 0, rec[CW_STATS + 3], rec[CW_STATS + 4], 1.0};
-                const double N2[9] = {s1, 0, 0, 0, s1, 0, rec[CW_STATS + 5], rec[CW_STATS + 6], 1.0};
-                const double N3[9] = {s2, 0, 0, 0, s2, 0, rec[CW_STATS + 7], rec[CW_STATS + 8], 1.0};
-                double N2i[9], N3i[9];
-                inv3(N2, N2i); inv3(N3, N3i);
-                if (lane == 0) {
-#pragma unroll
-                    for (int q = 0; q < 9; ++q) { sc.Nm[q] = N1[q]; sc.Nm[9 + q] = N2i[q]; sc.Nm[18 + q] = N3i[q]; }
-                }
-                __syncwarp();
+            if (normalize) {
+                // LinearTFTPoseEstimation.m:53 -> transform_TFT.m:43-49 with the three Normalize2Ddata matrices
+                // N_v = [s 0 tx; 0 s ty; 0 0 1]: T_new(:,:,i) = inv(N2) * (sum_r N1(r,i) T(:,:,r)) * inv(N3).'.  The matrices
+                // are similarities, so the sum over r has at most three terms, inv(N) = [1/s 0 -tx/s; 0 1/s -ty/s; 0 0 1] is
+                // known in closed form, and element (j,k) of the product touches rows {j, 2} and columns {k, 2} only.
+                const double s1 = st9[0], i2 = rcp_(st9[1]), i3 = rcp_(st9[2]);
+                const double t1x = st9[3], t1y = st9[4];
+                // row j of inv(N2): (a2, .., b2): out(j,:) = a2 * S(j,:) + b2 * S(2,:)   (j = 2: a2 = 1, b2 = 0)
+                const double a2 = (jr == 2) ? 1.0 : i2, b2 = (jr == 0) ? -st9[5] * i2 : ((jr == 1) ? -st9[6] * i2 : 0.0);
+                const double a3 = (kr == 2) ? 1.0 : i3, b3 = (kr == 0) ? -st9[7] * i3 : ((kr == 1) ? -st9[8] * i3 : 0.0);
                 double acc2 = 0.0;
                 if (lane < 27) {
-#pragma unroll
-                    for (int b = 0; b < 3; ++b)
-#pragma unroll
-                        for (int a = 0; a < 3; ++a) {
-                            const double sab = sc.Nm[3 * ir] * sc.T[a + 3 * b] + sc.Nm[1 + 3 * ir] * sc.T[9 + a + 3 * b] +
-                                               sc.Nm[2 + 3 * ir] * sc.T[18 + a + 3 * b];
-                            acc2 = fma(sc.Nm[9 + jr + 3 * a] * sc.Nm[18 + kr + 3 * b], sab, acc2);
-                        }
+                    // S(j',k') of slice i: i = 0,1: s1 * T_i;  i = 2: t1x T_0 + t1y T_1 + T_2
+                    auto S = [&](int jj, int kk) -> double {
+                        const int e = jj + 3 * kk;
+                        if (ir == 2) return fma(t1x, sc.T[e], fma(t1y, sc.T[9 + e], sc.T[18 + e]));
+                        return s1 * sc.T[9 * ir + e];
+                    };
+                    const double sjk = S(jr, kr), s2k = S(2, kr), sj2 = S(jr, 2), s22 = S(2, 2);
+                    // out(j,k) = sum_{j',k'} inv2(j,j') S(j',k') inv3(k,k') over j' in {j,2}, k' in {k,2}
+                    acc2 = a3 * (a2 * sjk + b2 * s2k) + b3 * (a2 * sj2 + b2 * s22);
                 }
                 tout = acc2 * rsqrt_(warp_sum(acc2 * acc2));                       // :49
             }
             if (lane < 27) Tout[prob * 27 + lane] = tout;
-            __syncwarp();                                                        // sc.T / sc.Nm are reused by the next problem
+            __syncwarp();                                                        // sc.T is reused by the next problem
         }
     }
 }

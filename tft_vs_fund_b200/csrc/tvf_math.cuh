@@ -244,7 +244,7 @@ TVF_HD void tft_epipoles(const double* T, double* e21, double* e31) {
 // Branch-free orthonormal completion {e,u1,u2} of a unit vector (Duff et al. 2017).
 TVF_HD void onb3(const double* e, double* u1, double* u2) {
     const double sg = copysign(1.0, e[2]);
-    const double a = -1.0 / (sg + e[2]);
+    const double a = -rcp_(sg + e[2]);                 // |sg + e2| >= 1: no special cases (IEEE 1/x on the host build)
     const double b = e[0] * e[1] * a;
     u1[0] = 1.0 + sg * e[0] * e[0] * a; u1[1] = sg * b; u1[2] = -sg * e[0];
     u2[0] = b; u2[1] = sg + e[1] * e[1] * a; u2[2] = -e[1];
