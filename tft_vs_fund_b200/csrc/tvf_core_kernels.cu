@@ -792,7 +792,8 @@ tft_stage2_kernel(CoreInput in, const double* __restrict__ ws, double* __restric
 struct __align__(16) Stage2DualScratch {
     double sbuf[64];
     double W[2][27 * FEAT_STRIDE + 3];   // G*Up of the two problems
-    double mom[98];
+    double mom2[2][98];                  // moments of the two problems (+ zero sentinel)
+    double es[2][16];                    // epipoles (6) + normalisation statistics (9) of the two problems
     double T[28];
     double tp[2][16];
     double Nm[28];
@@ -822,24 +823,42 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
         if (pair >= npairs) continue;
         const long long prob0 = 2 * pair;
         const int nprob = (prob0 + 1 < B) ? 2 : 1;
+        // ---- every global load of the pair is issued up front (moments, epipoles, normalisation statistics): one exposed
+        //      memory latency per pair instead of five; the epipoles stay in registers for all three phases
+        {
+            double mm[2][3];
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                const double* rec = ws + (prob0 + ((p < nprob) ? p : 0)) * CORE_WS_TFT;
+                mm[p][0] = rec[CW_MOM + lane]; mm[p][1] = rec[CW_MOM + 32 + lane]; mm[p][2] = rec[CW_MOM + 64 + lane];
+            }
+            // lane 16 p + q: epipoles (q < 6) and normalisation statistics (6 <= q < 15) of problem p -> shared memory
+            const int pq = lane >> 4, q15 = lane & 15;
+            const double* recq = ws + (prob0 + ((pq < nprob) ? pq : 0)) * CORE_WS_TFT;
+            const double ev = (q15 < 6) ? recq[CW_EPI + q15] : ((q15 < 15) ? recq[CW_STATS + q15 - 6] : 0.0);
+            __syncwarp();
+#pragma unroll
+            for (int p = 0; p < 2; ++p) {
+                sc.mom2[p][lane] = mm[p][0]; sc.mom2[p][lane + 32] = mm[p][1]; sc.mom2[p][lane + 64] = mm[p][2];
+            }
+            if (lane < 4) { sc.mom2[lane >> 1][96 + (lane & 1)] = 0.0; }
+            sc.es[pq][q15] = ev;
+            __syncwarp();
+        }
         // ---- 27-lane part, problem by problem: W = G*Up (linearTFT.m:82-84 without svd(E), see tft_stage2_kernel) ----
         for (int p = 0; p < nprob; ++p) {
-            const double* rec = ws + (prob0 + p) * CORE_WS_TFT;
-            __syncwarp();
-            sc.mom[lane] = rec[CW_MOM + lane]; sc.mom[lane + 32] = rec[CW_MOM + 32 + lane]; sc.mom[lane + 64] = rec[CW_MOM + 64 + lane];
-            if (lane == 0) { sc.mom[96] = 0.0; sc.mom[97] = 0.0; }
-            const double e21[3] = {rec[CW_EPI], rec[CW_EPI + 1], rec[CW_EPI + 2]};
-            const double e31[3] = {rec[CW_EPI + 3], rec[CW_EPI + 4], rec[CW_EPI + 5]};
+            const double* mom = sc.mom2[p];
+            const double e21[3] = {sc.es[p][0], sc.es[p][1], sc.es[p][2]};
+            const double e31[3] = {sc.es[p][3], sc.es[p][4], sc.es[p][5]};
             double u1[3], u2[3], v1[3], v2[3];
             onb3(e21, u1, u2);
             onb3(e31, v1, v2);
-            __syncwarp();
             double Ze[9], Zu1[9], Zu2[9];
 #pragma unroll
             for (int q = 0; q < 9; ++q) {
-                const double g0 = sc.mom[gidx[lane * 27 + 3 * q]];
-                const double g1 = sc.mom[gidx[lane * 27 + 3 * q + 1]];
-                const double g2 = sc.mom[gidx[lane * 27 + 3 * q + 2]];
+                const double g0 = mom[gidx[lane * 27 + 3 * q]];
+                const double g1 = mom[gidx[lane * 27 + 3 * q + 1]];
+                const double g2 = mom[gidx[lane * 27 + 3 * q + 2]];
                 Ze[q] = g0 * e21[0] + g1 * e21[1] + g2 * e21[2];
                 Zu1[q] = g0 * u1[0] + g1 * u1[1] + g2 * u1[2];
                 Zu2[q] = g0 * u2[0] + g1 * u2[1] + g2 * u2[2];
@@ -861,9 +880,9 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
         // ---- 15-lane part, both problems at once: half h = problem prob0 + h ------------------------------------
         {
             const bool live = h < nprob;
-            const double* rec = ws + (prob0 + (live ? h : 0)) * CORE_WS_TFT;
-            const double e21[3] = {rec[CW_EPI], rec[CW_EPI + 1], rec[CW_EPI + 2]};
-            const double e31[3] = {rec[CW_EPI + 3], rec[CW_EPI + 4], rec[CW_EPI + 5]};
+            const double* eh = sc.es[live ? h : 0];
+            const double e21[3] = {eh[0], eh[1], eh[2]};
+            const double e31[3] = {eh[3], eh[4], eh[5]};
             double u1[3], u2[3], v1[3], v2[3];
             onb3(e21, u1, u2);
             onb3(e31, v1, v2);
@@ -900,15 +919,9 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
         // ---- back to 27 lanes, problem by problem: t = Up*tp, P2/P3, undo the normalisation -----------------------
         for (int p = 0; p < nprob; ++p) {
             const long long prob = prob0 + p;
-            const double* rec = ws + prob * CORE_WS_TFT;
-            const double e21[3] = {rec[CW_EPI], rec[CW_EPI + 1], rec[CW_EPI + 2]};
-            const double e31[3] = {rec[CW_EPI + 3], rec[CW_EPI + 4], rec[CW_EPI + 5]};
-            // normalisation statistics early: their latency hides under the arithmetic below
-            double st9[9];
-            if (normalize) {
-#pragma unroll
-                for (int q = 0; q < 9; ++q) st9[q] = rec[CW_STATS + q];
-            }
+            const double e21[3] = {sc.es[p][0], sc.es[p][1], sc.es[p][2]};
+            const double e31[3] = {sc.es[p][3], sc.es[p][4], sc.es[p][5]};
+            const double* st9p = sc.es[p] + 6;
             double u1[3], u2[3], v1[3], v2[3];
             onb3(e21, u1, u2);
             onb3(e31, v1, v2);
@@ -946,11 +959,11 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
                 // N_v = [s 0 tx; 0 s ty; 0 0 1]: T_new(:,:,i) = inv(N2) * (sum_r N1(r,i) T(:,:,r)) * inv(N3).'.  The matrices
                 // are similarities, so the sum over r has at most three terms, inv(N) = [1/s 0 -tx/s; 0 1/s -ty/s; 0 0 1] is
                 // known in closed form, and element (j,k) of the product touches rows {j, 2} and columns {k, 2} only.
-                const double s1 = st9[0], i2 = rcp_(st9[1]), i3 = rcp_(st9[2]);
-                const double t1x = st9[3], t1y = st9[4];
+                const double s1 = st9p[0], i2 = rcp_(st9p[1]), i3 = rcp_(st9p[2]);
+                const double t1x = st9p[3], t1y = st9p[4];
                 // row j of inv(N2): (a2, .., b2): out(j,:) = a2 * S(j,:) + b2 * S(2,:)   (j = 2: a2 = 1, b2 = 0)
-                const double a2 = (jr == 2) ? 1.0 : i2, b2 = (jr == 0) ? -st9[5] * i2 : ((jr == 1) ? -st9[6] * i2 : 0.0);
-                const double a3 = (kr == 2) ? 1.0 : i3, b3 = (kr == 0) ? -st9[7] * i3 : ((kr == 1) ? -st9[8] * i3 : 0.0);
+                const double a2 = (jr == 2) ? 1.0 : i2, b2 = (jr == 0) ? -st9p[5] * i2 : ((jr == 1) ? -st9p[6] * i2 : 0.0);
+                const double a3 = (kr == 2) ? 1.0 : i3, b3 = (kr == 0) ? -st9p[7] * i3 : ((kr == 1) ? -st9p[8] * i3 : 0.0);
                 double acc2 = 0.0;
                 if (lane < 27) {
                     // S(j',k') of slice i: i = 0,1: s1 * T_i;  i = 2: t1x T_0 + t1y T_1 + T_2

@@ -329,6 +329,10 @@ TVF_HD void dlt_null(double (&a)[M][4], double* x, int* iters = nullptr) {
     double r[4][4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
+        if (M == 4 && k == 3) {          // a 1 x 1 reflection: alpha = -x1 exactly, nothing left to update (saves a sqrt and a reciprocal)
+            r[3][3] = -a[3][3];
+            break;
+        }
         double sig = 0.0;
 #pragma unroll
         for (int i = k; i < M; ++i) sig += a[i][k] * a[i][k];
