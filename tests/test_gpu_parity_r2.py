@@ -408,3 +408,28 @@ def test_pageable_staged_path_equals_pinned_path(tvf):
     one = _outputs(tvf.LinearFPoseEstimation(d["Corresp"][:120_000], d["CalM"], device=0))
     for a, b in zip(one, got):
         assert np.array_equal(a, b, equal_nan=True)
+    # staged path with a per-problem CalM (9 x 3 x B travels through the staging buffer too)
+    Bc = 70_003
+    got = _outputs(tvf.LinearTFTPoseEstimation(d["Corresp"][:Bc], np.broadcast_to(d["CalM"], (Bc, 9, 3)).copy()))
+    for a, b in zip(ref, got):
+        assert np.array_equal(a[:Bc], b, equal_nan=True)
+
+
+def test_group_handle_edge_cases(tvf):
+    """A batch smaller than the group (B < number of members), B = 1 through a group handle, B = 0, outputs not requested."""
+    import ctypes as C
+    from tft_vs_fund_b200 import scene, _lib
+    d = scene.sweep_batch(5, 20, first_trial=2)
+    one = tvf.LinearTFTPoseEstimation(d["Corresp"], d["CalM"])
+    grp = tvf.LinearTFTPoseEstimation(d["Corresp"][:2], d["CalM"], device=(0, 0, 0))
+    assert np.array_equal(grp[3], one[3][:2]) and np.array_equal(grp.votes, one.votes[:2])
+    single = tvf.LinearTFTPoseEstimation(d["Corresp"][3], d["CalM"], device=(0, 0))
+    assert np.array_equal(single[3], one[3][3]) and single.repr_err == one.repr_err[3]
+    h = _lib.handle((0, 0))
+    out = _lib.PoseOut()                                     # every member NULL: nothing is copied back, the call still runs
+    c = np.ascontiguousarray(d["Corresp"].transpose(0, 2, 1)); calm = np.ascontiguousarray(d["CalM"].T)
+    dp = lambda a: a.ctypes.data_as(_lib.c_double_p)
+    assert h.call("tvf_pose", 1, dp(c), dp(calm), 0, 20, 5, C.byref(out)) == 0
+    assert h.call("tvf_pose", 7, dp(c), dp(calm), 0, 20, 0, C.byref(out)) == 0        # B = 0
+    with pytest.raises(_lib.TvfError, match="method must be"):
+        h.call("tvf_pose", 3, dp(c), dp(calm), 0, 20, 5, C.byref(out))

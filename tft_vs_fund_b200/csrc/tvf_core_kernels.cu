@@ -589,6 +589,57 @@ tft_stage1_solve_kernel(long long B, double* __restrict__ ws, int* __restrict__ 
     }
 }
 
+// Solve-only kernel with the row-and-column split layout (smallest_eigvec_spd_cs): TVF_S1_SOLVER = 3.
+#ifndef TVF_S1C_MINB
+#define TVF_S1C_MINB 4
+#endif
+__global__ void __launch_bounds__(CORE_WARPS * 32, TVF_S1C_MINB)
+tft_stage1_solve_cs_kernel(long long B, double* __restrict__ ws, int* __restrict__ status) {
+    __shared__ Stage1Scratch scratch[CORE_WARPS];
+    __shared__ unsigned char gidx[32 * 27];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    build_gidx(gidx);
+    __syncthreads();
+    Stage1Scratch& sc = scratch[warp];
+    const int h = lane >> 4, r = lane & 15;
+    const int row0 = (r < 14) ? r : 31, row1 = (r < 13) ? r + 14 : 31;          // rows >= 27 gather the zero sentinel
+    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < B; base += (long long)gridDim.x * CORE_WARPS) {
+        STEP_SYNC();
+        const long long prob = base + warp;
+        if (prob >= B) continue;
+        double* rec = ws + prob * CORE_WS_TFT;
+        const double m0 = rec[CW_MOM + lane], m1 = rec[CW_MOM + 32 + lane], m2 = rec[CW_MOM + 64 + lane];
+        double part = 0.0;
+        part += is_diag_moment(lane) ? diag_moment_weight(lane) * m0 : 0.0;
+        part += is_diag_moment(lane + 32) ? diag_moment_weight(lane + 32) * m1 : 0.0;
+        part += is_diag_moment(lane + 64) ? diag_moment_weight(lane + 64) * m2 : 0.0;
+        const double scl = 1.0 / warp_sum(part);
+        const double delta = 1.0e-13 / 27.0;
+        __syncwarp();
+        sc.mom[lane] = fma(m0, scl, is_diag_moment(lane) ? delta : 0.0);
+        sc.mom[lane + 32] = fma(m1, scl, is_diag_moment(lane + 32) ? delta : 0.0);
+        sc.mom[lane + 64] = fma(m2, scl, is_diag_moment(lane + 64) ? delta : 0.0);
+        if (lane == 0) { sc.mom[96] = 0.0; sc.mom[97] = 0.0; }
+        __syncwarp();
+        double g0[14], g1[14];
+#pragma unroll
+        for (int c = 0; c < 14; ++c) {
+            const int col = 14 * h + c;                     // column 27 (h = 1, c = 13) is padding
+            const bool pad = (h == 1) && (c == 13);
+            g0[c] = pad ? 0.0 : sc.mom[gidx[row0 * 27 + (pad ? 0 : col)]];
+            g1[c] = pad ? 0.0 : sc.mom[gidx[row1 * 27 + (pad ? 0 : col)]];
+        }
+        double x0, x1;
+        bool conv;
+        smallest_eigvec_spd_cs<27>(g0, g1, lane, sc.sbuf, &x0, &x1, &conv);
+        if (h == 0) {
+            if (r < 14) rec[CW_T1 + r] = x0;
+            if (r < 13) rec[CW_T1 + 14 + r] = x1;
+        }
+        if (status != nullptr && lane == 0) status[prob] = conv ? 0 : ST_EIG_NOCONV;
+    }
+}
+
 // =========================================================================== TFT epipoles
 __global__ void __launch_bounds__(128, 4)
 tft_epipoles_kernel(double* __restrict__ ws, long long B) {
@@ -1168,6 +1219,8 @@ void launch_tft_stage1_solve(long long B, double* ws, int* status, int sm_count,
     if (B <= 0) return;
 #if TVF_S1_SOLVER == 2
     tft_stage1_solve_dual_kernel<<<core_grid_minb((B + 1) / 2, sm_count, TVF_S1D_MINB), CORE_WARPS * 32, 0, stream>>>(B, ws, status);
+#elif TVF_S1_SOLVER == 3
+    tft_stage1_solve_cs_kernel<<<core_grid_minb(B, sm_count, TVF_S1C_MINB), CORE_WARPS * 32, 0, stream>>>(B, ws, status);
 #else
     tft_stage1_solve_kernel<<<core_grid_minb(B, sm_count, TVF_S1S_MINB), CORE_WARPS * 32, 0, stream>>>(B, ws, status);
 #endif

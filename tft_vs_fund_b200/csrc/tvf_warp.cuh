@@ -565,4 +565,84 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
     *converged = done;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// One problem per warp, the matrix split over the lanes by ROWS AND COLUMNS: lane 16 h + r (r < 14) holds rows r and r + 14,
+// columns [14 h, 14 h + 14) -- 28 doubles, as many as one full row.  The solver is bound by shared-memory delivery (a
+// broadcast LDS.128 costs ~2 SM cycles, profiles/r02_microbench_smem_latency.txt): with one row per lane a sweep reads the
+// whole 27-entry pivot row per lane (14 LDS.128); here a lane needs only the 14 entries of its column half (7 LDS.128, two
+// addresses per instruction, same cost), its two multipliers (2 LDS.64) and the pivot (1 LDS.64): ~21 instead of ~29 SM
+// cycles per sweep for the same 27-28 DFMAs, and the power iteration's mat-vec reads 7 LDS.128 and combines the two column
+// halves with one shuffle pair.  The pivot column is published RAW (it is the pivot row by symmetry) and serves as row,
+// multipliers and pivot at once; multipliers are scaled by 1/d per lane.  g0/g1: rows r / r + 14, PRESCALED (unit trace,
+// shifted); entries of rows or columns >= N must be zero.  sbuf: 64 doubles.  Returns the components of rows r and r + 14.
+template <int N>
+__device__ __forceinline__ void smallest_eigvec_spd_cs(double (&g0)[14], double (&g1)[14], const int lane, double* sbuf,
+                                                       double* x0_out, double* x1_out, bool* converged) {
+    static_assert(N <= 28 && N > 14, "two rows x fourteen columns per lane");
+    const int h = lane >> 4, r = lane & 15;
+    const double floor_piv = 1.0e-3 * (1.0e-13 / N);
+    const bool act = r < 14;
+    const int rr = act ? r : 13;                       // lanes 14, 15 of each half idle (they mirror lane 13's loads)
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+        const int hk = k / 14, kc = k % 14;            // column k: half hk, local column kc; pivot row k: lane kc, array hk
+        double* vec = sbuf + (k & 1) * 32;
+        if (h == hk && act) { vec[r] = g0[kc]; vec[14 + r] = g1[kc]; }
+        __syncwarp();
+        const double d = vec[k];
+        const double c0 = vec[rr], c1 = vec[14 + rr];
+        const double2* v2 = reinterpret_cast<const double2*>(vec + 14 * h);
+        double2 q[7];
+#pragma unroll
+        for (int m = 0; m < 7; ++m) q[m] = v2[m];
+        const double piv = fast_rcp(pivot_floor(d, floor_piv));
+        const bool is_piv0 = (hk == 0) && (r == kc), is_piv1 = (hk == 1) && (r == kc);
+        const double cs0 = (c0 - (is_piv0 ? 1.0 : 0.0)) * piv;
+        const double cs1 = (c1 - (is_piv1 ? 1.0 : 0.0)) * piv;
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            g0[2 * m] = fma(-cs0, q[m].x, g0[2 * m]); g0[2 * m + 1] = fma(-cs0, q[m].y, g0[2 * m + 1]);
+            g1[2 * m] = fma(-cs1, q[m].x, g1[2 * m]); g1[2 * m + 1] = fma(-cs1, q[m].y, g1[2 * m + 1]);
+        }
+        if (h == hk) {                                 // column k itself: -1/d on the pivot row, (column entry)/d elsewhere
+            g0[kc] = is_piv0 ? -piv : c0 * piv;
+            g1[kc] = is_piv1 ? -piv : c1 * piv;
+        }
+    }
+    __syncwarp();
+    // g holds -(G + delta I)^-1.  Pivot-normalised power iteration; both halves carry the same iterate.
+    double x0 = act ? 1.0 : 0.0, x1 = (act && r + 14 < N) ? 1.0 : 0.0;
+    bool ok = false;
+#pragma unroll 1
+    for (int it = 0; it < EIG_MAX_ITER; ++it) {
+        double* vec = sbuf + (it & 1) * 32;
+        if (h == 0 && act) { vec[r] = x0; vec[14 + r] = x1; }
+        __syncwarp();
+        const double2* v2 = reinterpret_cast<const double2*>(vec + 14 * h);
+        double a0[2] = {0.0, 0.0}, a1[2] = {0.0, 0.0};
+#pragma unroll
+        for (int m = 0; m < 7; ++m) {
+            const double2 qq = v2[m];
+            a0[0] = fma(g0[2 * m], qq.x, a0[0]); a0[1] = fma(g0[2 * m + 1], qq.y, a0[1]);
+            a1[0] = fma(g1[2 * m], qq.x, a1[0]); a1[1] = fma(g1[2 * m + 1], qq.y, a1[1]);
+        }
+        double z0 = a0[0] + a0[1], z1 = a1[0] + a1[1];
+        z0 += __shfl_xor_sync(FULL, z0, 16); z1 += __shfl_xor_sync(FULL, z1, 16);       // the other column half
+        const unsigned h0 = (unsigned)__double2hiint(z0) & 0x7fffffffu, h1 = (unsigned)__double2hiint(z1) & 0x7fffffffu;
+        const unsigned hmax = __reduce_max_sync(FULL, max(h0, h1));
+        const unsigned bal0 = __ballot_sync(FULL, h0 == hmax), bal1 = __ballot_sync(FULL, h1 == hmax);
+        const int src = __ffs(bal0 ? bal0 : bal1) - 1;
+        const double pv = shfl_d(bal0 ? z0 : z1, src);
+        const double ip = fast_rcp(pv);
+        z0 *= ip; z1 *= ip;
+        const bool moving = (fabs(fabs(z0) - fabs(x0)) > EIG_TOL) || (fabs(fabs(z1) - fabs(x1)) > EIG_TOL);
+        x0 = z0; x1 = z1;
+        if (!__any_sync(FULL, moving)) { ok = true; break; }
+    }
+    const double nn = rsqrt_(half_sum(x0 * x0 + x1 * x1));
+    *x0_out = x0 * nn; *x1_out = x1 * nn;
+    *converged = ok;
+}
+
 }  // namespace tvf
