@@ -37,6 +37,24 @@ namespace tvf {
 #ifndef TVF_STEP_SYNC
 #define TVF_STEP_SYNC 1
 #endif
+// per-kernel overrides: the stage-2 two-problem kernel runs faster WITHOUT the barrier (26.6 against 27.4 ms per 10 M, its
+// warps' iteration counts differ), the two-problem stage-1 solver faster WITH it (40.8 against 44.3)
+#ifndef TVF_S2_SYNC
+#define TVF_S2_SYNC 0
+#endif
+#ifndef TVF_S1D_SYNC
+#define TVF_S1D_SYNC 1
+#endif
+#if TVF_S2_SYNC
+#define S2_SYNC() __syncthreads()
+#else
+#define S2_SYNC() ((void)0)
+#endif
+#if TVF_S1D_SYNC
+#define S1D_SYNC() __syncthreads()
+#else
+#define S1D_SYNC() ((void)0)
+#endif
 #if TVF_STEP_SYNC
 #define STEP_SYNC() __syncthreads()
 #else
@@ -330,7 +348,16 @@ tft_stage1_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ statu
 // registers, 20 warps per SM), 2 = two problems per warp, two rows per lane (168 registers, 12 warps per SM: 22 % fewer
 // instructions but measured 18 % SLOWER -- the per-sweep reciprocal / publish / read-back chain is exposed with so few warps)
 #ifndef TVF_S1_SOLVER
-#define TVF_S1_SOLVER 1
+#define TVF_S1_SOLVER 2
+#endif
+// 8-byte asynchronous global -> shared copy (LDGSTS) and the wait for all of this thread's copies
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+#ifndef TVF_S1D_PREFETCH
+#define TVF_S1D_PREFETCH 1
 #endif
 #ifndef TVF_S1D_MINB
 #define TVF_S1D_MINB 3
@@ -343,21 +370,11 @@ struct __align__(16) Stage1DualScratch {
     double mom[2][100];              // per half: 96 scaled + shifted moments, zero sentinel at 96
 };
 
-// moments in sc.mom[h] (raw) -> scaled to unit trace, shifted; then rows r and r + 14 -> null vector -> rec
-__device__ __forceinline__ void solve_pair_from_moments(Stage1DualScratch& sc, const unsigned char* gidx, int lane, bool live,
-                                                        double* rec, int* status, long long prob) {
+// scaled + shifted moment table in sc.mom[h] -> rows r and r + 14 -> null vector -> rec
+__device__ __forceinline__ void solve_pair_scaled(Stage1DualScratch& sc, const unsigned char* gidx, int lane, bool live,
+                                                  double* rec, int* status, long long prob) {
     const int h = lane >> 4, r = lane & 15;
-    double* mom = sc.mom[h];
-    const double tr = gram_trace_from_moments(mom);
-    const double scl = 1.0 / tr;
-    const double delta = 1.0e-13 / 27.0;
-    __syncwarp();
-#pragma unroll
-    for (int q = 0; q < 6; ++q) {
-        const int idx = q * 16 + r;
-        mom[idx] = fma(mom[idx], scl, is_diag_moment(idx) ? delta : 0.0);
-    }
-    __syncwarp();
+    const double* mom = sc.mom[h];
     const int row0 = (r < 14) ? r : 31, row1 = (r < 13) ? r + 14 : 31;          // rows >= 27 gather the zero sentinel
     double g0[27], g1[27];
 #pragma unroll
@@ -370,6 +387,25 @@ __device__ __forceinline__ void solve_pair_from_moments(Stage1DualScratch& sc, c
         if (r < 13) rec[CW_T1 + 14 + r] = x1;
         if (status != nullptr && r == 0) status[prob] = conv ? 0 : ST_EIG_NOCONV;
     }
+}
+
+// moments in sc.mom[h] (raw) -> scaled to unit trace, shifted; then rows r and r + 14 -> null vector -> rec
+// (raw: where the unscaled moments of this half lie -- sc.mom[h] itself, or the prefetch buffer of the solve-only kernel)
+__device__ __forceinline__ void solve_pair_from_moments(Stage1DualScratch& sc, const unsigned char* gidx, int lane, bool live,
+                                                        double* rec, int* status, long long prob, const double* raw) {
+    const int h = lane >> 4, r = lane & 15;
+    double* mom = sc.mom[h];
+    const double tr = gram_trace_from_moments(raw);
+    const double scl = 1.0 / tr;
+    const double delta = 1.0e-13 / 27.0;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 6; ++q) {
+        const int idx = q * 16 + r;
+        mom[idx] = fma(raw[idx], scl, is_diag_moment(idx) ? delta : 0.0);
+    }
+    __syncwarp();
+    solve_pair_scaled(sc, gidx, lane, live, rec, status, prob);
 }
 
 // Normalisation statistics and the 96 moments of one problem on one half-warp (r = lane & 15).  feat: this half's
@@ -482,7 +518,7 @@ tft_stage1_dual_kernel(CoreInput in, double* __restrict__ ws, int* __restrict__ 
         if (r < 4) sc.mom[h][96 + r] = 0.0;
         if (live) store_moments_stats(rec, r, acc, s, t);
         __syncwarp();
-        solve_pair_from_moments(sc, gidx, lane, live, rec, status, prob);
+        solve_pair_from_moments(sc, gidx, lane, live, rec, status, prob, sc.mom[h]);
     }
 }
 
@@ -527,19 +563,57 @@ tft_stage1_solve_dual_kernel(long long B, double* __restrict__ ws, int* __restri
     Stage1DualScratch& sc = scratch[warp];
     const int h = lane >> 4, r = lane & 15;
     const long long npairs = (B + 1) / 2;
+#if TVF_S1D_PREFETCH
+    // The raw moments of the NEXT pair travel global -> shared (cp.async, no registers: the solver leaves none) while this
+    // pair is solved; they land in the feature staging buffer, which the solve-only kernel does not use otherwise.
+    double* raw = sc.feat[h];
+    const long long stride = (long long)gridDim.x * CORE_WARPS;
+    {
+        const long long pair = (long long)blockIdx.x * CORE_WARPS + warp;
+        if (pair < npairs) {
+            const double* src = ws + min(2 * pair + h, B - 1) * CORE_WS_TFT + CW_MOM;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cp_async8(raw + q * 16 + r, src + q * 16 + r);
+        }
+        if (r < 4) sc.mom[h][96 + r] = 0.0;
+    }
+#endif
     for (long long base = (long long)blockIdx.x * CORE_WARPS; base < npairs; base += (long long)gridDim.x * CORE_WARPS) {
-        STEP_SYNC();
+        S1D_SYNC();
         const long long pair = base + warp;
         if (pair >= npairs) continue;
         const bool live = 2 * pair + h < B;
         const long long prob = live ? 2 * pair + h : B - 1;
         double* rec = ws + prob * CORE_WS_TFT;
+#if TVF_S1D_PREFETCH
+        cp_async_wait_all();
+        __syncwarp();
+        // scaled table -> sc.mom (two barriers inside); afterwards nobody reads `raw` any more, so the next pair's copy may
+        // start: each lane overwrites only the entries it read itself
+        const double tr = gram_trace_from_moments(raw);
+        const double scl = 1.0 / tr;
+        const double delta = 1.0e-13 / 27.0;
+        double m6[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) m6[q] = raw[q * 16 + r];
+        __syncwarp();
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sc.mom[h][q * 16 + r] = fma(m6[q], scl, is_diag_moment(q * 16 + r) ? delta : 0.0);
+        if (pair + stride < npairs) {
+            const double* src = ws + min(2 * (pair + stride) + h, B - 1) * CORE_WS_TFT + CW_MOM;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) cp_async8(raw + q * 16 + r, src + q * 16 + r);
+        }
+        __syncwarp();
+        solve_pair_scaled(sc, gidx, lane, live, rec, status, prob);
+#else
         __syncwarp();
 #pragma unroll
         for (int q = 0; q < 6; ++q) sc.mom[h][q * 16 + r] = rec[CW_MOM + q * 16 + r];
         if (r < 4) sc.mom[h][96 + r] = 0.0;
         __syncwarp();
-        solve_pair_from_moments(sc, gidx, lane, live, rec, status, prob);
+        solve_pair_from_moments(sc, gidx, lane, live, rec, status, prob, sc.mom[h]);
+#endif
     }
 }
 
@@ -557,20 +631,20 @@ tft_stage1_solve_kernel(long long B, double* __restrict__ ws, int* __restrict__ 
     build_gidx(gidx);
     __syncthreads();
     Stage1Scratch& sc = scratch[warp];
-    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < B; base += (long long)gridDim.x * CORE_WARPS) {
+    const long long stride = (long long)gridDim.x * CORE_WARPS;
+    long long prob = (long long)blockIdx.x * CORE_WARPS + warp;
+    // the three moments of this lane for the NEXT problem are fetched while the current one is being solved
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+    if (prob < B) { const double* rec = ws + prob * CORE_WS_TFT; m0 = rec[CW_MOM + lane]; m1 = rec[CW_MOM + 32 + lane]; m2 = rec[CW_MOM + 64 + lane]; }
+    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < B; base += stride, prob += stride) {
         STEP_SYNC();
-        const long long prob = base + warp;
         if (prob >= B) continue;
         double* rec = ws + prob * CORE_WS_TFT;
-        const double m0 = rec[CW_MOM + lane], m1 = rec[CW_MOM + 32 + lane], m2 = rec[CW_MOM + 64 + lane];
         // trace = sum of the 12 diagonal moments with multiplicities 4, 2, 2, 1 (gram_trace_from_moments), as one reduction
         double part = 0.0;
-        {
-            const int i0 = lane, i1 = lane + 32, i2 = lane + 64;
-            part += is_diag_moment(i0) ? diag_moment_weight(i0) * m0 : 0.0;
-            part += is_diag_moment(i1) ? diag_moment_weight(i1) * m1 : 0.0;
-            part += is_diag_moment(i2) ? diag_moment_weight(i2) * m2 : 0.0;
-        }
+        part += is_diag_moment(lane) ? diag_moment_weight(lane) * m0 : 0.0;
+        part += is_diag_moment(lane + 32) ? diag_moment_weight(lane + 32) * m1 : 0.0;
+        part += is_diag_moment(lane + 64) ? diag_moment_weight(lane + 64) * m2 : 0.0;
         const double scl = 1.0 / warp_sum(part);
         const double delta = 1.0e-13 / 27.0;
         __syncwarp();
@@ -579,6 +653,10 @@ tft_stage1_solve_kernel(long long B, double* __restrict__ ws, int* __restrict__ 
         sc.mom[lane + 64] = fma(m2, scl, is_diag_moment(lane + 64) ? delta : 0.0);
         if (lane == 0) { sc.mom[96] = 0.0; sc.mom[97] = 0.0; }
         __syncwarp();
+        if (prob + stride < B) {
+            const double* nrec = ws + (prob + stride) * CORE_WS_TFT;
+            m0 = nrec[CW_MOM + lane]; m1 = nrec[CW_MOM + 32 + lane]; m2 = nrec[CW_MOM + 64 + lane];
+        }
         double g[27];
 #pragma unroll
         for (int c = 0; c < 27; ++c) g[c] = sc.mom[gidx[lane * 27 + c]];
@@ -869,7 +947,7 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
     const long long npairs = (B + 1) / 2;
 
     for (long long base = (long long)blockIdx.x * CORE_WARPS; base < npairs; base += (long long)gridDim.x * CORE_WARPS) {
-        STEP_SYNC();
+        S2_SYNC();
         const long long pair = base + warp;
         if (pair >= npairs) continue;
         const long long prob0 = 2 * pair;

@@ -36,6 +36,9 @@ constexpr int EIG_MAX_ITER = 80;
 #ifndef TVF_GJ_RAWCOL
 #define TVF_GJ_RAWCOL 0
 #endif
+#ifndef TVF_PI_STICKY
+#define TVF_PI_STICKY 1
+#endif
 #ifndef TVF_EIG_TOL
 #define TVF_EIG_TOL 4.0e-15
 #endif
@@ -227,6 +230,9 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
     // a reciprocal instead of a five-level shuffle reduction and a reciprocal square root.  Dividing by the signed pivot
     // also removes the sign flip of -M.  One exact 2-norm normalisation follows the loop.
     double x = (lane < N) ? 1.0 : 0.0;
+#if TVF_PI_STICKY
+    int piv = 0;
+#endif
 #pragma unroll 1
     for (int it = 0; it < EIG_MAX_ITER; ++it) {
         double* buf = sbuf + (it & 1) * 32;
@@ -244,8 +250,20 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
         double z = (za[0] + za[1]) + (za[2] + za[3]);
         const unsigned hz = (unsigned)__double2hiint(z) & 0x7fffffffu;
         const unsigned hmax = __reduce_max_sync(FULL, hz);
+#if TVF_PI_STICKY
+        // the pivot lane is kept while its component stays within one binade of the largest: the shuffle runs beside the
+        // REDUX instead of behind REDUX -> ballot -> ffs, and two components of (almost) equal magnitude cannot make the
+        // normalisation alternate between them (which would never meet the tolerance although the direction converged)
+        double pv = shfl_d(z, piv);
+        if (((unsigned)__double2hiint(pv) & 0x7fffffffu) + 0x00100000u < hmax) {
+            piv = __ffs(__ballot_sync(FULL, hz == hmax)) - 1;
+            pv = shfl_d(z, piv);
+        }
+        z *= fast_rcp(pv);
+#else
         const int piv = __ffs(__ballot_sync(FULL, hz == hmax)) - 1;
         z *= fast_rcp(shfl_d(z, piv));
+#endif
         const bool moving = fabs(fabs(z) - fabs(x)) > EIG_TOL;            // max_lane |z - x| > tol, as one warp vote
         x = z;
         if (!__any_sync(FULL, moving)) { ok = true; break; }
@@ -304,6 +322,22 @@ __device__ __forceinline__ double smallest_eigvec_spd(double (&g)[N], const int 
 // solver; here both halves work.  Nothing crosses between the halves except the loop-exit vote: each half freezes its
 // iterate at the step where IT converged, so a problem's result does not depend on its neighbour (bit-reproducible under
 // any batching).  sbuf: 64 doubles; half h uses [16 h, 16 h + 16) of each 32-double parity buffer.
+// max over the 16 lanes of a half-warp with FULL-mask shuffles (xor distances < 16 stay inside the half).  Collectives with a
+// partial, lane-dependent member mask (__reduce_max_sync(0xffff << h16, ..)) compile to a WARPSYNC.COLLECTIVE loop with
+// divergent branches: ncu attributed 8 + 4 % of the two-row solver's samples to `branch_resolving` there.
+__device__ __forceinline__ unsigned half_max_u32(unsigned v) {
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(FULL, v, o));
+    return v;
+}
+
+// the same maximum as two FULL-mask REDUX operations (one per half, the other half contributing zeros): the two are
+// independent, so they pipeline, where the xor ladder is four dependent shuffles
+__device__ __forceinline__ unsigned half_max2_u32(unsigned v, int h16) {
+    const unsigned lo = __reduce_max_sync(FULL, h16 ? 0u : v), hi = __reduce_max_sync(FULL, h16 ? v : 0u);
+    return h16 ? hi : lo;
+}
+
 __device__ __forceinline__ double half_sum(double v) {
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -399,6 +433,9 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
     // g holds -(G + delta I)^-1.  Pivot-normalised power iteration (see smallest_eigvec_spd), per half.
     double x = (r < N) ? 1.0 : 0.0;
     bool done = false;                          // uniform within a half
+#if TVF_PI_STICKY
+    int piv = h16;                              // absolute lane of this half's pivot component
+#endif
 #pragma unroll 1
     for (int it = 0; it < EIG_MAX_ITER; ++it) {
         double* buf = sbuf + (it & 1) * 32 + h16;
@@ -414,9 +451,21 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
         }
         double z = z0 + z1;
         const unsigned hz = (unsigned)__double2hiint(z) & 0x7fffffffu;
-        const unsigned hmax = __reduce_max_sync(hmask, hz);
-        const int piv = __ffs(__ballot_sync(hmask, hz == hmax)) - 1;
+#if TVF_PI_STICKY
+        const unsigned hmax = half_max2_u32(hz, h16);
+        double pv = shfl_d(z, piv);
+        const bool stale = ((unsigned)__double2hiint(pv) & 0x7fffffffu) + 0x00100000u < hmax;     // uniform within a half
+        if (__any_sync(FULL, stale)) {
+            const int np = __ffs(__ballot_sync(FULL, hz == hmax) & hmask) - 1;
+            if (stale) piv = np;
+            pv = shfl_d(z, piv);
+        }
+        z *= fast_rcp(pv);
+#else
+        const unsigned hmax = half_max_u32(hz);
+        const int piv = __ffs(__ballot_sync(FULL, hz == hmax) & hmask) - 1;
         z *= fast_rcp(shfl_d(z, piv));
+#endif
         const bool moving = !done && (fabs(fabs(z) - fabs(x)) > EIG_TOL);
         if (!done) x = z;
         const unsigned bal = __ballot_sync(FULL, moving);
@@ -442,7 +491,7 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
 // parity buffer.  Nothing crosses between the halves except the loop-exit vote (each half freezes its iterate when IT
 // has converged), so a problem's result does not depend on its neighbour.
 #ifndef TVF_GJ2_PIPE
-#define TVF_GJ2_PIPE 1
+#define TVF_GJ2_PIPE 0
 #endif
 template <int N>
 __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], double (&g1)[N], const int lane, double* sbuf,
@@ -529,6 +578,10 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
     // g holds -(G + delta I)^-1.  Pivot-normalised power iteration (see smallest_eigvec_spd), per half.
     double x0 = own0 ? 1.0 : 0.0, x1 = own1 ? 1.0 : 0.0;
     bool done = false;                          // uniform within a half
+#if TVF_PI_STICKY
+    int src = lane & 16;                        // pivot component: row of array 0 (pivA) or 1 on absolute lane src
+    bool pivA = true;
+#endif
 #pragma unroll 1
     for (int it = 0; it < EIG_MAX_ITER; ++it) {
         double* buf = sbuf + (it & 1) * 64 + h32;
@@ -547,11 +600,23 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
         }
         double z0 = (a0[0] + a0[1]) + (a0[2] + a0[3]), z1 = (a1[0] + a1[1]) + (a1[2] + a1[3]);
         const unsigned h0 = (unsigned)__double2hiint(z0) & 0x7fffffffu, h1 = (unsigned)__double2hiint(z1) & 0x7fffffffu;
-        const unsigned hmax = __reduce_max_sync(hmask, max(h0, h1));
-        const unsigned bal0 = __ballot_sync(hmask, h0 == hmax) & hmask;
-        const unsigned bal1 = __ballot_sync(hmask, h1 == hmax) & hmask;
+#if TVF_PI_STICKY
+        const unsigned hmax = half_max2_u32(max(h0, h1), lane & 16);
+        double pv = shfl_d(pivA ? z0 : z1, src);
+        const bool stale = ((unsigned)__double2hiint(pv) & 0x7fffffffu) + 0x00100000u < hmax;     // uniform within a half
+        if (__any_sync(FULL, stale)) {
+            const unsigned bal0 = __ballot_sync(FULL, h0 == hmax) & hmask;
+            const unsigned bal1 = __ballot_sync(FULL, h1 == hmax) & hmask;
+            if (stale) { pivA = (bal0 != 0u); src = __ffs(bal0 ? bal0 : bal1) - 1; }
+            pv = shfl_d(pivA ? z0 : z1, src);
+        }
+#else
+        const unsigned hmax = half_max_u32(max(h0, h1));
+        const unsigned bal0 = __ballot_sync(FULL, h0 == hmax) & hmask;
+        const unsigned bal1 = __ballot_sync(FULL, h1 == hmax) & hmask;
         const int src = __ffs(bal0 ? bal0 : bal1) - 1;
         const double pv = shfl_d(bal0 ? z0 : z1, src);
+#endif
         const double ip = fast_rcp(pv);
         z0 *= ip; z1 *= ip;
         const bool moving = !done && ((fabs(fabs(z0) - fabs(x0)) > EIG_TOL) || (fabs(fabs(z1) - fabs(x1)) > EIG_TOL));
