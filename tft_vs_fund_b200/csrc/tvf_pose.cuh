@@ -236,4 +236,40 @@ TVF_HD double final_point(const double* P1, const double* P2, const double* P3, 
     return sq;
 }
 
+// final_point with the third camera given as K3*R3 (first nine entries of P3) and a separately held translation column
+// (the fused tail scales t3 in registers): the same operations on the same values as final_point on [K3*R3 | t3s].
+TVF_HD double final_point_kt(const double* P1, const double* P2, const double* P3, const double* t3s, const double* p6,
+                             double* Xout) {
+    double a[6][4];
+    dlt_rows(P1, p6[0], p6[1], a[0], a[1]);
+    dlt_rows(P2, p6[2], p6[3], a[2], a[3]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        a[4][c] = p6[5] * P3[2 + 3 * c] - P3[1 + 3 * c];
+        a[5][c] = P3[0 + 3 * c] - p6[4] * P3[2 + 3 * c];
+    }
+    a[4][3] = p6[5] * t3s[2] - t3s[1];
+    a[5][3] = t3s[0] - p6[4] * t3s[2];
+    double X[4];
+    dlt_null<6>(a, X);
+    const double iw = 1.0 / X[3];
+    const double Xe[4] = {X[0] * iw, X[1] * iw, X[2] * iw, 1.0};
+    Xout[0] = Xe[0]; Xout[1] = Xe[1]; Xout[2] = Xe[2];
+    double sq = 0.0;
+#pragma unroll
+    for (int v = 0; v < 3; ++v) {
+        double x[3];
+        if (v < 2) {
+            cam_apply(v == 0 ? P1 : P2, Xe, x);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) x[r] = P3[r] * Xe[0] + P3[r + 3] * Xe[1] + P3[r + 6] * Xe[2] + t3s[r] * Xe[3];
+        }
+        const double iz = 1.0 / x[2];
+        const double dx = x[0] * iz - p6[2 * v], dy = x[1] * iz - p6[2 * v + 1];
+        sq += dx * dx + dy * dy;
+    }
+    return sq;
+}
+
 }  // namespace tvf

@@ -365,6 +365,169 @@ constexpr int FUSED_MAX_PPB = PT_THREADS / TAIL_FUSED_MIN_N;     // 36 problems 
 #ifndef TVF_TAIL_MINB
 #define TVF_TAIL_MINB 2
 #endif
+#ifndef TVF_TAIL_V2
+#define TVF_TAIL_V2 1
+#endif
+#if TVF_TAIL_V2
+// entry i (0..35) of the three cameras P1 | P2 | P3 of a problem for the selected candidates k2, k3
+__device__ __forceinline__ double camera_entry(const double* calm, const double* cand, int k2, int k3, int i) {
+    if (i < 12) return (i < 9) ? calm[(i % 3) + 9 * (i / 3)] : 0.0;                  // K1*[I | 0]
+    const int pair = (i >= 24) ? 1 : 0, e = i - 12 - 12 * pair, k = pair ? k3 : k2;
+    const double* c = cand + pair * CAND_PAIR;
+    if (e < 9) return c[((k < 2) ? OFF_KR : OFF_KRP) + e];
+    return ((k == 0 || k == 3) ? 1.0 : -1.0) * c[OFF_KT + e - 9];
+}
+// entry i (0..11) of [R | t] of candidate k of a pair (selected_pose, one element)
+__device__ __forceinline__ double pose_entry(const double* c, int k, int i) {
+    if (i < 9) return c[((k < 2) ? OFF_R : OFF_RP) + i];
+    return ((k == 0 || k == 3) ? 1.0 : -1.0) * c[OFF_T + i - 9];
+}
+// seg_reduce2 for tpp <= 32 with the two arrays summed by two different threads of the problem (same index order as
+// seg_reduce2: bit-identical sums), result at the problem's first thread
+__device__ __forceinline__ void seg_reduce2_split(double* ra, double* rb, const PointMap& m) {
+    if (m.tpp > 32) { seg_reduce2(ra, rb, m); return; }
+    __syncthreads();
+    if (m.lp < m.ppb && m.lpt < 2) {
+        double* r = (m.lpt ? rb : ra) + (threadIdx.x - m.lpt);
+        double acc = r[0];
+        for (int i = 1; i < m.tpp; ++i) acc += r[i];
+        r[0] = acc;
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void seg_reduce1(double* ra, const PointMap& m) {
+    if (m.tpp > 32) { seg_reduce(ra, m); return; }
+    __syncthreads();
+    if (m.lp < m.ppb && m.lpt == 0) {
+        double* r = ra + threadIdx.x;
+        double acc = r[0];
+        for (int i = 1; i < m.tpp; ++i) acc += r[i];
+        r[0] = acc;
+    }
+}
+
+// Every per-problem scalar step (candidate selection, t3 scale) is recomputed by ALL threads of the problem from shared
+// memory instead of by one thread followed by a barrier, and the per-problem vectors (cameras, [R|t] outputs) are
+// spread one element per thread: a warp holds one or two "first threads", so the single-thread sections cost every
+// warp their full instruction count.  Five CTA barriers per iteration instead of nine.
+__global__ void __launch_bounds__(PT_THREADS, TVF_TAIL_MINB)
+pose_tail_fused_kernel(PoseTailArgs a) {
+    __shared__ int sv[FUSED_MAX_PPB * 4];       // per local problem: vote(R,t), vote(Rp,t) for pairs 2 and 3
+    __shared__ int snan[FUSED_MAX_PPB];
+    __shared__ double sP[FUSED_MAX_PPB * 36];   // P1 | P2 | P3 = [K3*R3 | K3*t3]  (3x4 column-major each), t3 NOT yet scaled
+    __shared__ double red0[PT_THREADS], red1[PT_THREADS], red2[PT_THREADS];
+    const PointMap m(a.n);
+    const int own = threadIdx.x - m.lpt;        // first thread of this thread's problem
+    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int e = threadIdx.x; e < m.ppb * 4; e += PT_THREADS) sv[e] = 0;
+    for (int e = threadIdx.x; e < m.ppb; e += PT_THREADS) snan[e] = 0;
+    __syncthreads();
+    for (long long b0 = (long long)blockIdx.x * m.ppb; b0 < a.B; b0 += (long long)gridDim.x * m.ppb) {
+        const long long b = b0 + m.lp;
+        const bool live = (m.lp < m.ppb && b < a.B);
+        const double* cand = a.cand + (live ? b : 0) * CAND_SIZE;
+        double* Ps = sP + (live ? m.lp : 0) * 36;
+        double p6[6] = {0, 0, 0, 0, 0, 0}, Xa[4] = {0, 0, 0, 1}, Xb[4] = {0, 0, 0, 1};
+        // ---- phase 1: cheirality votes (R_t_from_TFT.m:91-104) --------------------------------
+        if (live) {
+            double P1[12];
+            load_K1_as_P1(calm_of(a, b), P1);
+            const double2* q = reinterpret_cast<const double2*>(a.corresp + (b * a.n + m.lpt) * 6);
+            const double2 q1 = __ldg(q), q2 = __ldg(q + 1), q3 = __ldg(q + 2);
+            p6[0] = q1.x; p6[1] = q1.y; p6[2] = q2.x; p6[3] = q2.y; p6[4] = q3.x; p6[5] = q3.y;
+            double ra[4], rb[4];
+            dlt_rows(P1, p6[0], p6[1], ra, rb);
+            int v2[2] = {0, 0}, v3[2] = {0, 0}, n2 = 0, n3 = 0;
+            cheirality_point(ra, rb, cand, p6[2], p6[3], v2, &n2, Xa, Xb);
+            cheirality_point(ra, rb, cand + CAND_PAIR, p6[4], p6[5], v3, &n3, nullptr, nullptr);
+            int* dst = sv + m.lp * 4;
+            if (v2[0]) atomicAdd(dst + 0, v2[0]);
+            if (v2[1]) atomicAdd(dst + 1, v2[1]);
+            if (v3[0]) atomicAdd(dst + 2, v3[0]);
+            if (v3[1]) atomicAdd(dst + 3, v3[1]);
+            if (n2 | n3) atomicOr(snan + m.lp, n2 | (n3 << 2));
+        }
+        __syncthreads();
+        // ---- selection by every thread; the cameras one element per thread -----------------------------
+        int k2 = 15, k3 = 15;
+        if (live) {
+            int vote[8], nan2, nan3;
+            expand_votes(sv + m.lp * 4, snan[m.lp] & 3, vote, &nan2);
+            expand_votes(sv + m.lp * 4 + 2, (snan[m.lp] >> 2) & 3, vote + 4, &nan3);
+            const int s2 = select_candidate(vote, nan2), s3 = select_candidate(vote + 4, nan3);
+            k2 = (s2 < 0) ? 15 : s2; k3 = (s3 < 0) ? 15 : s3;
+            if (m.lpt == 0 && a.votes != nullptr) {
+                int* gv = a.votes + b * 10;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) gv[k] = vote[k];
+                gv[8] = nan2; gv[9] = nan3;
+            }
+            const double* calm = calm_of(a, b);
+            for (int i = m.lpt; i < 36; i += m.tpp) Ps[i] = camera_entry(calm, cand, s2 < 0 ? 0 : s2, s3 < 0 ? 0 : s3, i);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < m.ppb * 4; e += PT_THREADS) sv[e] = 0;       // for the next iteration (two barriers ahead)
+        for (int e = threadIdx.x; e < m.ppb; e += PT_THREADS) snan[e] = 0;
+        // ---- phase 2: t3 scale (R_t_from_TFT.m:68-74) ----------------------------------------------
+        double num = 0.0, den = 0.0;
+        if (live) {
+            // X of the selected pair-2 candidate: (R,t)->Xa, (R,-t)->(Xa, -w), (Rp,-t)->(Xb, -w), (Rp,t)->Xb
+            const bool useA = (k2 == 0 || k2 == 1 || k2 == 15);
+            const double w = ((k2 == 1 || k2 == 2) ? -1.0 : 1.0) * (useA ? Xa[3] : Xb[3]);
+            const double iw = 1.0 / w;
+            const double Xc[3] = {(useA ? Xa[0] : Xb[0]) * iw, (useA ? Xa[1] : Xb[1]) * iw, (useA ? Xa[2] : Xb[2]) * iw};
+            double X3[3], c1[3], c2[3];
+            mat3_vec(Ps + 24, Xc, X3);
+            const double p3[3] = {p6[4], p6[5], 1.0};
+            cross3(p3, X3, c1);
+            cross3(p3, Ps + 33, c2);
+            num = c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2];
+            den = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+        }
+        red0[threadIdx.x] = num; red1[threadIdx.x] = den;
+        seg_reduce2_split(red0, red1, m);
+        const bool ok = (k2 != 15) && (k3 != 15);
+        double sq = 0.0;
+        if (live) {
+            const double snum = red0[own], sden = red1[own];
+            const double lam = -snum / sden;
+            // [R2|t2], [R3|lam*t3] (:74), one element per thread; pose flags by the first thread
+            bool fin = true;
+            const int kk2 = (k2 == 15) ? 0 : k2, kk3 = (k3 == 15) ? 0 : k3;
+            for (int i = m.lpt; i < 12; i += m.tpp) {
+                const double r2 = pose_entry(cand, kk2, i);
+                double r3 = pose_entry(cand + CAND_PAIR, kk3, i);
+                if (i >= 9) r3 *= lam;
+                fin = fin && isfinite(r2) && isfinite(r3);
+                if (a.Rt2 != nullptr) a.Rt2[b * 12 + i] = ok ? r2 : qnan;
+                if (a.Rt3 != nullptr) a.Rt3[b * 12 + i] = ok ? r3 : qnan;
+            }
+            int st = fin ? 0 : ST_NONFINITE;
+            if (m.lpt == 0) {
+                if (a.scale != nullptr) { a.scale[2 * b] = snum; a.scale[2 * b + 1] = sden; }
+                if (k2 == 15) st |= ST_NO_POSE_2;
+                if (k3 == 15) st |= ST_NO_POSE_3;
+            }
+            if (a.status != nullptr && st != 0) atomicOr(a.status + b, st);
+            // ---- phase 3: final triangulation + ReprError, P3 = K3*[R3 | lam*t3] -------------------------
+            const double t3s[3] = {Ps[33] * lam, Ps[34] * lam, Ps[35] * lam};
+            double X[3];
+            sq = final_point_kt(Ps, Ps + 12, Ps + 24, t3s, p6, X);
+            if (a.reconst != nullptr) {
+                double* dst = a.reconst + (b * a.n + m.lpt) * 3;
+                dst[0] = ok ? X[0] : qnan; dst[1] = ok ? X[1] : qnan; dst[2] = ok ? X[2] : qnan;
+            }
+        }
+        red2[threadIdx.x] = sq;
+        seg_reduce1(red2, m);
+        if (live && m.lpt == 0) {
+            const double err = sqrt(red2[threadIdx.x] / (3.0 * (double)a.n));       // ReprError.m:65
+            if (a.repr_err != nullptr) a.repr_err[b] = ok ? err : qnan;
+            if (a.status != nullptr && !isfinite(err)) atomicOr(a.status + b, ST_NONFINITE);
+        }
+    }
+}
+#else
 __global__ void __launch_bounds__(PT_THREADS, TVF_TAIL_MINB)
 pose_tail_fused_kernel(PoseTailArgs a) {
     __shared__ int sv[FUSED_MAX_PPB * 4];       // per local problem: vote(R,t), vote(Rp,t) for pairs 2 and 3
@@ -491,6 +654,8 @@ pose_tail_fused_kernel(PoseTailArgs a) {
         __syncthreads();
     }
 }
+
+#endif  // TVF_TAIL_V2
 
 // -------------------------------------------------- T = TFT_from_P(K1[I|0], K2 Rt2, K3 Rt3)
 __global__ void __launch_bounds__(128)

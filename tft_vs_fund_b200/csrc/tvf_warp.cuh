@@ -524,15 +524,21 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
         const int a = (k >= NR) ? 1 : 0, rk = k - a * NR;     // pivot row k lives on lane rk of each half, array a
         __syncwarp();                          // row k is in parity buffer k & 1; the other one is free again
         const double2* b2 = reinterpret_cast<const double2*>(sbuf + (k & 1) * 64 + h32);
+#if TVF_GJ2_PIPE == 1
         double2 q[NP / 2];
 #pragma unroll
         for (int m2 = 0; m2 < NP / 2; ++m2) q[m2] = b2[m2];
+#endif
         const double c0 = c0j - ((a == 0 && r == rk) ? 1.0 : 0.0);
         const double c1 = c1j - ((a == 1 && r == rk) ? 1.0 : 0.0);
         double n0j = 0.0, n1j = 0.0, npiv = 0.0, nr0 = 0.0, nr1 = 0.0;
         if (k + 1 < N) {
             const int an = (k + 1 >= NR) ? 1 : 0, rkn = k + 1 - an * NR;
+#if TVF_GJ2_PIPE == 1
             const double v = ((k + 1) & 1) ? q[(k + 1) >> 1].y : q[(k + 1) >> 1].x;
+#else
+            const double v = sbuf[(k & 1) * 64 + h32 + k + 1];     // variant 2: loads stay one at a time (no 56-register row)
+#endif
             g0[k + 1] = fma(-c0, v, g0[k + 1]); g1[k + 1] = fma(-c1, v, g1[k + 1]);
             n0j = g0[k + 1]; n1j = g1[k + 1];
             npiv = fast_rcp(pivot_floor(__shfl_sync(FULL, an ? n1j : n0j, rkn, 16), floor_piv));
@@ -542,8 +548,13 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
         }
 #pragma unroll
         for (int m2 = 0; m2 < NP / 2; ++m2) {
-            if (2 * m2 != k && 2 * m2 != k + 1 && 2 * m2 < N) { g0[2 * m2] = fma(-c0, q[m2].x, g0[2 * m2]); g1[2 * m2] = fma(-c1, q[m2].x, g1[2 * m2]); }
-            if (2 * m2 + 1 != k && 2 * m2 + 1 != k + 1 && 2 * m2 + 1 < N) { g0[2 * m2 + 1] = fma(-c0, q[m2].y, g0[2 * m2 + 1]); g1[2 * m2 + 1] = fma(-c1, q[m2].y, g1[2 * m2 + 1]); }
+#if TVF_GJ2_PIPE == 1
+            const double2 qq = q[m2];
+#else
+            const double2 qq = b2[m2];
+#endif
+            if (2 * m2 != k && 2 * m2 != k + 1 && 2 * m2 < N) { g0[2 * m2] = fma(-c0, qq.x, g0[2 * m2]); g1[2 * m2] = fma(-c1, qq.x, g1[2 * m2]); }
+            if (2 * m2 + 1 != k && 2 * m2 + 1 != k + 1 && 2 * m2 + 1 < N) { g0[2 * m2 + 1] = fma(-c0, qq.y, g0[2 * m2 + 1]); g1[2 * m2 + 1] = fma(-c1, qq.y, g1[2 * m2 + 1]); }
         }
         g0[k] = (a == 0 && r == rk) ? -piv : r0;
         g1[k] = (a == 1 && r == rk) ? -piv : r1;

@@ -1,41 +1,23 @@
-"""Aggregate an `ncu --page source --csv --print-source cuda,sass` dump by CUDA source line (samples and instructions)."""
-import collections
-import csv
-import sys
-
-
-def num(x):
-    try:
-        return int(float(x))
-    except Exception:
-        return 0
-
-
-def main(path, top=24):
-    rows = list(csv.reader(open(path)))
-    kern = collections.OrderedDict(); fname = None; func = None; hdr = None
-    for r in rows:
-        if not r:
-            continue
-        if r[0] == "File Path":
-            fname = r[1].split('/')[-1]; continue
-        if r[0] == "Function Name":
-            func = r[1]; kern.setdefault(func, collections.defaultdict(lambda: [0, 0, ""])); continue
-        if r[0] == "Line No":
-            hdr = r; ixS = hdr.index("# Samples"); ixI = hdr.index("Instructions Executed"); continue
-        if r[0] == "" or func is None:
-            continue
-        try:
-            ln = int(r[0])
-        except ValueError:
-            continue
-        e = kern[func][(fname, ln)]; e[0] += num(r[ixS]); e[1] += num(r[ixI]); e[2] = r[1]
-    for name, lines in kern.items():
-        tot_s = sum(v[0] for v in lines.values()); tot_i = sum(v[1] for v in lines.values())
-        print("=====", name[:60], "samples", tot_s, "inst", tot_i)
-        for (f, ln), v in sorted(lines.items(), key=lambda kv: -kv[1][0])[:top]:
-            print("  %5.1f%% smp %5.1f%% ins  %s:%d  %s" % (100 * v[0] / max(1, tot_s), 100 * v[1] / max(1, tot_i), f[:16], ln, v[2].strip()[:84]))
-
-
-if __name__ == "__main__":
-    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 24)
+#!/usr/bin/env python
+"""Per-CUDA-source-line share of warp-stall samples and executed instructions from an ncu report
+(ncu -i REP --page source --csv --print-source cuda,sass).  Usage: ncu_lines.py REP [top]"""
+import csv, subprocess, sys, collections
+rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+rows = list(csv.reader(txt.splitlines()))
+cur = None; hdr = None; out = []
+for r in rows:
+    if len(r) == 2 and r[0] in ("File Path", "File Name"): cur = r[1]; continue
+    if len(r) == 2: continue
+    if r and r[0] == "Line No":
+        hdr = r; n = len(hdr); iS = hdr.index("# Samples") - n; iI = hdr.index("Instructions Executed") - n; continue
+    if hdr is None or not r or not r[0].isdigit(): continue
+    try: smp = int(r[iS]); ins = int(r[iI])
+    except Exception: continue
+    out.append((smp, ins, cur.split("/")[-1], int(r[0]), ",".join(r[1:len(r) - n + 2])[:100]))
+tot = sum(o[0] for o in out) or 1; toti = sum(o[1] for o in out) or 1
+print("total samples", tot, "warp instructions", toti)
+pf = collections.Counter(); pi = collections.Counter()
+for o in out: pf[o[2]] += o[0]; pi[o[2]] += o[1]
+for k, v in pf.most_common(): print("  %-28s samples %5.1f%%  instructions %5.1f%%" % (k, 100 * v / tot, 100 * pi[k] / toti))
+for o in sorted(out, reverse=True)[:top]: print("%5.2f%% %5.2f%%i %s:%d %s" % (100 * o[0] / tot, 100 * o[1] / toti, o[2], o[3], o[4]))
