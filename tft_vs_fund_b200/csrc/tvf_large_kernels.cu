@@ -27,6 +27,7 @@
 
 #include "tvf_kernels.h"
 #include "tvf_warp.cuh"
+#include "tvf_async.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -36,34 +37,6 @@ constexpr int LG_CLUSTER = 8;
 constexpr int LG_THREADS = 128;
 constexpr int LG_WARPS = LG_THREADS / 32;
 constexpr int CW_MOM_L = 0, CW_STATS_L = 96;
-
-// ---- mbarrier / bulk-copy PTX --------------------------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-    unsigned done;
-    do {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!done);
-}
-// global -> shared bulk copy (TMA engine), completion counted in bytes on `bar`
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 // address of `local_smem_addr` in the shared memory of CTA `rank` of this cluster
 __device__ __forceinline__ unsigned mapa_u32(unsigned local_smem_addr, unsigned rank) {

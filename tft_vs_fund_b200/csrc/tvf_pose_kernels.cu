@@ -10,6 +10,7 @@
 //       shared-memory tree for the FP64 sums) -> bit-reproducible results.
 #include "tvf_kernels.h"
 #include "tvf_pose.cuh"
+#include "tvf_async.cuh"
 
 namespace tvf {
 
@@ -368,6 +369,9 @@ constexpr int FUSED_MAX_PPB = PT_THREADS / TAIL_FUSED_MIN_N;     // 36 problems 
 #ifndef TVF_TAIL_V2
 #define TVF_TAIL_V2 1
 #endif
+#ifndef TVF_TAIL_TMA
+#define TVF_TAIL_TMA 1
+#endif
 #if TVF_TAIL_V2
 // entry i (0..35) of the three cameras P1 | P2 | P3 of a problem for the selected candidates k2, k3
 __device__ __forceinline__ double camera_entry(const double* calm, const double* cand, int k2, int k3, int i) {
@@ -419,21 +423,61 @@ pose_tail_fused_kernel(PoseTailArgs a) {
     const PointMap m(a.n);
     const int own = threadIdx.x - m.lpt;        // first thread of this thread's problem
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
+#if TVF_TAIL_TMA
+    // The correspondences and the candidate records of the CTA's NEXT group of problems (two contiguous ranges of global
+    // memory: ppb*n*48 and ppb*672 bytes) are brought into the other half of a two-stage shared-memory buffer by two bulk
+    // asynchronous copies (TMA engine) that one thread issues at the top of the iteration; every phase reads shared memory.
+    extern __shared__ __align__(16) unsigned char tail_dsm[];
+    __shared__ unsigned long long tbar[2];
+    const unsigned pts_bytes = (unsigned)m.ppb * (unsigned)a.n * 48u, cand_bytes = (unsigned)m.ppb * (unsigned)(CAND_SIZE * 8);
+    const unsigned stage_bytes = pts_bytes + cand_bytes;
+    const long long bstep = (long long)gridDim.x * m.ppb;
+    auto issue = [&](long long b0n, int stage) {          // thread 0 only
+        const long long left = a.B - b0n;
+        const unsigned np = (unsigned)(left < m.ppb ? left : m.ppb);
+        unsigned char* dst = tail_dsm + (size_t)stage * stage_bytes;
+        mbar_expect_tx(&tbar[stage], np * (unsigned)a.n * 48u + np * (unsigned)(CAND_SIZE * 8));
+        bulk_g2s(dst, a.corresp + b0n * a.n * 6, np * (unsigned)a.n * 48u, &tbar[stage]);
+        bulk_g2s(dst + pts_bytes, a.cand + b0n * CAND_SIZE, np * (unsigned)(CAND_SIZE * 8), &tbar[stage]);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&tbar[0], 1); mbar_init(&tbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+#endif
     for (int e = threadIdx.x; e < m.ppb * 4; e += PT_THREADS) sv[e] = 0;
     for (int e = threadIdx.x; e < m.ppb; e += PT_THREADS) snan[e] = 0;
     __syncthreads();
+#if TVF_TAIL_TMA
+    if (threadIdx.x == 0 && (long long)blockIdx.x * m.ppb < a.B) issue((long long)blockIdx.x * m.ppb, 0);
+    int iter = 0;
+#endif
     for (long long b0 = (long long)blockIdx.x * m.ppb; b0 < a.B; b0 += (long long)gridDim.x * m.ppb) {
         const long long b = b0 + m.lp;
         const bool live = (m.lp < m.ppb && b < a.B);
+#if TVF_TAIL_TMA
+        // the other stage was last read before the final barrier of the previous iteration: free to be refilled
+        if (threadIdx.x == 0 && b0 + bstep < a.B) issue(b0 + bstep, (iter + 1) & 1);
+        const unsigned char* stg = tail_dsm + (size_t)(iter & 1) * stage_bytes;
+        mbar_wait(&tbar[iter & 1], (unsigned)(iter >> 1) & 1u);
+        ++iter;
+        const double* cand = reinterpret_cast<const double*>(stg + pts_bytes) + (live ? m.lp : 0) * CAND_SIZE;
+#else
         const double* cand = a.cand + (live ? b : 0) * CAND_SIZE;
+#endif
         double* Ps = sP + (live ? m.lp : 0) * 36;
         double p6[6] = {0, 0, 0, 0, 0, 0}, Xa[4] = {0, 0, 0, 1}, Xb[4] = {0, 0, 0, 1};
         // ---- phase 1: cheirality votes (R_t_from_TFT.m:91-104) --------------------------------
         if (live) {
             double P1[12];
             load_K1_as_P1(calm_of(a, b), P1);
+#if TVF_TAIL_TMA
+            const double2* q = reinterpret_cast<const double2*>(stg) + (m.lp * a.n + m.lpt) * 3;
+            const double2 q1 = q[0], q2 = q[1], q3 = q[2];
+#else
             const double2* q = reinterpret_cast<const double2*>(a.corresp + (b * a.n + m.lpt) * 6);
             const double2 q1 = __ldg(q), q2 = __ldg(q + 1), q3 = __ldg(q + 2);
+#endif
             p6[0] = q1.x; p6[1] = q1.y; p6[2] = q2.x; p6[3] = q2.y; p6[4] = q3.x; p6[5] = q3.y;
             double ra[4], rb[4];
             dlt_rows(P1, p6[0], p6[1], ra, rb);
@@ -913,7 +957,16 @@ static inline unsigned tail_grid(const PoseTailArgs& a, int sm_count) {
 
 void launch_pose_tail_fused(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
     if (a.B <= 0) return;
+#if TVF_TAIL_V2 && TVF_TAIL_TMA
+    const int tpp = (a.n <= PT_THREADS) ? a.n : PT_THREADS;
+    const int ppb = PT_THREADS / tpp;
+    const size_t dyn = 2 * (size_t)ppb * ((size_t)a.n * 48 + CAND_SIZE * 8);      // two stages of points + candidate records
+    // (set on every launch: the attribute is per device and per context, a process-wide flag would miss the second GPU)
+    cudaFuncSetAttribute(pose_tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    pose_tail_fused_kernel<<<tail_grid(a, sm_count), PT_THREADS, dyn, stream>>>(a);
+#else
     pose_tail_fused_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
+#endif
 }
 
 void launch_votes(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {

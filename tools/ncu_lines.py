@@ -3,7 +3,8 @@
 (ncu -i REP --page source --csv --print-source cuda,sass).  Usage: ncu_lines.py REP [top]"""
 import csv, subprocess, sys, collections
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 50
-txt = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
+kf = (["--kernel-name", "regex:" + sys.argv[3]] if len(sys.argv) > 3 else [])
+txt = subprocess.run(["ncu", "-i", rep] + kf + ["--page", "source", "--csv", "--print-source", "cuda,sass"], capture_output=True, text=True).stdout
 rows = list(csv.reader(txt.splitlines()))
 cur = None; hdr = None; out = []
 for r in rows:
