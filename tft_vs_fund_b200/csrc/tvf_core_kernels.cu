@@ -17,6 +17,7 @@
 #include "tvf_kernels.h"
 #include "tvf_warp.cuh"
 #include "tvf_pose.cuh"
+#include "tvf_async.cuh"
 
 namespace tvf {
 
@@ -74,9 +75,16 @@ __device__ __constant__ signed char c_m4[9] = {0, -1, 1, -1, 0, 2, 1, 2, 3};
 // v[i] for a runtime i without forcing the array into local memory
 __device__ __forceinline__ double sel3(const double* v, int i) { return (i == 0) ? v[0] : ((i == 1) ? v[1] : v[2]); }
 
-template <bool PACKED>
+// PACKED: 0 = three separate point arrays, 1 = 6 x n correspondences in global memory, 2 = the same layout staged in
+// shared memory (in.p1 = the stage, prob = index inside it)
+template <int PACKED>
 __device__ __forceinline__ void load_point(const CoreInput& in, long long prob, int i, double* p) {
-    if (PACKED) {
+    if (PACKED == 2) {
+        const unsigned addr = smem_u32(in.p1) + (unsigned)(((int)prob * in.n + i) * 48);
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(p[0]), "=d"(p[1]) : "r"(addr));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(p[2]), "=d"(p[3]) : "r"(addr));
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+32];" : "=d"(p[4]), "=d"(p[5]) : "r"(addr));
+    } else if (PACKED) {
         const double2* q = reinterpret_cast<const double2*>(in.p1 + (prob * in.n + i) * 6);
         const double2 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
         p[0] = a.x; p[1] = a.y; p[2] = b.x; p[3] = b.y; p[4] = c.x; p[5] = c.y;
@@ -410,7 +418,7 @@ __device__ __forceinline__ void solve_pair_from_moments(Stage1DualScratch& sc, c
 
 // Normalisation statistics and the 96 moments of one problem on one half-warp (r = lane & 15).  feat: this half's
 // 16 x S1D_FEAT staging buffer.  acc[q] receives moment q*16 + r; (s, t): new = s*x + t per view.
-template <bool PACKED>
+template <int PACKED>
 __device__ __forceinline__ void half_stats_moments(const CoreInput& in, long long prob, int r, double* feat, double (&acc)[6],
                                                    double (&s)[3], double (&t)[6]) {
     const int n = in.n;
@@ -548,6 +556,55 @@ tft_moments_kernel(CoreInput in, double* __restrict__ ws) {
         const long long prob = live ? 2 * pair + h : in.B - 1;
         double acc[6], s[3], t[6];
         half_stats_moments<PACKED>(in, prob, r, scratch[warp].feat[h], acc, s, t);
+        if (live) store_moments_stats(ws + prob * CORE_WS_TFT, r, acc, s, t);
+    }
+}
+
+// The same with the correspondences of the CTA's next eight problems (one contiguous 8 * n * 48-byte range) brought into a
+// two-stage shared-memory buffer by a bulk asynchronous copy (TMA engine) while the current eight are processed: the three
+// passes over the points (sums, distances, moments) read shared memory, and no warp waits for DRAM (the plain kernel
+// spent most of its stall samples in `long_scoreboard`).  Packed input, n <= MOM_TMA_MAX_N.
+#ifndef TVF_S1M_TMA
+#define TVF_S1M_TMA 1
+#endif
+#ifndef TVF_S1M_TMA_MINB
+#define TVF_S1M_TMA_MINB 6
+#endif
+constexpr int MOM_TMA_MAX_N = 64;
+__global__ void __launch_bounds__(CORE_WARPS * 32, TVF_S1M_TMA_MINB)
+tft_moments_tma_kernel(CoreInput in, double* __restrict__ ws) {
+    __shared__ MomentsScratch scratch[CORE_WARPS];
+    __shared__ unsigned long long bar[2];
+    extern __shared__ __align__(16) unsigned char mom_dsm[];
+    constexpr int PPG = 2 * CORE_WARPS;                    // problems per CTA iteration
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = lane >> 4, r = lane & 15;
+    const unsigned prob_bytes = (unsigned)in.n * 48u, stage_bytes = PPG * prob_bytes;
+    const long long ngroups = (in.B + PPG - 1) / PPG;
+    auto issue = [&](long long g, int stage) {             // thread 0 only
+        const long long left = in.B - g * PPG;
+        const unsigned bytes = (unsigned)(left < PPG ? left : PPG) * prob_bytes;
+        mbar_expect_tx(&bar[stage], bytes);
+        bulk_g2s(mom_dsm + (size_t)stage * stage_bytes, in.p1 + g * PPG * in.n * 6, bytes, &bar[stage]);
+    };
+    if (threadIdx.x == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && blockIdx.x < ngroups) issue(blockIdx.x, 0);
+    int iter = 0;
+    for (long long g = blockIdx.x; g < ngroups; g += gridDim.x, ++iter) {
+        __syncthreads();                                   // every warp is done with the stage that is refilled now
+        if (threadIdx.x == 0 && g + gridDim.x < ngroups) issue(g + gridDim.x, (iter + 1) & 1);
+        mbar_wait(&bar[iter & 1], (unsigned)(iter >> 1) & 1u);
+        CoreInput ins = in;
+        ins.p1 = reinterpret_cast<const double*>(mom_dsm + (size_t)(iter & 1) * stage_bytes);
+        const int lp = 2 * warp + h;
+        const long long prob = g * PPG + lp;
+        const bool live = prob < in.B;
+        double acc[6], s[3], t[6];
+        half_stats_moments<2>(ins, live ? lp : 0, r, scratch[warp].feat[h], acc, s, t);
         if (live) store_moments_stats(ws + prob * CORE_WS_TFT, r, acc, s, t);
     }
 }
@@ -1275,6 +1332,15 @@ int launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count
     if (!refine) {
 #if TVF_STAGE1_SPLIT
         const unsigned gm = core_grid_minb((in.B + 1) / 2, sm_count, TVF_S1M_MINB);
+#if TVF_S1M_TMA
+        if (in.packed && in.n <= MOM_TMA_MAX_N) {
+            const size_t dyn = 2 * (size_t)(2 * CORE_WARPS) * in.n * 48;
+            cudaFuncSetAttribute(tft_moments_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);   // per launch: per device
+            const unsigned gt = core_grid_minb((in.B + 1) / 2, sm_count, TVF_S1M_TMA_MINB);
+            tft_moments_tma_kernel<<<gt, CORE_WARPS * 32, dyn, stream>>>(in, ws);
+            return 1;
+        }
+#endif
         if (in.packed) tft_moments_kernel<true><<<gm, CORE_WARPS * 32, 0, stream>>>(in, ws);
         else tft_moments_kernel<false><<<gm, CORE_WARPS * 32, 0, stream>>>(in, ws);
         return 1;                 // the caller follows up with launch_tft_stage1_solve
