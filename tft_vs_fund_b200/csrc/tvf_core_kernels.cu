@@ -225,10 +225,10 @@ __device__ __forceinline__ double f_apply_AtA(const CoreInput& in, long long pro
 }
 
 // G(r,c) -> moment index (96 = structural zero), one table per CTA
-__device__ __forceinline__ void build_gidx(unsigned char* gidx) {
+__device__ __forceinline__ void build_gidx(unsigned char* gidx, int zero_slot = 96) {
     for (int e = threadIdx.x; e < 32 * 27; e += blockDim.x) {
         const int r = e / 27, c = e % 27;
-        int idx = 96;
+        int idx = zero_slot;                 // structural zeros of the Gram (and rows >= 27) read a slot that holds 0.0
         if (r < 27) {
             const int j = r % 3, k = (r / 3) % 3, i = r / 9;
             const int j2 = c % 3, k2 = (c / 3) % 3, i2 = c / 9;
@@ -975,10 +975,20 @@ tft_stage2_kernel(CoreInput in, const double* __restrict__ ws, double* __restric
 // ---- two problems per warp (n >= REFINE_N_MAX): the 27-lane parts run once per problem, the 15-lane parts (the
 // projected Gram Up'(G Up), its Gauss-Jordan inverse and the power iteration: half of this kernel's instructions) run
 // for both problems at once on the two half-warps (smallest_eigvec_spd_half).
+// The pair's two work-space records are adjacent in global memory (2 x 1120 bytes): lane 0 fetches the NEXT pair's with one
+// bulk asynchronous copy per warp (own mbarrier) as soon as the current pair's moments have been consumed (the epipoles
+// and statistics are copied aside first), so no pair waits for its loads.
+#ifndef TVF_S2_TMA
+#define TVF_S2_TMA 1
+#endif
 struct __align__(16) Stage2DualScratch {
     double sbuf[64];
     double W[2][27 * FEAT_STRIDE + 3];   // G*Up of the two problems
+#if TVF_S2_TMA
+    double rec2[2 * CORE_WS_TFT];        // the two work-space records as they lie in global memory (one bulk copy)
+#else
     double mom2[2][98];                  // moments of the two problems (+ zero sentinel)
+#endif
     double es[2][16];                    // epipoles (6) + normalisation statistics (9) of the two problems
     double T[28];
     double tp[2][16];
@@ -995,13 +1005,31 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
     __shared__ Stage2DualScratch scratch[CORE_WARPS];
     __shared__ unsigned char gidx[32 * 27];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#if TVF_S2_TMA
+    build_gidx(gidx, CW_STATS + 9);         // the unused pad slot of the staged record, zeroed after every copy
+#else
     build_gidx(gidx);
+#endif
     __syncthreads();
     Stage2DualScratch& sc = scratch[warp];
     const int jr = lane % 3, kr = (lane / 3) % 3, ir = (lane < 27) ? lane / 9 : 0;
     const int h = lane >> 4, r15 = lane & 15;
     const int ia = (r15 < 15) ? r15 / 5 : 0, aa = (r15 < 15) ? r15 % 5 : 0;
     const long long npairs = (B + 1) / 2;
+#if TVF_S2_TMA
+    __shared__ unsigned long long wbar[CORE_WARPS];
+    const long long pstride = (long long)gridDim.x * CORE_WARPS;
+    auto fetch = [&](long long pr) {                        // lane 0 only: records of pair pr -> sc.rec2
+        const unsigned bytes = (2 * pr + 1 < B ? 2u : 1u) * (unsigned)(CORE_WS_TFT * 8);
+        mbar_expect_tx(&wbar[warp], bytes);
+        bulk_g2s(sc.rec2, ws + 2 * pr * CORE_WS_TFT, bytes, &wbar[warp]);
+    };
+    if (lane == 0) mbar_init(&wbar[warp], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    if (lane == 0 && (long long)blockIdx.x * CORE_WARPS + warp < npairs) fetch((long long)blockIdx.x * CORE_WARPS + warp);
+    unsigned parity = 0;
+#endif
 
     for (long long base = (long long)blockIdx.x * CORE_WARPS; base < npairs; base += (long long)gridDim.x * CORE_WARPS) {
         S2_SYNC();
@@ -1009,6 +1037,18 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
         if (pair >= npairs) continue;
         const long long prob0 = 2 * pair;
         const int nprob = (prob0 + 1 < B) ? 2 : 1;
+#if TVF_S2_TMA
+        mbar_wait(&wbar[warp], parity);
+        parity ^= 1u;
+        {
+            // lane 16 p + q: epipoles (q < 6) and normalisation statistics (6 <= q < 15) of problem p, set aside
+            const int pq = lane >> 4, q15 = lane & 15;
+            const double* recq = sc.rec2 + ((pq < nprob) ? pq : 0) * CORE_WS_TFT;
+            sc.es[pq][q15] = (q15 < 6) ? recq[CW_EPI + q15] : ((q15 < 15) ? recq[CW_STATS + q15 - 6] : 0.0);
+            if (q15 == 15) sc.rec2[pq * CORE_WS_TFT + CW_STATS + 9] = 0.0;          // the Gram gather's zero slot
+            __syncwarp();
+        }
+#else
         // ---- every global load of the pair is issued up front (moments, epipoles, normalisation statistics): one exposed
         //      memory latency per pair instead of five; the epipoles stay in registers for all three phases
         {
@@ -1031,9 +1071,14 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
             sc.es[pq][q15] = ev;
             __syncwarp();
         }
+#endif
         // ---- 27-lane part, problem by problem: W = G*Up (linearTFT.m:82-84 without svd(E), see tft_stage2_kernel) ----
         for (int p = 0; p < nprob; ++p) {
+#if TVF_S2_TMA
+            const double* mom = sc.rec2 + p * CORE_WS_TFT + CW_MOM;
+#else
             const double* mom = sc.mom2[p];
+#endif
             const double e21[3] = {sc.es[p][0], sc.es[p][1], sc.es[p][2]};
             const double e31[3] = {sc.es[p][3], sc.es[p][4], sc.es[p][5]};
             double u1[3], u2[3], v1[3], v2[3];
@@ -1063,6 +1108,9 @@ tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws
             }
         }
         __syncwarp();
+#if TVF_S2_TMA
+        if (lane == 0 && pair + pstride < npairs) fetch(pair + pstride);       // every lane is done with sc.rec2
+#endif
         // ---- 15-lane part, both problems at once: half h = problem prob0 + h ------------------------------------
         {
             const bool live = h < nprob;
