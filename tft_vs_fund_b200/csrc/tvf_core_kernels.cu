@@ -609,10 +609,15 @@ tft_moments_tma_kernel(CoreInput in, double* __restrict__ ws) {
     }
 }
 
+// warps per CTA of the two-problem solve kernel (the CTA barrier per pair keeps them on the same instruction-cache lines)
+#ifndef TVF_S1D_WARPS
+#define TVF_S1D_WARPS TVF_CORE_WARPS
+#endif
+constexpr int S1D_WARPS = TVF_S1D_WARPS;
 // Large-n path, two problems per warp: the moments were produced by tft_moments_large_kernel.
-__global__ void __launch_bounds__(CORE_WARPS * 32, TVF_S1D_MINB)
+__global__ void __launch_bounds__(S1D_WARPS * 32, TVF_S1D_MINB)
 tft_stage1_solve_dual_kernel(long long B, double* __restrict__ ws, int* __restrict__ status) {
-    __shared__ Stage1DualScratch scratch[CORE_WARPS];
+    __shared__ Stage1DualScratch scratch[S1D_WARPS];
     __shared__ unsigned char gidx[32 * 27];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     build_gidx(gidx);
@@ -624,9 +629,9 @@ tft_stage1_solve_dual_kernel(long long B, double* __restrict__ ws, int* __restri
     // The raw moments of the NEXT pair travel global -> shared (cp.async, no registers: the solver leaves none) while this
     // pair is solved; they land in the feature staging buffer, which the solve-only kernel does not use otherwise.
     double* raw = sc.feat[h];
-    const long long stride = (long long)gridDim.x * CORE_WARPS;
+    const long long stride = (long long)gridDim.x * S1D_WARPS;
     {
-        const long long pair = (long long)blockIdx.x * CORE_WARPS + warp;
+        const long long pair = (long long)blockIdx.x * S1D_WARPS + warp;
         if (pair < npairs) {
             const double* src = ws + min(2 * pair + h, B - 1) * CORE_WS_TFT + CW_MOM;
 #pragma unroll
@@ -635,7 +640,7 @@ tft_stage1_solve_dual_kernel(long long B, double* __restrict__ ws, int* __restri
         if (r < 4) sc.mom[h][96 + r] = 0.0;
     }
 #endif
-    for (long long base = (long long)blockIdx.x * CORE_WARPS; base < npairs; base += (long long)gridDim.x * CORE_WARPS) {
+    for (long long base = (long long)blockIdx.x * S1D_WARPS; base < npairs; base += (long long)gridDim.x * S1D_WARPS) {
         S1D_SYNC();
         const long long pair = base + warp;
         if (pair >= npairs) continue;
@@ -1410,7 +1415,12 @@ int launch_tft_stage1(const CoreInput& in, double* ws, int* status, int sm_count
 void launch_tft_stage1_solve(long long B, double* ws, int* status, int sm_count, cudaStream_t stream) {
     if (B <= 0) return;
 #if TVF_S1_SOLVER == 2
-    tft_stage1_solve_dual_kernel<<<core_grid_minb((B + 1) / 2, sm_count, TVF_S1D_MINB), CORE_WARPS * 32, 0, stream>>>(B, ws, status);
+    {
+        long long blocks = ((B + 1) / 2 + S1D_WARPS - 1) / S1D_WARPS;
+        const long long cap = (long long)sm_count * TVF_S1D_MINB * 4;
+        if (blocks > cap) blocks = cap;
+        tft_stage1_solve_dual_kernel<<<(unsigned)(blocks < 1 ? 1 : blocks), S1D_WARPS * 32, 0, stream>>>(B, ws, status);
+    }
 #elif TVF_S1_SOLVER == 3
     tft_stage1_solve_cs_kernel<<<core_grid_minb(B, sm_count, TVF_S1C_MINB), CORE_WARPS * 32, 0, stream>>>(B, ws, status);
 #else

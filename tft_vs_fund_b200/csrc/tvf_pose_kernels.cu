@@ -21,9 +21,9 @@ struct PointMap {
     int tpp;    // threads per problem
     int lp;     // local problem of this thread
     int lpt;    // thread's rank inside its problem
-    __device__ __forceinline__ PointMap(int n) {
-        tpp = (n <= PT_THREADS) ? n : PT_THREADS;
-        ppb = PT_THREADS / tpp;
+    __device__ __forceinline__ PointMap(int n, int threads = PT_THREADS) {
+        tpp = (n <= threads) ? n : threads;
+        ppb = threads / tpp;
         lp = threadIdx.x / tpp;
         lpt = threadIdx.x - lp * tpp;
     }
@@ -361,18 +361,13 @@ final_large_kernel(PoseTailArgs a) {
 // __syncthreads only.  The two-view solutions found during the cheirality test are reused for the scale
 // (the selected candidate's DLT is the one R_t_from_TFT.m:69 computes again).  The selected cameras live
 // in shared memory (36 doubles per problem), not in registers, between the phases.
-constexpr int FUSED_MAX_PPB = PT_THREADS / TAIL_FUSED_MIN_N;     // 36 problems per CTA at most
 
 #ifndef TVF_TAIL_MINB
 #define TVF_TAIL_MINB 2
 #endif
-#ifndef TVF_TAIL_V2
-#define TVF_TAIL_V2 1
-#endif
 #ifndef TVF_TAIL_TMA
 #define TVF_TAIL_TMA 1
 #endif
-#if TVF_TAIL_V2
 // entry i (0..35) of the three cameras P1 | P2 | P3 of a problem for the selected candidates k2, k3
 __device__ __forceinline__ double camera_entry(const double* calm, const double* cand, int k2, int k3, int i) {
     if (i < 12) return (i < 9) ? calm[(i % 3) + 9 * (i / 3)] : 0.0;                  // K1*[I | 0]
@@ -414,13 +409,16 @@ __device__ __forceinline__ void seg_reduce1(double* ra, const PointMap& m) {
 // memory instead of by one thread followed by a barrier, and the per-problem vectors (cameras, [R|t] outputs) are
 // spread one element per thread: a warp holds one or two "first threads", so the single-thread sections cost every
 // warp their full instruction count.  Five CTA barriers per iteration instead of nine.
-__global__ void __launch_bounds__(PT_THREADS, TVF_TAIL_MINB)
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, (TVF_TAIL_MINB * PT_THREADS) / THREADS)
 pose_tail_fused_kernel(PoseTailArgs a) {
-    __shared__ int sv[FUSED_MAX_PPB * 4];       // per local problem: vote(R,t), vote(Rp,t) for pairs 2 and 3
-    __shared__ int snan[FUSED_MAX_PPB];
-    __shared__ double sP[FUSED_MAX_PPB * 36];   // P1 | P2 | P3 = [K3*R3 | K3*t3]  (3x4 column-major each), t3 NOT yet scaled
-    __shared__ double red0[PT_THREADS], red1[PT_THREADS], red2[PT_THREADS];
-    const PointMap m(a.n);
+    constexpr int MAX_PPB = THREADS / TAIL_FUSED_MIN_N;
+    constexpr int PT_THREADS = THREADS;         // (shadows the file-wide constant inside this kernel)
+    __shared__ int sv[MAX_PPB * 4];             // per local problem: vote(R,t), vote(Rp,t) for pairs 2 and 3
+    __shared__ int snan[MAX_PPB];
+    __shared__ double sP[MAX_PPB * 36];         // P1 | P2 | P3 = [K3*R3 | K3*t3]  (3x4 column-major each), t3 NOT yet scaled
+    __shared__ double red0[THREADS], red1[THREADS], red2[THREADS];
+    const PointMap m(a.n, THREADS);
     const int own = threadIdx.x - m.lpt;        // first thread of this thread's problem
     const double qnan = __longlong_as_double(0x7ff8000000000000LL);
 #if TVF_TAIL_TMA
@@ -571,135 +569,6 @@ pose_tail_fused_kernel(PoseTailArgs a) {
         }
     }
 }
-#else
-__global__ void __launch_bounds__(PT_THREADS, TVF_TAIL_MINB)
-pose_tail_fused_kernel(PoseTailArgs a) {
-    __shared__ int sv[FUSED_MAX_PPB * 4];       // per local problem: vote(R,t), vote(Rp,t) for pairs 2 and 3
-    __shared__ int snan[FUSED_MAX_PPB];
-    __shared__ int ssel[FUSED_MAX_PPB];         // k2 | k3 << 4 (each 0..3, or 15 for "none")
-    __shared__ double sP[FUSED_MAX_PPB * 36];   // P1 | P2 | P3 = [K3*R3 | K3*t3]  (3x4 column-major each)
-    __shared__ double red0[PT_THREADS], red1[PT_THREADS];
-    const PointMap m(a.n);
-    const double qnan = __longlong_as_double(0x7ff8000000000000LL);
-    for (long long b0 = (long long)blockIdx.x * m.ppb; b0 < a.B; b0 += (long long)gridDim.x * m.ppb) {
-        for (int e = threadIdx.x; e < m.ppb * 4; e += PT_THREADS) sv[e] = 0;
-        for (int e = threadIdx.x; e < m.ppb; e += PT_THREADS) snan[e] = 0;
-        __syncthreads();
-        const long long b = b0 + m.lp;
-        const bool live = (m.lp < m.ppb && b < a.B);
-        const double* cand = a.cand + (live ? b : 0) * CAND_SIZE;
-        double* Ps = sP + (live ? m.lp : 0) * 36;
-        double p6[6] = {0, 0, 0, 0, 0, 0}, Xa[4] = {0, 0, 0, 1}, Xb[4] = {0, 0, 0, 1};
-        // ---- phase 1: cheirality votes (R_t_from_TFT.m:91-104) --------------------------------
-        if (live) {
-            double P1[12];
-            load_K1_as_P1(calm_of(a, b), P1);
-            const double2* q = reinterpret_cast<const double2*>(a.corresp + (b * a.n + m.lpt) * 6);
-            const double2 q1 = __ldg(q), q2 = __ldg(q + 1), q3 = __ldg(q + 2);
-            p6[0] = q1.x; p6[1] = q1.y; p6[2] = q2.x; p6[3] = q2.y; p6[4] = q3.x; p6[5] = q3.y;
-            double ra[4], rb[4];
-            dlt_rows(P1, p6[0], p6[1], ra, rb);
-            int v2[2] = {0, 0}, v3[2] = {0, 0}, n2 = 0, n3 = 0;
-            cheirality_point(ra, rb, cand, p6[2], p6[3], v2, &n2, Xa, Xb);
-            cheirality_point(ra, rb, cand + CAND_PAIR, p6[4], p6[5], v3, &n3, nullptr, nullptr);
-            int* dst = sv + m.lp * 4;
-            if (v2[0]) atomicAdd(dst + 0, v2[0]);
-            if (v2[1]) atomicAdd(dst + 1, v2[1]);
-            if (v3[0]) atomicAdd(dst + 2, v3[0]);
-            if (v3[1]) atomicAdd(dst + 3, v3[1]);
-            if (n2 | n3) atomicOr(snan + m.lp, n2 | (n3 << 2));
-        }
-        __syncthreads();
-        // ---- selection: one thread per problem publishes it together with the cameras ---------------
-        if (live && m.lpt == 0) {
-            int vote[8], nan2, nan3;
-            expand_votes(sv + m.lp * 4, snan[m.lp] & 3, vote, &nan2);
-            expand_votes(sv + m.lp * 4 + 2, (snan[m.lp] >> 2) & 3, vote + 4, &nan3);
-            const int k2 = select_candidate(vote, nan2), k3 = select_candidate(vote + 4, nan3);
-            ssel[m.lp] = (k2 < 0 ? 15 : k2) | ((k3 < 0 ? 15 : k3) << 4);
-            if (a.votes != nullptr) {
-                int* gv = a.votes + b * 10;
-#pragma unroll
-                for (int k = 0; k < 8; ++k) gv[k] = vote[k];
-                gv[8] = nan2; gv[9] = nan3;
-            }
-            double Rt[12];
-            load_K1_as_P1(calm_of(a, b), Ps);
-            selected_pose(cand, k2 < 0 ? 0 : k2, Rt, Ps + 12);
-            selected_pose(cand + CAND_PAIR, k3 < 0 ? 0 : k3, Rt, Ps + 24);
-        }
-        __syncthreads();
-        // ---- phase 2: t3 scale (R_t_from_TFT.m:68-74) ----------------------------------------------
-        double num = 0.0, den = 0.0;
-        const int sel = live ? ssel[m.lp] : 0;
-        const int k2 = sel & 15;
-        if (live) {
-            // X of the selected pair-2 candidate: (R,t)->Xa, (R,-t)->(Xa, -w), (Rp,-t)->(Xb, -w), (Rp,t)->Xb
-            const bool useA = (k2 == 0 || k2 == 1 || k2 == 15);
-            const double w = ((k2 == 1 || k2 == 2) ? -1.0 : 1.0) * (useA ? Xa[3] : Xb[3]);
-            const double iw = 1.0 / w;
-            const double Xc[3] = {(useA ? Xa[0] : Xb[0]) * iw, (useA ? Xa[1] : Xb[1]) * iw, (useA ? Xa[2] : Xb[2]) * iw};
-            double X3[3], c1[3], c2[3];
-            mat3_vec(Ps + 24, Xc, X3);
-            const double p3[3] = {p6[4], p6[5], 1.0};
-            cross3(p3, X3, c1);
-            cross3(p3, Ps + 33, c2);
-            num = c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2];
-            den = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
-        }
-        red0[threadIdx.x] = num; red1[threadIdx.x] = den;
-        seg_reduce2(red0, red1, m);
-        const bool ok = ((sel & 15) != 15) && ((sel >> 4) != 15);
-        if (live && m.lpt == 0) {
-            const double lam = -red0[threadIdx.x] / red1[threadIdx.x];
-            if (a.scale != nullptr) { a.scale[2 * b] = red0[threadIdx.x]; a.scale[2 * b + 1] = red1[threadIdx.x]; }
-            Ps[33] *= lam; Ps[34] *= lam; Ps[35] *= lam;                          // P3 = K3*[R3 | lam*t3]
-            double Rt[12], dummy[12];
-            const int k3 = sel >> 4;
-            selected_pose(cand, k2 == 15 ? 0 : k2, Rt, dummy);
-            bool fin = true;
-#pragma unroll
-            for (int i = 0; i < 12; ++i) fin = fin && isfinite(Rt[i]);
-            if (a.Rt2 != nullptr)
-#pragma unroll
-                for (int i = 0; i < 12; ++i) a.Rt2[b * 12 + i] = ok ? Rt[i] : qnan;
-            selected_pose(cand + CAND_PAIR, k3 == 15 ? 0 : k3, Rt, dummy);
-#pragma unroll
-            for (int i = 9; i < 12; ++i) Rt[i] *= lam;                             // t3 = lam*t3 (:74)
-#pragma unroll
-            for (int i = 0; i < 12; ++i) fin = fin && isfinite(Rt[i]);
-            if (a.Rt3 != nullptr)
-#pragma unroll
-                for (int i = 0; i < 12; ++i) a.Rt3[b * 12 + i] = ok ? Rt[i] : qnan;
-            int st = 0;
-            if (k2 == 15) st |= ST_NO_POSE_2;
-            if (k3 == 15) st |= ST_NO_POSE_3;
-            if (!fin) st |= ST_NONFINITE;
-            if (a.status != nullptr && st != 0) a.status[b] |= st;
-        }
-        __syncthreads();
-        // ---- phase 3: final triangulation + ReprError ------------------------------------------------
-        double sq = 0.0;
-        if (live) {
-            double X[3];
-            sq = final_point(Ps, Ps + 12, Ps + 24, p6, X);
-            if (a.reconst != nullptr) {
-                double* dst = a.reconst + (b * a.n + m.lpt) * 3;
-                dst[0] = ok ? X[0] : qnan; dst[1] = ok ? X[1] : qnan; dst[2] = ok ? X[2] : qnan;
-            }
-        }
-        red0[threadIdx.x] = sq; red1[threadIdx.x] = 0.0;
-        seg_reduce2(red0, red1, m);
-        if (live && m.lpt == 0) {
-            const double err = sqrt(red0[threadIdx.x] / (3.0 * (double)a.n));       // ReprError.m:65
-            if (a.repr_err != nullptr) a.repr_err[b] = ok ? err : qnan;
-            if (a.status != nullptr && !isfinite(err)) a.status[b] |= ST_NONFINITE;
-        }
-        __syncthreads();
-    }
-}
-
-#endif  // TVF_TAIL_V2
 
 // -------------------------------------------------- T = TFT_from_P(K1[I|0], K2 Rt2, K3 Rt3)
 __global__ void __launch_bounds__(128)
@@ -955,18 +824,40 @@ static inline unsigned tail_grid(const PoseTailArgs& a, int sm_count) {
     return grid_for(a.B, ppb, (long long)sm_count * 32);
 }
 
-void launch_pose_tail_fused(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
-    if (a.B <= 0) return;
-#if TVF_TAIL_V2 && TVF_TAIL_TMA
-    const int tpp = (a.n <= PT_THREADS) ? a.n : PT_THREADS;
-    const int ppb = PT_THREADS / tpp;
+// CTA size of the fused tail: 128 threads (four resident CTAs per SM: the five barriers of an iteration wait for four warps
+// instead of eight) unless 256 threads pack whole problems noticeably better (n = 48: 5 x 48 of 256 against 2 x 48 of 128)
+#ifndef TVF_TAIL_SMALL_CTA
+#define TVF_TAIL_SMALL_CTA 1
+#endif
+static inline int fused_tail_threads(int n) {
+#if TVF_TAIL_SMALL_CTA
+    if (n <= 128) {
+        const int live128 = (128 / n) * n * 2, live256 = (256 / n) * n;      // live threads per 256
+        if (live128 * 16 >= live256 * 15) return 128;
+    }
+#endif
+    return 256;
+}
+
+template <int THREADS>
+static void launch_fused_t(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
+    const int tpp = (a.n <= THREADS) ? a.n : THREADS;
+    const int ppb = THREADS / tpp;
+    const unsigned grid = grid_for(a.B, ppb, (long long)sm_count * 32 * (PT_THREADS / THREADS));
+#if TVF_TAIL_TMA
     const size_t dyn = 2 * (size_t)ppb * ((size_t)a.n * 48 + CAND_SIZE * 8);      // two stages of points + candidate records
     // (set on every launch: the attribute is per device and per context, a process-wide flag would miss the second GPU)
-    cudaFuncSetAttribute(pose_tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    pose_tail_fused_kernel<<<tail_grid(a, sm_count), PT_THREADS, dyn, stream>>>(a);
+    cudaFuncSetAttribute(pose_tail_fused_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    pose_tail_fused_kernel<THREADS><<<grid, THREADS, dyn, stream>>>(a);
 #else
-    pose_tail_fused_kernel<<<tail_grid(a, sm_count), PT_THREADS, 0, stream>>>(a);
+    pose_tail_fused_kernel<THREADS><<<grid, THREADS, 0, stream>>>(a);
 #endif
+}
+
+void launch_pose_tail_fused(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
+    if (a.B <= 0) return;
+    if (fused_tail_threads(a.n) == 128) launch_fused_t<128>(a, sm_count, stream);
+    else launch_fused_t<256>(a, sm_count, stream);
 }
 
 void launch_votes(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
