@@ -433,3 +433,27 @@ def test_group_handle_edge_cases(tvf):
     assert h.call("tvf_pose", 7, dp(c), dp(calm), 0, 20, 0, C.byref(out)) == 0        # B = 0
     with pytest.raises(_lib.TvfError, match="method must be"):
         h.call("tvf_pose", 3, dp(c), dp(calm), 0, 20, 5, C.byref(out))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [33, 48, 64, 65, 100, 128, 129, 256, 257])
+def test_point_counts_across_kernel_selection_boundaries_against_live_oracle(tvf, n):
+    """The estimator picks its kernels by n: bulk-copy-staged moments up to n = 64 and the plain moments kernel above,
+    the fused tail on 128-thread CTAs (n = 33, 64, 100, 128) or 256-thread CTAs (n = 48, 129, 256) and the three un-fused
+    tail kernels from n = 257.  Seven trials each (an odd batch: partial problem groups in every kernel), noise 1 px,
+    trial by trial against the live oracle for both linear methods, votes integer for integer."""
+    from tft_vs_fund_b200 import scene
+    B = 7
+    jobs = [(j, n, [1.0], 50, 0) for j in range(B)]
+    with pw.pool(min(B, 8)) as pool:
+        ref = pool.map(pw.oracle_trial, jobs)
+    C = np.stack([r["Corresp"] for r in ref]); CalM = ref[0]["CalM"]
+    mine = scene.sweep_batch(B, n, noise_levels=[1.0])
+    assert np.array_equal(mine["Corresp"], C)
+    for method, fn in (("tft", tvf.LinearTFTPoseEstimation), ("f", tvf.LinearFPoseEstimation)):
+        res = fn(C, CalM)
+        assert not np.any(res.status), (n, method, res.status)
+        for k in range(B):
+            r = ref[k][method]
+            assert votes_equal(res.votes[k], r[5]), (n, method, k, res.votes[k], r[5])
+            assert_pose_close(r[:5], (res[0][k], res[1][k], res[2][k], res[3][k], res.repr_err[k]), "n=%d %s trial %d" % (n, method, k))

@@ -96,7 +96,7 @@ def counters_json(rep, out, problems_per_launch):
     for r in rows[2:]:
         name = r[ix["Kernel Name"]].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]
         launched = name
-        name = {"tft_stage2_dual_kernel": "tft_stage2_kernel", "tft_moments_kernel": "tft_stage1_kernel",
+        name = {"tft_stage2_dual_kernel": "tft_stage2_kernel", "tft_moments_kernel": "tft_stage1_kernel", "tft_moments_tma_kernel": "tft_stage1_kernel",
                 "tft_stage1_solve_dual_kernel": "tft_stage1_solve_kernel"}.get(name, name)   # the library's profile slot (tvf_kernel_name)
         if name in out_d["kernels"]:
             continue

@@ -27,3 +27,8 @@ for opt in ("focal", "points", "angle"):
 r2 = tvf.LinearTFTPoseEstimation(d["Corresp"], d["CalM"], device=(0, 0)); print("group ok", np.array_equal(r2[3], tvf.LinearTFTPoseEstimation(d["Corresp"], d["CalM"])[3]))
 big = scene.sweep_batch(6000, 20, first_trial=3)
 r = tvf.LinearTFTPoseEstimation(big["Corresp"], big["CalM"]); print("staged ok", int(np.count_nonzero(r.status)))
+# round 2, late: TMA-staged moments (n <= 64) against the plain moments kernel (n = 65), both CTA sizes of the fused tail
+# (n = 48 -> 256 threads, n = 100 -> 128 threads), odd batches
+for nn, bb in ((48, 11), (64, 9), (65, 7), (100, 5)):
+    dn = scene.sweep_batch(bb, nn, first_trial=11)
+    r = tvf.LinearTFTPoseEstimation(dn["Corresp"], dn["CalM"]); print("n=%d ok" % nn, int(np.count_nonzero(r.status)))
