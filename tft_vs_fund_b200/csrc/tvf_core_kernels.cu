@@ -1004,7 +1004,12 @@ struct __align__(16) Stage2DualScratch {
 #define TVF_STAGE2_DUAL 1
 #endif
 
-__global__ void __launch_bounds__(CORE_WARPS * 32, CORE_MINB)
+// resident CTAs per SM the kernel is compiled for: 4 (128 registers, no spills) measured 24.8 ms per 10 M against 26.0 at 5 (96
+// registers, 92 bytes spilled) and 27.4 at 6
+#ifndef TVF_S2D_MINB
+#define TVF_S2D_MINB 4
+#endif
+__global__ void __launch_bounds__(CORE_WARPS * 32, TVF_S2D_MINB)
 tft_stage2_dual_kernel(int normalize, long long B, const double* __restrict__ ws, double* __restrict__ Tout,
                        double* __restrict__ P2out, double* __restrict__ P3out, int* __restrict__ status) {
     __shared__ Stage2DualScratch scratch[CORE_WARPS];
@@ -1440,7 +1445,7 @@ void launch_tft_stage2(const CoreInput& in, const double* ws, double* T, double*
     const bool refine = in.n < REFINE_N_MAX;
 #if TVF_STAGE2_DUAL
     if (!refine) {          // the un-refined step never touches the points again: two problems per warp
-        tft_stage2_dual_kernel<<<core_grid((in.B + 1) / 2, sm_count), CORE_WARPS * 32, 0, stream>>>(in.normalize, in.B, ws, T, P2, P3, status);
+        tft_stage2_dual_kernel<<<core_grid_minb((in.B + 1) / 2, sm_count, TVF_S2D_MINB), CORE_WARPS * 32, 0, stream>>>(in.normalize, in.B, ws, T, P2, P3, status);
         return;
     }
 #endif

@@ -829,11 +829,14 @@ static inline unsigned tail_grid(const PoseTailArgs& a, int sm_count) {
 #ifndef TVF_TAIL_SMALL_CTA
 #define TVF_TAIL_SMALL_CTA 1
 #endif
+#ifndef TVF_TAIL_CTA
+#define TVF_TAIL_CTA 128
+#endif
 static inline int fused_tail_threads(int n) {
 #if TVF_TAIL_SMALL_CTA
-    if (n <= 128) {
-        const int live128 = (128 / n) * n * 2, live256 = (256 / n) * n;      // live threads per 256
-        if (live128 * 16 >= live256 * 15) return 128;
+    if (n <= TVF_TAIL_CTA) {
+        const int live_s = (TVF_TAIL_CTA / n) * n * (256 / TVF_TAIL_CTA), live256 = (256 / n) * n;      // live threads per 256
+        if (live_s * 16 >= live256 * 15) return TVF_TAIL_CTA;
     }
 #endif
     return 256;
@@ -856,7 +859,7 @@ static void launch_fused_t(const PoseTailArgs& a, int sm_count, cudaStream_t str
 
 void launch_pose_tail_fused(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
     if (a.B <= 0) return;
-    if (fused_tail_threads(a.n) == 128) launch_fused_t<128>(a, sm_count, stream);
+    if (fused_tail_threads(a.n) == TVF_TAIL_CTA) launch_fused_t<TVF_TAIL_CTA>(a, sm_count, stream);
     else launch_fused_t<256>(a, sm_count, stream);
 }
 
