@@ -409,8 +409,14 @@ __device__ __forceinline__ void seg_reduce1(double* ra, const PointMap& m) {
 // memory instead of by one thread followed by a barrier, and the per-problem vectors (cameras, [R|t] outputs) are
 // spread one element per thread: a warp holds one or two "first threads", so the single-thread sections cost every
 // warp their full instruction count.  Five CTA barriers per iteration instead of nine.
+#ifndef TVF_TAIL_CTA
+#define TVF_TAIL_CTA 128
+#endif
+#ifndef TVF_TAIL_MINB_SMALL
+#define TVF_TAIL_MINB_SMALL ((TVF_TAIL_MINB * PT_THREADS) / TVF_TAIL_CTA)
+#endif
 template <int THREADS>
-__global__ void __launch_bounds__(THREADS, (TVF_TAIL_MINB * PT_THREADS) / THREADS)
+__global__ void __launch_bounds__(THREADS, THREADS == PT_THREADS ? TVF_TAIL_MINB : TVF_TAIL_MINB_SMALL)
 pose_tail_fused_kernel(PoseTailArgs a) {
     constexpr int MAX_PPB = THREADS / TAIL_FUSED_MIN_N;
     constexpr int PT_THREADS = THREADS;         // (shadows the file-wide constant inside this kernel)
@@ -829,9 +835,6 @@ static inline unsigned tail_grid(const PoseTailArgs& a, int sm_count) {
 #ifndef TVF_TAIL_SMALL_CTA
 #define TVF_TAIL_SMALL_CTA 1
 #endif
-#ifndef TVF_TAIL_CTA
-#define TVF_TAIL_CTA 128
-#endif
 static inline int fused_tail_threads(int n) {
 #if TVF_TAIL_SMALL_CTA
     if (n <= TVF_TAIL_CTA) {
@@ -846,7 +849,7 @@ template <int THREADS>
 static void launch_fused_t(const PoseTailArgs& a, int sm_count, cudaStream_t stream) {
     const int tpp = (a.n <= THREADS) ? a.n : THREADS;
     const int ppb = THREADS / tpp;
-    const unsigned grid = grid_for(a.B, ppb, (long long)sm_count * 32 * (PT_THREADS / THREADS));
+    const unsigned grid = grid_for(a.B, ppb, (long long)sm_count * 16 * (THREADS == PT_THREADS ? TVF_TAIL_MINB : TVF_TAIL_MINB_SMALL));
 #if TVF_TAIL_TMA
     const size_t dyn = 2 * (size_t)ppb * ((size_t)a.n * 48 + CAND_SIZE * 8);      // two stages of points + candidate records
     // (set on every launch: the attribute is per device and per context, a process-wide flag would miss the second GPU)

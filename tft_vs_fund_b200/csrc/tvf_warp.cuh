@@ -36,6 +36,9 @@ constexpr int EIG_MAX_ITER = 80;
 #ifndef TVF_GJ_RAWCOL
 #define TVF_GJ_RAWCOL 0
 #endif
+#ifndef TVF_GJ2_FUSEDRCP
+#define TVF_GJ2_FUSEDRCP 1
+#endif
 #ifndef TVF_PI_STICKY
 #define TVF_PI_STICKY 1
 #endif
@@ -413,8 +416,18 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
     for (int k = 0; k < N; ++k) {
         const double colj = g[k];
         const double d = pivot_floor(__shfl_sync(FULL, colj, k, 16), floor_piv);
+#if TVF_GJ2_FUSEDRCP
+        double seed;                                     // see smallest_eigvec_spd_half2: three dependent operations behind the seed
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(d));
+        const double e = fma(-d, seed, 1.0);
+        const double u = colj * seed;
+        const double t = fma(e, e, e);
+        const double rk = fma(u, t, u);
+        const double piv = fma(seed, t, seed);
+#else
         const double piv = fast_rcp(d);
         const double rk = colj * piv;
+#endif
         double* buf = sbuf + (k & 1) * 32 + h16;
         if (r < N) buf[r] = rk;
         __syncwarp();
@@ -493,6 +506,7 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
 #ifndef TVF_GJ2_PIPE
 #define TVF_GJ2_PIPE 0
 #endif
+
 template <int N>
 __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], double (&g1)[N], const int lane, double* sbuf,
                                                           double* x0_out, double* x1_out, bool* converged) {
@@ -566,8 +580,21 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
         const int a = (k >= NR) ? 1 : 0, rk = k - a * NR;     // pivot row k lives on lane rk of each half, array a
         const double c0j = g0[k], c1j = g1[k];
         const double d = pivot_floor(__shfl_sync(FULL, a ? c1j : c0j, rk, 16), floor_piv);
+#if TVF_GJ2_FUSEDRCP
+        // the scaled column leaves the reciprocal's refinement in THREE dependent FP64 operations behind the MUFU seed
+        // (e | c*seed -> e + e^2 -> c*seed*(1 + e + e^2)) instead of five (two Newton steps, then the product): the seed's
+        // 2^-20 relative error becomes e^3 = 2^-60, and this chain is the serial part of every sweep
+        double seed;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(seed) : "d"(d));
+        const double e = fma(-d, seed, 1.0);
+        const double u0 = c0j * seed, u1 = c1j * seed;
+        const double t = fma(e, e, e);
+        const double r0 = fma(u0, t, u0), r1 = fma(u1, t, u1);
+        const double piv = fma(seed, t, seed);
+#else
         const double piv = fast_rcp(d);
         const double r0 = c0j * piv, r1 = c1j * piv;
+#endif
         double* buf = sbuf + (k & 1) * 64 + h32;
         if (own0) buf[r] = r0;
         if (own1) buf[NR + r] = r1;
