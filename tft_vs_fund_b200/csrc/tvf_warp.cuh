@@ -429,7 +429,7 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
         const double rk = colj * piv;
 #endif
         double* buf = sbuf + (k & 1) * 32 + h16;
-        if (r < N) buf[r] = rk;
+        buf[r] = rk;                               // lanes r >= N hold zero rows: they write zeros into padding nobody uses
         __syncwarp();
         const double c = colj - ((r == k) ? 1.0 : 0.0);
         const double2* b2 = reinterpret_cast<const double2*>(buf);
@@ -517,6 +517,8 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
     const unsigned hmask = 0xffffu << (lane & 16);
     const double floor_piv = 1.0e-3 * (1.0e-13 / N);
     const bool own0 = r < NR, own1 = r + NR < N;
+    static_assert(((N + 1) & ~1) <= 30, "slots 30 and 31 of a half's segment take the idle lanes' stores");
+    const int slot0 = own0 ? r : 30, slot1 = own1 ? NR + r : 31;
     __syncwarp();                              // sbuf may still be read by a previous phase
     if (r == 0) {                              // padding entry of the row buffers (odd N)
         if (NP > N) { sbuf[h32 + N] = 0.0; sbuf[64 + h32 + N] = 0.0; }
@@ -528,7 +530,7 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
     // then starts sweep k+1's serial chain -- pivot shuffle, reciprocal, scaled column, publication into the other
     // parity buffer -- which completes under the remaining 2(N-2) DFMAs of sweep k.  Same operations on the same
     // operands as the plain loop below: bit-identical results.
-    const int dst0 = own0 ? r : 30, dst1 = own1 ? NR + r : 31;      // idle lanes write two unused slots of the segment
+    const int dst0 = slot0, dst1 = slot1;                            // idle lanes write two unused slots of the segment
     double c0j = g0[0], c1j = g1[0];
     double piv = fast_rcp(pivot_floor(__shfl_sync(FULL, c0j, 0, 16), floor_piv));
     double r0 = c0j * piv, r1 = c1j * piv;
@@ -596,8 +598,8 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
         const double r0 = c0j * piv, r1 = c1j * piv;
 #endif
         double* buf = sbuf + (k & 1) * 64 + h32;
-        if (own0) buf[r] = r0;
-        if (own1) buf[NR + r] = r1;
+        buf[slot0] = r0;                           // unconditional stores: idle lanes write the unused slots 30 / 31
+        buf[slot1] = r1;
         __syncwarp();
         const double c0 = c0j - ((a == 0 && r == rk) ? 1.0 : 0.0);
         const double c1 = c1j - ((a == 1 && r == rk) ? 1.0 : 0.0);
@@ -623,8 +625,8 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
 #pragma unroll 1
     for (int it = 0; it < EIG_MAX_ITER; ++it) {
         double* buf = sbuf + (it & 1) * 64 + h32;
-        if (own0) buf[r] = x0;
-        if (own1) buf[NR + r] = x1;
+        buf[slot0] = x0;
+        buf[slot1] = x1;
         __syncwarp();
         const double2* b2 = reinterpret_cast<const double2*>(buf);
         // four independent accumulation chains per row (the mat-vec is latency bound: 3 resident warps per scheduler)
