@@ -30,9 +30,10 @@ namespace {
 constexpr int NSLOT = TVF_NSLOT;
 constexpr int NSCRATCH = 24;
 constexpr int64_t DEFAULT_CHUNK = 65536;        // host-pointer entry points: chunks are the H2D / kernels / D2H pipeline stages
-constexpr int64_t DEFAULT_CHUNK_DEV = 524288;   // device-pointer entry points: fewer, larger launches (less launch and wave-tail
-                                                // overhead: +8 % at n = 20, profiles/r01_variants.md); the 1.2 GB of work space no
-                                                // longer sits in L2, which costs nothing measurable (the path is FP64-bound)
+constexpr int64_t DEFAULT_CHUNK_DEV = 1 << 20;  // device-pointer entry points: fewer, larger launches (less launch and wave-tail
+                                                // overhead: 8.32e7 / 8.48e7 / 8.58e7 / 8.63e7 solves/s at 262 144 / 524 288 / 1 M /
+                                                // 2 M problems per launch, profiles/r02_variants.md); the 2.3 GB of work space is
+                                                // far from L2-resident, which costs nothing measurable (the path is FP64-bound)
 constexpr size_t ARENA_BUDGET = 384u << 20;   // bytes of per-slot work space the automatic chunk aims for
 
 struct Slot {
@@ -156,7 +157,7 @@ int64_t pick_chunk(tvf_handle_t h, int n, int64_t B, bool host_io) {
     if (h->chunk_user <= 0) {   // automatic: keep one slot's work space near ARENA_BUDGET
         size_t payload = (27 + 18 + CORE_WS_TFT + CAND_SIZE + 2) * 8 + 14 * 4;
         if (host_io) payload += (size_t)(6 * n + 27 + 24 + 3 * n + 1) * 8;
-        const int64_t fit = (int64_t)((host_io ? ARENA_BUDGET : 4 * ARENA_BUDGET) / payload);
+        const int64_t fit = (int64_t)((host_io ? ARENA_BUDGET : 8 * ARENA_BUDGET) / payload);
         if (c > fit) c = fit;
     }
     if (c < 1) c = 1;
