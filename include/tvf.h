@@ -238,7 +238,9 @@ int tvf_sweep_run_levels(tvf_handle_t h, int method, int64_t first_trial, int64_
                          double hi_x, double hi_y, double* table);
 
 /* ---- device-pointer forms (inputs/outputs already in HBM; asynchronous on the handle's stream,
- *      return 0 without synchronising -- read `status` after tvf_synchronize) ----------------- */
+ *      return 0 without synchronising -- read `status` after tvf_synchronize).  `corresp` must be
+ *      16-byte aligned (any cudaMalloc'ed buffer, and any problem boundary inside one, is); otherwise
+ *      TVF_ERR_ARG ------------------------------------------------------------------------------ */
 int tvf_linear_tft_pose_dev(tvf_handle_t h, const double* corresp, const double* calm, int calm_batched, int n,
                             int64_t B, double* Rt2, double* Rt3, double* reconst, double* T, double* repr_err,
                             int32_t* status);

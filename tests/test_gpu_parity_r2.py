@@ -457,3 +457,41 @@ def test_point_counts_across_kernel_selection_boundaries_against_live_oracle(tvf
             r = ref[k][method]
             assert votes_equal(res.votes[k], r[5]), (n, method, k, res.votes[k], r[5])
             assert_pose_close(r[:5], (res[0][k], res[1][k], res[2][k], res[3][k], res.repr_err[k]), "n=%d %s trial %d" % (n, method, k))
+
+
+@pytest.mark.gpu
+def test_device_pointer_entry_points_alignment_and_interior_offsets(tvf):
+    """`*_dev` entry points: a correspondence pointer at a problem boundary INSIDE a buffer (16-byte aligned, not 256) gives
+    the same results as the batch it is part of; a pointer that is only 8-byte aligned is refused with TVF_ERR_ARG before any
+    launch (the kernels read 128-bit words and issue bulk copies)."""
+    import ctypes as C
+    import torch
+    from tft_vs_fund_b200 import scene, _lib
+    B, n = 37, 21                                   # 48 n = 1008 bytes per problem: boundaries are 16- but not 32-byte aligned
+    d = scene.sweep_batch(B, n, noise_levels=[1.0])
+    calm = np.ascontiguousarray(d["CalM"].T)
+    dev = torch.device("cuda", 0)
+    corresp = torch.from_numpy(np.ascontiguousarray(d["Corresp"].transpose(0, 2, 1))).to(dev)       # (B, n, 6): 6 x n x B column-major
+    h = _lib.Handle(0)
+    ptr = lambda t, off=0: C.c_void_p(t.data_ptr() + off)
+    d_calm = torch.from_numpy(calm).to(dev)
+    def run(first):
+        k = B - first
+        T = torch.empty((k, 27), dtype=torch.float64, device=dev); rep = torch.empty(k, dtype=torch.float64, device=dev)
+        st = torch.zeros(k, dtype=torch.int32, device=dev)
+        r2 = torch.empty((k, 12), dtype=torch.float64, device=dev); r3 = torch.empty((k, 12), dtype=torch.float64, device=dev)
+        rc = h.lib.tvf_linear_tft_pose_dev(h._h, ptr(corresp, first * n * 48), ptr(d_calm), 0, n, k, ptr(r2), ptr(r3), None, ptr(T), ptr(rep), ptr(st))
+        assert rc == 0, h.error()
+        h.call("tvf_synchronize")
+        return T.cpu().numpy(), rep.cpu().numpy(), st.cpu().numpy()
+    T0, rep0, st0 = run(0)
+    T5, rep5, st5 = run(5)
+    assert (corresp.data_ptr() + 5 * n * 48) % 32 != 0
+    assert np.array_equal(T0[5:], T5) and np.array_equal(rep0[5:], rep5) and not st0.any()
+    res = tvf.LinearTFTPoseEstimation(d["Corresp"], d["CalM"])
+    assert np.array_equal(res.repr_err, rep0)
+    k = B - 1
+    out = torch.empty((k, 27), dtype=torch.float64, device=dev)
+    rc = h.lib.tvf_linear_tft_pose_dev(h._h, ptr(corresp, 8), ptr(d_calm), 0, n, k, None, None, None, ptr(out), None, None)
+    assert rc == _lib.TVF_ERR_ARG and "16-byte aligned" in h.error()
+    h.close()

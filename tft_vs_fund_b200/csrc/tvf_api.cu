@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 #include <sched.h>
 
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -503,6 +504,9 @@ int pose_dev(tvf_handle_t h, Method method, const double* corresp, const double*
              int64_t B, const PoseOut& o) {
     int rc = check_pose_args(h, corresp, calm, n, B, method);
     if (rc != TVF_OK) return rc;
+    // the kernels read the correspondences with 128-bit loads and bulk asynchronous copies: 16-byte alignment (every
+    // cudaMalloc'ed buffer and every problem boundary inside one satisfies it: a problem is 48 n bytes)
+    if ((reinterpret_cast<uintptr_t>(corresp) & 15u) != 0) return fail(h, TVF_ERR_ARG, "device pointer `corresp` must be 16-byte aligned");
     if (B == 0) return TVF_OK;
     TVF_CK(cudaSetDevice(h->device));
     Slot& s = h->slot[0];
