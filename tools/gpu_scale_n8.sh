@@ -2,11 +2,11 @@
 # round 2, call Q (8 GPUs, final build): the scaling bench at N = 8 (host-link ceiling with all ranks at once, shard check)
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/r2q_bench_n8.json 2> gpurun_out/r2q_bench_n8.err
-nvidia-smi topo -m > gpurun_out/r2q_topo.txt 2>&1; nproc >> gpurun_out/r2q_topo.txt; numactl -H >> gpurun_out/r2q_topo.txt 2>&1
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --warmup 3 > gpurun_out/n8_bench_n8.json 2> gpurun_out/n8_bench_n8.err
+nvidia-smi topo -m > gpurun_out/n8_topo.txt 2>&1; nproc >> gpurun_out/n8_topo.txt; numactl -H >> gpurun_out/n8_topo.txt 2>&1
 python - <<'PY'
 import json
-d=json.load(open("gpurun_out/r2q_bench_n8.json"))
+d=json.load(open("gpurun_out/n8_bench_n8.json"))
 print("value %.4g"%d["value"], "e2e %.4g"%d["e2e"]["value"], d["shard_check"], d["host_link"], {k:(round(v["value"]/1e6,2), round(v["frac_of_link_ceiling"],3)) for k,v in d["e2e_variants"].items()}, d["device_resident_sweep"]["value"])
 PY
-tail -3 gpurun_out/r2q_bench_n8.err
+tail -3 gpurun_out/n8_bench_n8.err
