@@ -50,10 +50,10 @@ int hc_dlt(const double* rows, int M, double* x) {
     return it;
 }
 
-// Certified depth signs (dlt4_depth_signs) against the accurate route on every point and candidate of a problem:
+// Certified depth signs (route 0: dlt4_depth_signs, route 1: dlt4_depth_signs_ray) against the accurate route on every point and candidate of a problem:
 // counts[0] = DLTs examined, counts[1] = answered by the shortcut, counts[2] = shortcut answers that DIFFER from the
 // accurate route's signs (must stay 0).
-void hc_vote_signs_check(int mode, const double* model, const double* CalM, const double* corresp, int n, long long* counts) {
+void hc_vote_signs_check(int route, int mode, const double* model, const double* CalM, const double* corresp, int n, long long* counts) {
     double cand[CAND_SIZE];
     if (mode == 0) candidates_from_tft(model, CalM, cand); else candidates_from_f(model, model + 9, CalM, cand);
     double P1[12];
@@ -72,7 +72,11 @@ void hc_vote_signs_check(int mode, const double* model, const double* CalM, cons
                 for (int r = 0; r < 4; ++r) for (int e = 0; e < 4; ++e) b[r][e] = a[r][e];
                 counts[0] += 1;
                 int sx, sz;
-                if (!dlt4_depth_signs(a, r3, tz, &sx, &sz)) continue;
+                if (route == 1) {                  // certified ray / plane test (dlt4_depth_signs_ray)
+                    double m7[7];
+                    dlt_row_minors(ra, rb, m7);
+                    if (!dlt4_depth_signs_ray(m7, a[2], a[3], r3, tz, &sx, &sz)) continue;
+                } else if (!dlt4_depth_signs(a, r3, tz, &sx, &sz)) continue;
                 counts[1] += 1;
                 double X[4];
                 dlt_null<4>(b, X);
@@ -100,8 +104,10 @@ int hc_pose_tail(int mode, const double* model, const double* CalM, const double
             const double* p = corresp + 6 * i;
             double ra[4], rb[4];
             dlt_rows(P1, p[0], p[1], ra, rb);
-            cheirality_point(ra, rb, cand, p[2], p[3], v2, &n2, nullptr, nullptr);
-            cheirality_point(ra, rb, cand + CAND_PAIR, p[4], p[5], v3, &n3, nullptr, nullptr);
+            double m7[7];
+            dlt_row_minors(ra, rb, m7);
+            cheirality_point(ra, rb, m7, cand, p[2], p[3], v2, &n2, nullptr, nullptr);
+            cheirality_point(ra, rb, m7, cand + CAND_PAIR, p[4], p[5], v3, &n3, nullptr, nullptr);
         }
         expand_votes(v2, n2, vote, &nan2);
         expand_votes(v3, n3, vote + 4, &nan3);

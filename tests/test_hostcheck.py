@@ -130,14 +130,17 @@ def test_scene_generator_code_is_bit_exact_with_host_generator(hostcheck):
         assert np.array_equal(out.T, d["Corresp"][j]), j
 
 
-def test_certified_vote_signs_equal_the_accurate_route(hostcheck):
-    """dlt4_depth_signs (the votes' shortcut: normal equations + certificate) against the accurate Householder route,
-    point by point and candidate by candidate: wherever the shortcut answers, its two signs are the accurate route's --
-    on the benchmark scenes, on the long-focal / collinear / minimal scenes of experiments.m:38-47, and under heavy
-    noise; and it does answer for the overwhelming majority of regular points."""
+@pytest.mark.parametrize("route", [1, 0])
+def test_certified_vote_signs_equal_the_accurate_route(hostcheck, route):
+    """The votes' certified shortcuts -- route 1: dlt4_depth_signs_ray (ray / plane intersection + sin-theta certificate,
+    the one the kernels try first), route 0: dlt4_depth_signs (normal equations + certificate) -- against the accurate
+    Householder route, point by point and candidate by candidate: wherever a shortcut answers, its two signs are the
+    accurate route's -- on the benchmark scenes, on the long-focal / collinear / minimal scenes of experiments.m:38-47,
+    and under heavy noise; and it does answer for the overwhelming majority of regular points."""
     tot = np.zeros(3, dtype=np.int64)
     cases = [(20, nz, 50, 0) for nz in (0.0, 0.25, 1.0, 3.0)] + [(12, 1.0, f, 0) for f in (20, 100, 300)] + \
-            [(12, 1.0, 50, a) for a in (166, 175, 179.5, 180)] + [(8, 3.0, 50, 0), (60, 10.0, 50, 0), (25, 30.0, 50, 0)]
+            [(12, 1.0, 50, a) for a in (166, 175, 179.5, 180)] + [(8, 3.0, 50, 0), (60, 10.0, 50, 0), (25, 30.0, 50, 0)] + \
+            [(400, 1.0, 50, 0)]
     for n, noise, f, ang in cases:
         c = np.zeros(3, dtype=np.int64)
         for seed in range(1, 9):
@@ -146,15 +149,15 @@ def test_certified_vote_signs_equal_the_accurate_route(hostcheck):
                 T = o.LinearTFTPoseEstimation(Cr, CalM)[3]
             except RuntimeError:
                 continue
-            hostcheck.hc_vote_signs_check(0, dp(T.ravel(order="F").copy()), dp(cm(CalM)), dp(cm(Cr)), n,
+            hostcheck.hc_vote_signs_check(route, 0, dp(T.ravel(order="F").copy()), dp(cm(CalM)), dp(cm(Cr)), n,
                                           c.ctypes.data_as(C.POINTER(C.c_longlong)))
             if n >= 8:
                 F21, F31 = o.LinearFPoseEstimation(Cr, CalM, return_F=True)[5:7]
-                hostcheck.hc_vote_signs_check(1, dp(np.concatenate([cm(F21), cm(F31)])), dp(cm(CalM)), dp(cm(Cr)), n,
+                hostcheck.hc_vote_signs_check(route, 1, dp(np.concatenate([cm(F21), cm(F31)])), dp(cm(CalM)), dp(cm(Cr)), n,
                                               c.ctypes.data_as(C.POINTER(C.c_longlong)))
         assert c[2] == 0, (n, noise, f, ang, c)
         if noise <= 3.0 and f == 50 and ang == 0 and n >= 12:
             assert c[1] >= 0.95 * c[0], (n, noise, f, ang, c)          # the benchmark scene: the shortcut almost always answers
-        print("  n=%d noise=%g f=%g angle=%g: %d DLTs, %.1f %% answered by the shortcut" % (n, noise, f, ang, c[0], 100.0 * c[1] / max(1, c[0])))
+        print("  route %d n=%d noise=%g f=%g angle=%g: %d DLTs, %.1f %% answered by the shortcut" % (route, n, noise, f, ang, c[0], 100.0 * c[1] / max(1, c[0])))
         tot += c
-    print("certified sign shortcut: %d DLTs, %d answered (%.1f %%), %d disagreements" % (tot[0], tot[1], 100.0 * tot[1] / tot[0], tot[2]))
+    print("certified sign shortcut (route %d): %d DLTs, %d answered (%.1f %%), %d disagreements" % (route, tot[0], tot[1], 100.0 * tot[1] / tot[0], tot[2]))

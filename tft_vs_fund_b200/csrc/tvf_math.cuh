@@ -474,6 +474,51 @@ TVF_HD bool dlt4_depth_signs(const double (&a)[4][4], const double* r3, double t
     return true;
 }
 
+// ------------------------------------------------- depth signs from the ray / plane intersection, certified
+// A cheaper certificate for the same two signs, tried first.  Let B = the first three rows of the 4 x 4 DLT system A (both
+// rows of view 1 and the first row of the candidate view) and rd its fourth row.  The 4-D cross product Xt of B's rows is
+// the null vector of B -- geometrically the point where the ray of view 1 meets the plane that rd's sibling row
+// back-projects -- and costs twelve multiply-adds from the 2 x 2 minors of the view-1 rows, which all four candidates of
+// a point share.  With xh = Xt/|Xt| and v the smallest right singular vector of A:
+//   |A xh| = |rd.Xt| / |Xt|                                    (B xh = 0),
+//   |A xh|^2 = sum_i sigma_i^2 (v_i.xh)^2 >= sigma_3(A)^2 sin^2(angle(xh, v))
+//   sigma_3(A) >= s_3(B)                                        (interlacing: B is A without a row)
+//   s_3(B) = |Xt| / (s_1 s_2) >= 2 |Xt| / |B|_F^2               (|Xt| = s_1 s_2 s_3, AM-GM)
+// so sin(angle) <= eta = |rd.Xt| |B|_F^2 / (2 |Xt|^2).  For eta <= 0.2 the distance between the unit vectors is
+// <= 1.01 eta =: d, the sign-deciding products move by at most  |D(x3 x4)| <= d + d^2/2  and
+// |D(z x4)| <= sqrt(2) d (2 + d)  (|[r3 tz]| <= sqrt 2), and the routine answers only when both products of xh exceed
+// 2.1 d resp. 3.2 d plus an absolute 1e-6 (rounding of the cofactors, guarded by |Xt|^2 >= 1e-12 |B|_F^6, and of the
+// accurate route itself).  Everything is written without a division; any NaN fails a comparison and returns false.
+// m7: minors M01, M02, M03, M12, M13, M23 of the view-1 rows (M_jk = a_j b_k - a_k b_j) and |a|^2 + |b|^2.
+TVF_HD void dlt_row_minors(const double* ra, const double* rb, double* m7) {
+    m7[0] = ra[0] * rb[1] - ra[1] * rb[0]; m7[1] = ra[0] * rb[2] - ra[2] * rb[0]; m7[2] = ra[0] * rb[3] - ra[3] * rb[0];
+    m7[3] = ra[1] * rb[2] - ra[2] * rb[1]; m7[4] = ra[1] * rb[3] - ra[3] * rb[1]; m7[5] = ra[2] * rb[3] - ra[3] * rb[2];
+    m7[6] = (ra[0] * ra[0] + ra[1] * ra[1] + ra[2] * ra[2] + ra[3] * ra[3]) + (rb[0] * rb[0] + rb[1] * rb[1] + rb[2] * rb[2] + rb[3] * rb[3]);
+}
+TVF_HD bool dlt4_depth_signs_ray(const double* m7, const double* rc, const double* rd, const double* r3, double tz,
+                                 int* s_x, int* s_z) {
+    const double M01 = m7[0], M02 = m7[1], M03 = m7[2], M12 = m7[3], M13 = m7[4], M23 = m7[5];
+    const double X0 = rc[1] * M23 - rc[2] * M13 + rc[3] * M12;
+    const double X1 = -(rc[0] * M23 - rc[2] * M03 + rc[3] * M02);
+    const double X2 = rc[0] * M13 - rc[1] * M03 + rc[3] * M01;
+    const double X3 = -(rc[0] * M12 - rc[1] * M02 + rc[2] * M01);
+    const double xx = X0 * X0 + X1 * X1 + X2 * X2 + X3 * X3;
+    const double b2 = m7[6] + (rc[0] * rc[0] + rc[1] * rc[1] + rc[2] * rc[2] + rc[3] * rc[3]);
+    const double rho = rd[0] * X0 + rd[1] * X1 + rd[2] * X2 + rd[3] * X3;
+    const double rb2 = fabs(rho) * b2;                            // = 2 eta |Xt|^2
+    if (!(rb2 < 0.4 * xx)) return false;                          // eta < 0.2 (also catches NaN and xx = 0)
+    if (!(xx >= 1.0e-12 * (b2 * b2 * b2))) return false;          // cofactors not dominated by cancellation
+    const double q1 = X2 * X3;                                    // sign(X3 / X4), times |Xt|^2
+    const double zc = r3[0] * X0 + r3[1] * X1 + r3[2] * X2 + tz * X3;
+    const double q2 = zc * X3;                                    // sign(([R t] X)_3 / X4), times |Xt|^2
+    const double floor_ = 1.0e-6 * xx;
+    if (!(fabs(q1) >= 1.0605 * rb2 + floor_)) return false;       // 2.1 * 1.01 eta
+    if (!(fabs(q2) >= 1.616 * rb2 + floor_)) return false;        // 3.2 * 1.01 eta
+    *s_x = (q1 > 0.0) ? 1 : -1;
+    *s_z = (q2 > 0.0) ? 1 : -1;
+    return true;
+}
+
 // rows of the DLT system contributed by one view (triangulation3D.m:58-59):
 // [0 -1 y; 1 0 -x]*P  ->  (-P(2,:) + y*P(3,:) ; P(1,:) - x*P(3,:)).  P 3x4 column-major.
 TVF_HD void dlt_rows(const double* P, double x, double y, double* row_a, double* row_b) {

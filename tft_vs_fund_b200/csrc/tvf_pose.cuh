@@ -12,6 +12,16 @@
 #ifndef TVF_VOTE_FAST_SIGNS
 #define TVF_VOTE_FAST_SIGNS 1
 #endif
+// second-chance certificate from the 4 x 4 normal equations (dlt4_depth_signs, round 2 first half) between the ray test
+// and the accurate route: off -- what the ray test declines it mostly declines too
+#ifndef TVF_VOTE_GRAM_SIGNS
+#define TVF_VOTE_GRAM_SIGNS 0
+#endif
+// certified ray / plane test (dlt4_depth_signs_ray) first; 0 with TVF_VOTE_GRAM_SIGNS=1 and TVF_TAIL_REUSE_X=1 is the tail of
+// the first half of round 2
+#ifndef TVF_VOTE_RAY_SIGNS
+#define TVF_VOTE_RAY_SIGNS 1
+#endif
 
 namespace tvf {
 
@@ -136,7 +146,10 @@ TVF_HD void triangulate3(const double* Pa, const double* Pb, const double* Pc, c
 // vote(Rp,-t) = -vote(Rp,t) -- not an approximation, the same numbers the four separate DLTs give.
 // v[0] += vote of (R,t), v[1] += vote of (Rp,t); nanmask bit 0/1 set when that sum is NaN.
 // Xa/Xb (may be null) receive the homogeneous solutions for (R,t) and (Rp,t).
-TVF_HD void cheirality_point(const double* ra, const double* rb, const double* c, double x2, double y2,
+// m7 (may be null): dlt_row_minors of (ra, rb).  When the solutions themselves are not asked for, the two depth signs
+// come from the certified ray/plane test (dlt4_depth_signs_ray, ~45 FP64 operations) and only the DLTs it declines
+// (0.1 % of the sweep's, none at n = 10 000) take the accurate route.
+TVF_HD void cheirality_point(const double* ra, const double* rb, const double* m7, const double* c, double x2, double y2,
                              int* v, int* nanmask, double* Xa, double* Xb) {
     constexpr int kUnroll = TVF_CHEIR_UNROLL;
 #pragma unroll(kUnroll)
@@ -144,12 +157,18 @@ TVF_HD void cheirality_point(const double* ra, const double* rb, const double* c
         double P[12], r3[3], tz;
         candidate_camera(c, q == 0 ? 0 : 3, P, r3, &tz);
         double a[4][4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { a[0][e] = ra[e]; a[1][e] = rb[e]; }
         dlt_rows(P, x2, y2, a[2], a[3]);
         double* dst = (q == 0) ? Xa : Xb;
-#if TVF_VOTE_FAST_SIGNS
-        if (dst == nullptr) {          // only the two depth signs are needed: certified shortcut, else the accurate route below
+#if TVF_VOTE_FAST_SIGNS && TVF_VOTE_RAY_SIGNS
+        if (dst == nullptr) {          // only the two depth signs are needed: certified shortcuts, else the accurate route below
+            int sx, sz;
+            if (m7 != nullptr && dlt4_depth_signs_ray(m7, a[2], a[3], r3, tz, &sx, &sz)) { v[q] += sx + sz; continue; }
+        }
+#endif
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { a[0][e] = ra[e]; a[1][e] = rb[e]; }
+#if TVF_VOTE_FAST_SIGNS && TVF_VOTE_GRAM_SIGNS
+        if (dst == nullptr) {
             int sx, sz;
             if (dlt4_depth_signs(a, r3, tz, &sx, &sz)) { v[q] += sx + sz; continue; }
         }

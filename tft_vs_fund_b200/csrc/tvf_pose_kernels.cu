@@ -134,10 +134,11 @@ votes_kernel(PoseTailArgs a) {
             for (int pt = m.lpt; pt < a.n; pt += m.tpp) {
                 const double2* q = reinterpret_cast<const double2*>(a.corresp + (b * a.n + pt) * 6);
                 const double2 p1 = __ldg(q), p2 = __ldg(q + 1), p3 = __ldg(q + 2);
-                double ra[4], rb[4];
+                double ra[4], rb[4], m7[7];
                 dlt_rows(P1, p1.x, p1.y, ra, rb);
-                cheirality_point(ra, rb, cand, p2.x, p2.y, v2, &n2, nullptr, nullptr);
-                cheirality_point(ra, rb, cand + CAND_PAIR, p3.x, p3.y, v3, &n3, nullptr, nullptr);
+                dlt_row_minors(ra, rb, m7);
+                cheirality_point(ra, rb, m7, cand, p2.x, p2.y, v2, &n2, nullptr, nullptr);
+                cheirality_point(ra, rb, m7, cand + CAND_PAIR, p3.x, p3.y, v3, &n3, nullptr, nullptr);
             }
             int vote[8], nan2, nan3;
             expand_votes(v2, n2, vote, &nan2);
@@ -365,6 +366,12 @@ final_large_kernel(PoseTailArgs a) {
 #ifndef TVF_TAIL_MINB
 #define TVF_TAIL_MINB 2
 #endif
+// 1 = round-2 form: both pair-2 candidates are triangulated accurately during the votes and the selected solution is
+// reused for the scale (3 accurate DLTs per point); 0 = all four votes by the certified ray test, ONE accurate two-view
+// DLT of the selected pose in the scale phase
+#ifndef TVF_TAIL_REUSE_X
+#define TVF_TAIL_REUSE_X 0
+#endif
 #ifndef TVF_TAIL_TMA
 #define TVF_TAIL_TMA 1
 #endif
@@ -470,7 +477,10 @@ pose_tail_fused_kernel(PoseTailArgs a) {
         const double* cand = a.cand + (live ? b : 0) * CAND_SIZE;
 #endif
         double* Ps = sP + (live ? m.lp : 0) * 36;
-        double p6[6] = {0, 0, 0, 0, 0, 0}, Xa[4] = {0, 0, 0, 1}, Xb[4] = {0, 0, 0, 1};
+        double p6[6] = {0, 0, 0, 0, 0, 0};
+#if TVF_TAIL_REUSE_X
+        double Xa[4] = {0, 0, 0, 1}, Xb[4] = {0, 0, 0, 1};
+#endif
         // ---- phase 1: cheirality votes (R_t_from_TFT.m:91-104) --------------------------------
         if (live) {
             double P1[12];
@@ -483,11 +493,16 @@ pose_tail_fused_kernel(PoseTailArgs a) {
             const double2 q1 = __ldg(q), q2 = __ldg(q + 1), q3 = __ldg(q + 2);
 #endif
             p6[0] = q1.x; p6[1] = q1.y; p6[2] = q2.x; p6[3] = q2.y; p6[4] = q3.x; p6[5] = q3.y;
-            double ra[4], rb[4];
+            double ra[4], rb[4], m7[7];
             dlt_rows(P1, p6[0], p6[1], ra, rb);
+            dlt_row_minors(ra, rb, m7);
             int v2[2] = {0, 0}, v3[2] = {0, 0}, n2 = 0, n3 = 0;
-            cheirality_point(ra, rb, cand, p6[2], p6[3], v2, &n2, Xa, Xb);
-            cheirality_point(ra, rb, cand + CAND_PAIR, p6[4], p6[5], v3, &n3, nullptr, nullptr);
+#if TVF_TAIL_REUSE_X
+            cheirality_point(ra, rb, m7, cand, p6[2], p6[3], v2, &n2, Xa, Xb);
+#else
+            cheirality_point(ra, rb, m7, cand, p6[2], p6[3], v2, &n2, nullptr, nullptr);
+#endif
+            cheirality_point(ra, rb, m7, cand + CAND_PAIR, p6[4], p6[5], v3, &n3, nullptr, nullptr);
             int* dst = sv + m.lp * 4;
             if (v2[0]) atomicAdd(dst + 0, v2[0]);
             if (v2[1]) atomicAdd(dst + 1, v2[1]);
@@ -519,6 +534,7 @@ pose_tail_fused_kernel(PoseTailArgs a) {
         // ---- phase 2: t3 scale (R_t_from_TFT.m:68-74) ----------------------------------------------
         double num = 0.0, den = 0.0;
         if (live) {
+#if TVF_TAIL_REUSE_X
             // X of the selected pair-2 candidate: (R,t)->Xa, (R,-t)->(Xa, -w), (Rp,-t)->(Xb, -w), (Rp,t)->Xb
             const bool useA = (k2 == 0 || k2 == 1 || k2 == 15);
             const double w = ((k2 == 1 || k2 == 2) ? -1.0 : 1.0) * (useA ? Xa[3] : Xb[3]);
@@ -531,6 +547,10 @@ pose_tail_fused_kernel(PoseTailArgs a) {
             cross3(p3, Ps + 33, c2);
             num = c1[0] * c2[0] + c1[1] * c2[1] + c1[2] * c2[2];
             den = c2[0] * c2[0] + c2[1] * c2[1] + c2[2] * c2[2];
+#else
+            // the ONE accurate two-view DLT of the point: cameras 1 and 2 of the selected pose (R_t_from_TFT.m:69)
+            scale_point(Ps, Ps + 12, Ps + 24, Ps + 33, p6, &num, &den);
+#endif
         }
         red0[threadIdx.x] = num; red1[threadIdx.x] = den;
         seg_reduce2_split(red0, red1, m);
