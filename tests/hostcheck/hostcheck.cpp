@@ -10,6 +10,8 @@ using namespace tvf;
 extern "C" {
 
 void hc_null3(const double* M, double* v) { null3(M, v); }
+// the QR + inverse-iteration route alone: 1 = it answered (v valid), 0 = it declined (null3 then takes the Jacobi route)
+int hc_null3_qr(const double* M, int transpose, double* v) { return null3_qr(M, transpose != 0, v) ? 1 : 0; }
 
 int hc_jacobi_sweeps(const double* M) {
     double A[9], V[9], s[3];

@@ -29,6 +29,51 @@ def test_null3_and_svd3(hostcheck):
             assert np.allclose(U.T @ U, np.eye(3), atol=1e-12) and abs(np.linalg.det(U) * np.linalg.det(V) - 1) < 2.1
 
 
+def test_null3_qr_route_and_its_fallback(hostcheck):
+    """null3's fast route (Householder QR + inverse iteration, tvf_math.cuh::null3_qr) against numpy's SVD on the matrices
+    it meets -- nearly rank-2 slices at every gap up to s3/s2 = 0.3, exactly rank-2 matrices, both orientations -- and its
+    refusals: two (nearly) equal smallest singular values, rank-1, zero, NaN / Inf input must be DECLINED (return 0) so that
+    null3 takes the Jacobi route, and null3 itself must then still equal the SVD wherever that is defined."""
+    rng = np.random.RandomState(5)
+    answered = 0
+    for trial in range(400):
+        U, _ = np.linalg.qr(rng.randn(3, 3)); V, _ = np.linalg.qr(rng.randn(3, 3))
+        gap = [0.0, 1e-12, 1e-6, 1e-3, 0.05, 0.3][trial % 6]
+        s = np.array([1.0 + rng.rand(), 0.2 + rng.rand(), 0.0]); s[2] = gap * s[1]
+        M = (U * s) @ V.T * 10.0 ** rng.randint(-3, 4)
+        for tr in (0, 1):
+            v = np.zeros(3)
+            ok = hostcheck.hc_null3_qr(dp(cm(M)), tr, dp(v))
+            ref = np.linalg.svd(M.T if tr else M)[2][2]
+            if gap >= 0.3 and not ok:          # rate (s3/s2)^2 = 0.09: may need more than NULL3_MAX_IT steps -> declined, fine
+                continue
+            assert ok == 1, (trial, gap)
+            answered += 1
+            assert min(np.linalg.norm(v - ref), np.linalg.norm(v + ref)) < 1e-12 / max(1e-3, 1.0 - gap), (trial, gap, v, ref)
+    # refusals
+    v = np.zeros(3)
+    U, _ = np.linalg.qr(rng.randn(3, 3)); V, _ = np.linalg.qr(rng.randn(3, 3))
+    for s in ([1.0, 0.5, 0.5], [1.0, 0.5, 0.4999]):
+        M = (U * np.array(s)) @ V.T
+        ok = hostcheck.hc_null3_qr(dp(cm(M)), 0, dp(v))
+        if ok:      # an answer is allowed only if it is right (a spectral gap the iteration could resolve in 12 steps)
+            ref = np.linalg.svd(M)[2][2]
+            assert s[1] != s[2] and min(np.linalg.norm(v - ref), np.linalg.norm(v + ref)) < 1e-9, s
+    # rank 1: the null space is two-dimensional and V(:,3) is whatever the SVD picks in it (the reference's LAPACK too); an answer
+    # must be a unit vector of that null space
+    M = (U * np.array([1.0, 1e-20, 0.0])) @ V.T
+    if hostcheck.hc_null3_qr(dp(cm(M)), 0, dp(v)):
+        assert abs(np.linalg.norm(v) - 1.0) < 1e-12 and np.linalg.norm(M @ v) < 1e-15
+    for bad in (np.zeros((3, 3)), np.full((3, 3), np.nan), np.array([[1.0, 2, 3], [4, np.inf, 6], [7, 8, 9]])):
+        assert hostcheck.hc_null3_qr(dp(cm(bad)), 0, dp(v)) == 0
+    # null3 (fast route + fallback) on a matrix the fast route declines: well separated s3 but s2 == s3 is not; use equal pair
+    M = (U * np.array([1.0, 0.5, 0.49])) @ V.T
+    hostcheck.hc_null3(dp(cm(M)), dp(v))
+    ref = np.linalg.svd(M)[2][2]
+    assert min(np.linalg.norm(v - ref), np.linalg.norm(v + ref)) < 1e-10
+    assert answered >= 660            # every matrix with s3/s2 <= 0.05 was answered
+
+
 def test_transform_tft_and_tft_from_p(hostcheck):
     rs = np.random.RandomState(1)
     for inverse in (0, 1):

@@ -118,7 +118,10 @@ candidates_kernel(int mode, const double* __restrict__ model, PoseTailArgs a) {
 }
 
 // ------------------------------------------------------------------------ votes
-__global__ void __launch_bounds__(PT_THREADS, 2)
+#ifndef TVF_VOTES_MINB
+#define TVF_VOTES_MINB 2
+#endif
+__global__ void __launch_bounds__(PT_THREADS, TVF_VOTES_MINB)
 votes_kernel(PoseTailArgs a) {
     __shared__ int sv[PT_THREADS * 10];
     const PointMap m(a.n);
