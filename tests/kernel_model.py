@@ -64,7 +64,8 @@ def smallest_eigvec_spd(G, max_iter=80, tol=4e-15):
         A = newA
     # pivot-normalised power iteration (TVF_EIG_PIVOTNORM): the iterate is scaled so that its largest component is 1
     # (dividing by the signed pivot also absorbs the sign of -M); one exact 2-norm normalisation at the end
-    x = np.ones(N)
+    # start: M (e_0 + e_{N/2} + e_{N-1}), the sum of three columns of the inverse (TVF_PI_FREE_START): a free first application
+    x = A[:, 0] + A[:, N // 2] + A[:, N - 1]
     its = 0
     for its in range(1, max_iter + 1):
         z = A @ x

@@ -45,6 +45,12 @@ constexpr int EIG_MAX_ITER = 80;
 #ifndef TVF_EIG_TOL
 #define TVF_EIG_TOL 4.0e-15
 #endif
+// Start vector of the power iterations: M (e_0 + e_{N/2} + e_{N-1}) instead of the vector of ones -- with M = -(G + delta I)^-1
+// in registers row by row, that product is the sum of three entries of the lane's own row: the first application of M costs two
+// additions instead of a mat-vec (one iteration of ~7 saved; the fixed point and the stopping test are unchanged).
+#ifndef TVF_PI_FREE_START
+#define TVF_PI_FREE_START 1
+#endif
 // Largest change of a component's MAGNITUDE between two steps.  Magnitudes, not signed values: the iterate is normalised
 // by its largest component, and when two components of opposite sign tie for that role to within rounding the pivot can
 // alternate between them from step to step, flipping the sign of the whole (otherwise converged) vector each time.  The
@@ -444,7 +450,11 @@ __device__ __forceinline__ double smallest_eigvec_spd_half(double (&g)[N], const
 #endif
     __syncwarp();
     // g holds -(G + delta I)^-1.  Pivot-normalised power iteration (see smallest_eigvec_spd), per half.
+#if TVF_PI_FREE_START
+    double x = (r < N) ? (g[0] + g[N / 2]) + g[N - 1] : 0.0;
+#else
     double x = (r < N) ? 1.0 : 0.0;
+#endif
     bool done = false;                          // uniform within a half
 #if TVF_PI_STICKY
     int piv = h16;                              // absolute lane of this half's pivot component
@@ -616,7 +626,11 @@ __device__ __forceinline__ void smallest_eigvec_spd_half2(double (&g0)[N], doubl
 #endif
     __syncwarp();
     // g holds -(G + delta I)^-1.  Pivot-normalised power iteration (see smallest_eigvec_spd), per half.
+#if TVF_PI_FREE_START
+    double x0 = own0 ? (g0[0] + g0[N / 2]) + g0[N - 1] : 0.0, x1 = own1 ? (g1[0] + g1[N / 2]) + g1[N - 1] : 0.0;
+#else
     double x0 = own0 ? 1.0 : 0.0, x1 = own1 ? 1.0 : 0.0;
+#endif
     bool done = false;                          // uniform within a half
 #if TVF_PI_STICKY
     int src = lane & 16;                        // pivot component: row of array 0 (pivA) or 1 on absolute lane src
