@@ -781,7 +781,10 @@ tft_stage1_solve_cs_kernel(long long B, double* __restrict__ ws, int* __restrict
 }
 
 // =========================================================================== TFT epipoles
-__global__ void __launch_bounds__(128, 4)
+#ifndef TVF_EPI_MINB
+#define TVF_EPI_MINB 4
+#endif
+__global__ void __launch_bounds__(128, TVF_EPI_MINB)
 tft_epipoles_kernel(double* __restrict__ ws, long long B) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;

@@ -83,7 +83,12 @@ __device__ __forceinline__ const double* calm_of(const PoseTailArgs& a, long lon
 #ifndef TVF_CAND_THREADS
 #define TVF_CAND_THREADS 128
 #endif
-__global__ void __launch_bounds__(TVF_CAND_THREADS, 512 / TVF_CAND_THREADS)
+#ifndef TVF_CAND_PER_SM
+#define TVF_CAND_PER_SM 384          // resident threads per SM the candidates kernel is compiled for (register cap 65536 / this):
+                                     // 384 (168 registers, 140 bytes spilled) 4.98 ms per 10 M against 5.12 at 512 (128 registers, 1.1 KB
+                                     // spilled), 5.63 at 256 (196 registers, no spills), 6.02 at 640
+#endif
+__global__ void __launch_bounds__(TVF_CAND_THREADS, TVF_CAND_PER_SM / TVF_CAND_THREADS)
 candidates_kernel(int mode, const double* __restrict__ model, PoseTailArgs a) {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= a.B) return;
