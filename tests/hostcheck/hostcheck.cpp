@@ -74,10 +74,14 @@ void hc_vote_signs_check(int route, int mode, const double* model, const double*
                 for (int r = 0; r < 4; ++r) for (int e = 0; e < 4; ++e) b[r][e] = a[r][e];
                 counts[0] += 1;
                 int sx, sz;
-                if (route == 1) {                  // certified ray / plane test (dlt4_depth_signs_ray)
+                if (route == 1) {                  // certified ray / plane test (dlt4_depth_signs_ray), general form
                     double m7[7];
                     dlt_row_minors(ra, rb, m7);
                     if (!dlt4_depth_signs_ray(m7, a[2], a[3], r3, tz, &sx, &sz)) continue;
+                } else if (route == 2) {           // the form for a view-1 camera K1*[I | 0] (what the kernels run)
+                    double m7[7];
+                    dlt_row_minors<true>(ra, rb, m7);
+                    if (!dlt4_depth_signs_ray<true>(m7, a[2], a[3], r3, tz, &sx, &sz)) continue;
                 } else if (!dlt4_depth_signs(a, r3, tz, &sx, &sz)) continue;
                 counts[1] += 1;
                 double X[4];
@@ -107,9 +111,9 @@ int hc_pose_tail(int mode, const double* model, const double* CalM, const double
             double ra[4], rb[4];
             dlt_rows(P1, p[0], p[1], ra, rb);
             double m7[7];
-            dlt_row_minors(ra, rb, m7);
-            cheirality_point(ra, rb, m7, cand, p[2], p[3], v2, &n2, nullptr, nullptr);
-            cheirality_point(ra, rb, m7, cand + CAND_PAIR, p[4], p[5], v3, &n3, nullptr, nullptr);
+            dlt_row_minors<true>(ra, rb, m7);
+            cheirality_point<true>(ra, rb, m7, cand, p[2], p[3], v2, &n2, nullptr, nullptr);
+            cheirality_point<true>(ra, rb, m7, cand + CAND_PAIR, p[4], p[5], v3, &n3, nullptr, nullptr);
         }
         expand_votes(v2, n2, vote, &nan2);
         expand_votes(v3, n3, vote + 4, &nan3);

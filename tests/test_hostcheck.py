@@ -175,10 +175,10 @@ def test_scene_generator_code_is_bit_exact_with_host_generator(hostcheck):
         assert np.array_equal(out.T, d["Corresp"][j]), j
 
 
-@pytest.mark.parametrize("route", [1, 0])
+@pytest.mark.parametrize("route", [2, 1, 0])
 def test_certified_vote_signs_equal_the_accurate_route(hostcheck, route):
-    """The votes' certified shortcuts -- route 1: dlt4_depth_signs_ray (ray / plane intersection + sin-theta certificate,
-    the one the kernels try first), route 0: dlt4_depth_signs (normal equations + certificate) -- against the accurate
+    """The votes' certified shortcuts -- route 2: dlt4_depth_signs_ray<true> (ray / plane intersection + sin-theta certificate
+    in the form for a view-1 camera K1*[I | 0]: what the kernels run first), route 1: its general form, route 0: dlt4_depth_signs (normal equations + certificate) -- against the accurate
     Householder route, point by point and candidate by candidate: wherever a shortcut answers, its two signs are the
     accurate route's -- on the benchmark scenes, on the long-focal / collinear / minimal scenes of experiments.m:38-47,
     and under heavy noise; and it does answer for the overwhelming majority of regular points."""

@@ -575,17 +575,27 @@ TVF_HD bool dlt4_depth_signs(const double (&a)[4][4], const double* r3, double t
 // 2.1 d resp. 3.2 d plus an absolute 1e-6 (rounding of the cofactors, guarded by |Xt|^2 >= 1e-12 |B|_F^6, and of the
 // accurate route itself).  Everything is written without a division; any NaN fails a comparison and returns false.
 // m7: minors M01, M02, M03, M12, M13, M23 of the view-1 rows (M_jk = a_j b_k - a_k b_j) and |a|^2 + |b|^2.
+// AFF: the view-1 camera is K1*[I | 0] (always, in this pipeline), so both of its rows end in an exact zero: the three minors
+// with index 3 vanish and three of the four cofactors are single products -- the same values as the general form.
+template <bool AFF = false>
 TVF_HD void dlt_row_minors(const double* ra, const double* rb, double* m7) {
-    m7[0] = ra[0] * rb[1] - ra[1] * rb[0]; m7[1] = ra[0] * rb[2] - ra[2] * rb[0]; m7[2] = ra[0] * rb[3] - ra[3] * rb[0];
-    m7[3] = ra[1] * rb[2] - ra[2] * rb[1]; m7[4] = ra[1] * rb[3] - ra[3] * rb[1]; m7[5] = ra[2] * rb[3] - ra[3] * rb[2];
-    m7[6] = (ra[0] * ra[0] + ra[1] * ra[1] + ra[2] * ra[2] + ra[3] * ra[3]) + (rb[0] * rb[0] + rb[1] * rb[1] + rb[2] * rb[2] + rb[3] * rb[3]);
+    m7[0] = ra[0] * rb[1] - ra[1] * rb[0]; m7[1] = ra[0] * rb[2] - ra[2] * rb[0];
+    m7[3] = ra[1] * rb[2] - ra[2] * rb[1];
+    if (AFF) {
+        m7[2] = 0.0; m7[4] = 0.0; m7[5] = 0.0;
+        m7[6] = (ra[0] * ra[0] + ra[1] * ra[1] + ra[2] * ra[2]) + (rb[0] * rb[0] + rb[1] * rb[1] + rb[2] * rb[2]);
+    } else {
+        m7[2] = ra[0] * rb[3] - ra[3] * rb[0]; m7[4] = ra[1] * rb[3] - ra[3] * rb[1]; m7[5] = ra[2] * rb[3] - ra[3] * rb[2];
+        m7[6] = (ra[0] * ra[0] + ra[1] * ra[1] + ra[2] * ra[2] + ra[3] * ra[3]) + (rb[0] * rb[0] + rb[1] * rb[1] + rb[2] * rb[2] + rb[3] * rb[3]);
+    }
 }
+template <bool AFF = false>
 TVF_HD bool dlt4_depth_signs_ray(const double* m7, const double* rc, const double* rd, const double* r3, double tz,
                                  int* s_x, int* s_z) {
     const double M01 = m7[0], M02 = m7[1], M03 = m7[2], M12 = m7[3], M13 = m7[4], M23 = m7[5];
-    const double X0 = rc[1] * M23 - rc[2] * M13 + rc[3] * M12;
-    const double X1 = -(rc[0] * M23 - rc[2] * M03 + rc[3] * M02);
-    const double X2 = rc[0] * M13 - rc[1] * M03 + rc[3] * M01;
+    const double X0 = AFF ? rc[3] * M12 : rc[1] * M23 - rc[2] * M13 + rc[3] * M12;
+    const double X1 = AFF ? -(rc[3] * M02) : -(rc[0] * M23 - rc[2] * M03 + rc[3] * M02);
+    const double X2 = AFF ? rc[3] * M01 : rc[0] * M13 - rc[1] * M03 + rc[3] * M01;
     const double X3 = -(rc[0] * M12 - rc[1] * M02 + rc[2] * M01);
     const double xx = X0 * X0 + X1 * X1 + X2 * X2 + X3 * X3;
     const double b2 = m7[6] + (rc[0] * rc[0] + rc[1] * rc[1] + rc[2] * rc[2] + rc[3] * rc[3]);

@@ -22,6 +22,10 @@
 #ifndef TVF_VOTE_RAY_SIGNS
 #define TVF_VOTE_RAY_SIGNS 1
 #endif
+// the accurate route behind the ray test as an out-of-line device function (it runs for 0.1 % of the vote DLTs)
+#ifndef TVF_CHEIR_NOINLINE
+#define TVF_CHEIR_NOINLINE 0
+#endif
 
 namespace tvf {
 
@@ -149,6 +153,39 @@ TVF_HD void triangulate3(const double* Pa, const double* Pb, const double* Pc, c
 // m7 (may be null): dlt_row_minors of (ra, rb).  When the solutions themselves are not asked for, the two depth signs
 // come from the certified ray/plane test (dlt4_depth_signs_ray, ~45 FP64 operations) and only the DLTs it declines
 // (0.1 % of the sweep's, none at n = 10 000) take the accurate route.
+// AFF: m7 comes from dlt_row_minors<true> (view-1 camera K1*[I | 0]).
+#if defined(__CUDACC__) && TVF_CHEIR_NOINLINE
+#define TVF_COLD_DEV __host__ __device__ __noinline__ static
+#else
+#define TVF_COLD_DEV TVF_HD
+#endif
+// the accurate route of one candidate: Householder DLT, the two depth signs (or the NaN flag), optionally the solution
+TVF_COLD_DEV void cheirality_accurate(const double* ra, const double* rb, const double* rc, const double* rd, const double* r3,
+                                      double tz, int q, int* v, int* nanmask, double* dst) {
+    double a[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { a[0][e] = ra[e]; a[1][e] = rb[e]; a[2][e] = rc[e]; a[3][e] = rd[e]; }
+#if TVF_VOTE_FAST_SIGNS && TVF_VOTE_GRAM_SIGNS
+    if (dst == nullptr) {
+        int sx, sz;
+        if (dlt4_depth_signs(a, r3, tz, &sx, &sz)) { v[q] += sx + sz; return; }
+    }
+#endif
+    double X[4];
+    dlt_null<4>(a, X);
+    // X1./X1(4): one reciprocal, same inf/NaN outcomes as the division (x*inf = +-inf, 0*inf = NaN)
+    const double iw = (X[3] != 0.0) ? rcp_(X[3]) : 1.0 / X[3];
+    const double X0 = X[0] * iw, X1 = X[1] * iw, X2 = X[2] * iw, X3 = X[3] * iw;
+    const double z2 = r3[0] * X0 + r3[1] * X1 + r3[2] * X2 + tz * X3;                      // [R t]*X1
+    if (X2 != X2 || z2 != z2) {
+        *nanmask |= (1 << q);
+    } else {
+        v[q] += (int)sign_(X2) + (int)sign_(z2);
+    }
+    if (dst != nullptr) { dst[0] = X[0]; dst[1] = X[1]; dst[2] = X[2]; dst[3] = X[3]; }
+}
+
+template <bool AFF = false>
 TVF_HD void cheirality_point(const double* ra, const double* rb, const double* m7, const double* c, double x2, double y2,
                              int* v, int* nanmask, double* Xa, double* Xb) {
     constexpr int kUnroll = TVF_CHEIR_UNROLL;
@@ -156,35 +193,16 @@ TVF_HD void cheirality_point(const double* ra, const double* rb, const double* m
     for (int q = 0; q < 2; ++q) {
         double P[12], r3[3], tz;
         candidate_camera(c, q == 0 ? 0 : 3, P, r3, &tz);
-        double a[4][4];
-        dlt_rows(P, x2, y2, a[2], a[3]);
+        double rc[4], rd[4];
+        dlt_rows(P, x2, y2, rc, rd);
         double* dst = (q == 0) ? Xa : Xb;
 #if TVF_VOTE_FAST_SIGNS && TVF_VOTE_RAY_SIGNS
-        if (dst == nullptr) {          // only the two depth signs are needed: certified shortcuts, else the accurate route below
+        if (dst == nullptr) {          // only the two depth signs are needed: certified shortcut, else the accurate route
             int sx, sz;
-            if (m7 != nullptr && dlt4_depth_signs_ray(m7, a[2], a[3], r3, tz, &sx, &sz)) { v[q] += sx + sz; continue; }
+            if (m7 != nullptr && dlt4_depth_signs_ray<AFF>(m7, rc, rd, r3, tz, &sx, &sz)) { v[q] += sx + sz; continue; }
         }
 #endif
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { a[0][e] = ra[e]; a[1][e] = rb[e]; }
-#if TVF_VOTE_FAST_SIGNS && TVF_VOTE_GRAM_SIGNS
-        if (dst == nullptr) {
-            int sx, sz;
-            if (dlt4_depth_signs(a, r3, tz, &sx, &sz)) { v[q] += sx + sz; continue; }
-        }
-#endif
-        double X[4];
-        dlt_null<4>(a, X);
-        // X1./X1(4): one reciprocal, same inf/NaN outcomes as the division (x*inf = +-inf, 0*inf = NaN)
-        const double iw = (X[3] != 0.0) ? rcp_(X[3]) : 1.0 / X[3];
-        const double X0 = X[0] * iw, X1 = X[1] * iw, X2 = X[2] * iw, X3 = X[3] * iw;
-        const double z2 = r3[0] * X0 + r3[1] * X1 + r3[2] * X2 + tz * X3;                      // [R t]*X1
-        if (X2 != X2 || z2 != z2) {
-            *nanmask |= (1 << q);
-        } else {
-            v[q] += (int)sign_(X2) + (int)sign_(z2);
-        }
-        if (dst != nullptr) { dst[0] = X[0]; dst[1] = X[1]; dst[2] = X[2]; dst[3] = X[3]; }
+        cheirality_accurate(ra, rb, rc, rd, r3, tz, q, v, nanmask, dst);
     }
 }
 

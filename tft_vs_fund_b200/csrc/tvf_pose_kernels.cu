@@ -123,6 +123,10 @@ candidates_kernel(int mode, const double* __restrict__ model, PoseTailArgs a) {
 }
 
 // ------------------------------------------------------------------------ votes
+// the ray test in its form for a view-1 camera K1*[I | 0] (three cofactors are single products)
+#ifndef TVF_RAY_AFF
+#define TVF_RAY_AFF true
+#endif
 #ifndef TVF_VOTES_MINB
 #define TVF_VOTES_MINB 2
 #endif
@@ -144,9 +148,9 @@ votes_kernel(PoseTailArgs a) {
                 const double2 p1 = __ldg(q), p2 = __ldg(q + 1), p3 = __ldg(q + 2);
                 double ra[4], rb[4], m7[7];
                 dlt_rows(P1, p1.x, p1.y, ra, rb);
-                dlt_row_minors(ra, rb, m7);
-                cheirality_point(ra, rb, m7, cand, p2.x, p2.y, v2, &n2, nullptr, nullptr);
-                cheirality_point(ra, rb, m7, cand + CAND_PAIR, p3.x, p3.y, v3, &n3, nullptr, nullptr);
+                dlt_row_minors<TVF_RAY_AFF>(ra, rb, m7);               // P1 = K1*[I | 0]
+                cheirality_point<TVF_RAY_AFF>(ra, rb, m7, cand, p2.x, p2.y, v2, &n2, nullptr, nullptr);
+                cheirality_point<TVF_RAY_AFF>(ra, rb, m7, cand + CAND_PAIR, p3.x, p3.y, v3, &n3, nullptr, nullptr);
             }
             int vote[8], nan2, nan3;
             expand_votes(v2, n2, vote, &nan2);
@@ -503,14 +507,14 @@ pose_tail_fused_kernel(PoseTailArgs a) {
             p6[0] = q1.x; p6[1] = q1.y; p6[2] = q2.x; p6[3] = q2.y; p6[4] = q3.x; p6[5] = q3.y;
             double ra[4], rb[4], m7[7];
             dlt_rows(P1, p6[0], p6[1], ra, rb);
-            dlt_row_minors(ra, rb, m7);
+            dlt_row_minors<TVF_RAY_AFF>(ra, rb, m7);                   // P1 = K1*[I | 0]
             int v2[2] = {0, 0}, v3[2] = {0, 0}, n2 = 0, n3 = 0;
 #if TVF_TAIL_REUSE_X
-            cheirality_point(ra, rb, m7, cand, p6[2], p6[3], v2, &n2, Xa, Xb);
+            cheirality_point<TVF_RAY_AFF>(ra, rb, m7, cand, p6[2], p6[3], v2, &n2, Xa, Xb);
 #else
-            cheirality_point(ra, rb, m7, cand, p6[2], p6[3], v2, &n2, nullptr, nullptr);
+            cheirality_point<TVF_RAY_AFF>(ra, rb, m7, cand, p6[2], p6[3], v2, &n2, nullptr, nullptr);
 #endif
-            cheirality_point(ra, rb, m7, cand + CAND_PAIR, p6[4], p6[5], v3, &n3, nullptr, nullptr);
+            cheirality_point<TVF_RAY_AFF>(ra, rb, m7, cand + CAND_PAIR, p6[4], p6[5], v3, &n3, nullptr, nullptr);
             int* dst = sv + m.lp * 4;
             if (v2[0]) atomicAdd(dst + 0, v2[0]);
             if (v2[1]) atomicAdd(dst + 1, v2[1]);
