@@ -1,4 +1,4 @@
-cd /root/repo; mkdir -p gpurun_out
+cd "$(dirname "$0")/.."; mkdir -p gpurun_out
 for v in base "$@"; do
   if [ $v = base ]; then unset TVF_LIBPATH; else export TVF_LIBPATH=tools/_build/variants/libtvf_$v.so; fi
   timeout 300 python bench.py --workload large-n --n 10000 --trials 8192 --steps 3 --warmup 1 > gpurun_out/lq_large_$v.json 2> gpurun_out/lq_large_$v.err
