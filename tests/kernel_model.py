@@ -2,7 +2,7 @@
 
 Mirrors, step for step, what the CUDA kernels in tft_vs_fund_b200/csrc do
 (96 Kronecker moments -> 27x27 Gram -> Gauss-Jordan sweep inverse + power iteration ->
-epipoles by one-sided Jacobi -> 15-dim projected Gram -> ... -> QR-based DLT),
+epipoles by QR + inverse iteration (Jacobi fallback) -> 15-dim projected Gram -> ... -> QR-based DLT),
 so the numerical design (tolerances, iteration counts) can be validated
 against the oracle on CPU before any GPU time is spent.
 """
@@ -106,7 +106,37 @@ def jacobi_svd_V(A, sweeps=12):
     return V[:, order], nrm[order], A[:, order]
 
 
+def null3_qr(Mx, max_iter=12):
+    """tvf_math.cuh::null3_qr: Householder QR of the 3x3 + inverse iteration with R (rate (s3/s2)^2); None when it has not
+    converged in max_iter steps or the input is not finite -- null3 then takes the Jacobi route, as the kernels do."""
+    Mx = np.asarray(Mx, dtype=np.float64)
+    if not np.all(np.isfinite(Mx)):
+        return None
+    R = np.linalg.qr(Mx, mode='r')
+    rmax = np.max(np.abs(np.diag(R)))
+    if not rmax > 0.0:
+        return None
+    tiny = 1e-300 + 1e-18 * rmax
+    for k in range(3):
+        if abs(R[k, k]) < tiny:
+            R[k, k] = np.copysign(tiny, R[k, k]) if R[k, k] != 0 else tiny
+    x = np.linalg.solve(R, np.array([0.0, 0.0, 1.0]))
+    x /= np.linalg.norm(x)
+    dprev = 0.0
+    for _ in range(max_iter):
+        z = np.linalg.solve(R, np.linalg.solve(R.T, x))
+        z /= np.linalg.norm(z)
+        d2 = float(np.sum((z - x) ** 2)); x = z
+        if not d2 > 1e-26 or not d2 * d2 > 1e-28 * dprev:
+            return x
+        dprev = d2
+    return None
+
+
 def null3(Mx):
+    v = null3_qr(Mx)
+    if v is not None:
+        return v
     V, _, _ = jacobi_svd_V(Mx)
     return V[:, 2]
 
