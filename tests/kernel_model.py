@@ -248,6 +248,22 @@ def decompose_E(E):
     return R, Rp, U[:, 2].copy()
 
 
+def depth_signs_ray(A, r3, tz):
+    """tvf_math.cuh::dlt4_depth_signs_ray: the two depth signs of the DLT solution of the 4x4 system A from the 4-D cross
+    product Xt of its first three rows (ray of view 1 meets a plane of view 2), certified by
+    sin(angle(Xt, v)) <= eta = |A[3].Xt| |B|_F^2 / (2 |Xt|^2)  (B = A[:3]); None when the certificate declines."""
+    B = A[:3]
+    Xt = np.array([np.linalg.det(B[:, [1, 2, 3]]), -np.linalg.det(B[:, [0, 2, 3]]),
+                   np.linalg.det(B[:, [0, 1, 3]]), -np.linalg.det(B[:, [0, 1, 2]])])
+    xx = Xt @ Xt; b2 = float(np.sum(B * B)); rb2 = abs(A[3] @ Xt) * b2
+    if not rb2 < 0.4 * xx or not xx >= 1e-12 * b2 ** 3:
+        return None
+    q1 = Xt[2] * Xt[3]; q2 = (r3 @ Xt[:3] + tz * Xt[3]) * Xt[3]
+    if not abs(q1) >= 1.0605 * rb2 + 1e-6 * xx or not abs(q2) >= 1.616 * rb2 + 1e-6 * xx:
+        return None
+    return (1 if q1 > 0 else -1), (1 if q2 > 0 else -1)
+
+
 def cheirality(R, Rp, t, P1, K2, x1, x2):
     cands = [(R, t), (R, -t), (Rp, -t), (Rp, t)]
     best = 0; sel = None; votes = []
@@ -255,7 +271,12 @@ def cheirality(R, Rp, t, P1, K2, x1, x2):
         P2 = K2 @ np.column_stack([Rc, tc])
         v = 0
         for n in range(x1.shape[1]):
-            X, _ = dlt_null(dlt_rows([P1, P2], [x1[:, n], x2[:, n]]))
+            A = dlt_rows([P1, P2], [x1[:, n], x2[:, n]])
+            sg = depth_signs_ray(A, Rc[2], tc[2])         # certified shortcut first, as in the kernels
+            if sg is not None:
+                v += sg[0] + sg[1]
+                continue
+            X, _ = dlt_null(A)
             X = X / X[3]
             z2 = Rc[2] @ X[:3] + tc[2]
             v += np.sign(X[2]) + np.sign(z2)
